@@ -1,0 +1,181 @@
+"""Pin the CPU oracle (oracle/sun_oracle.py) against the outputs of the real reference modules
+stored in tests/golden/ by oracle/make_golden.py.  fp32 vs fp32: tolerances only cover summation order."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import sun_oracle as O
+from make_golden import _checksum, sd_checksum  # checksum helpers only; no reference import at test time
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def close(a, b, rtol=2e-4, atol=2e-4):
+    a = torch.as_tensor(np.asarray(a), dtype=torch.float32)
+    b = torch.as_tensor(np.asarray(b), dtype=torch.float32)
+    scale = b.abs().max().item() + 1e-12
+    err = (a - b).abs().max().item()
+    assert err <= atol * max(1.0, scale) + rtol * scale, f"max err {err} (scale {scale})"
+
+
+@pytest.fixture(scope="module")
+def sd_wr():
+    return O.randomize_bn(O.init_meta_baseline_state_dict(12345), seed=7)
+
+
+@pytest.fixture(scope="module")
+def sd_w1():
+    return O.calibrate_bn(O.init_meta_baseline_state_dict(12345))
+
+
+def test_state_dict_layout():
+    sd = O.init_meta_baseline_state_dict(12345)
+    assert len(sd) == 149
+    n_param = sum(v.numel() for k, v in sd.items()
+                  if not (k.endswith("running_mean") or k.endswith("running_var") or k.endswith("num_batches_tracked")))
+    assert n_param == 12_531_393          # SURVEY.md 8b (incl. temp)
+    assert O.head_dim(256) == 42 and O.head_dim(512) == 85
+
+
+def test_encoder_layer_boundaries(golden_dir, sd_wr):
+    g = load(golden_dir, "encoder_eval_wr.npz")
+    x = O.make_episode_images(101, 2, 2)
+    np.testing.assert_allclose(_checksum(x), g["x_checksum"], rtol=1e-9)
+    np.testing.assert_allclose(sd_checksum(sd_wr), g["sd_checksum"], rtol=1e-9)
+    taps = {}
+    with torch.no_grad():
+        dense, pooled = O.encoder_forward(sd_wr, x, "encoder.", taps=taps)
+    close(pooled, g["pooled"])
+    close(dense, g["dense"])
+    sub = {k[len("encoder."):]: v for k, v in sd_wr.items() if k.startswith("encoder.")}
+    for name in [f"stage1.{i}" for i in range(4)] + [f"stage2.{i}" for i in range(2)] + [f"stage3.{i}" for i in range(3)]:
+        close(taps[name][0], g["tap0." + name])
+    close(taps["stem"][0] - sub["pos_embed1"][0], g["tap0.stem_nopos"], atol=1e-3)
+    close(taps["patch_embed2"][0] - sub["pos_embed2"][0], g["tap0.patch_embed2_nopos"], atol=1e-3)
+    close(taps["patch_embed3"][0] - sub["pos_embed3"][0], g["tap0.patch_embed3_nopos"], atol=1e-3)
+
+
+def test_small_episode(golden_dir, sd_wr):
+    g = load(golden_dir, "episode_small_wr.npz")
+    data = O.make_episode_images(202, 5, 4)
+    np.testing.assert_allclose(_checksum(data), g["x_checksum"], rtol=1e-9)
+    xs, xq = O.split_shot_query(data, 5, 1, 3)
+    with torch.no_grad():
+        logits = O.meta_baseline_forward(sd_wr, xs, xq)
+    close(logits, g["logits"], atol=1e-4)
+    label = O.make_nk_label(5, 3)
+    assert np.array_equal(label.numpy(), g["label"])
+    assert abs(O.cross_entropy(logits.view(-1, 5), label).item() - float(g["loss"])) < 1e-4
+    assert O.compute_acc(logits.view(-1, 5), label) == pytest.approx(float(g["acc"]))
+
+
+def test_full_episode_w1_argmax(golden_dir, sd_w1):
+    g = load(golden_dir, "episode_full_w1.npz")
+    np.testing.assert_allclose(sd_checksum(sd_w1), g["sd_checksum"], rtol=1e-6)
+    data = O.make_episode_images(300, 5, 16)
+    np.testing.assert_allclose(_checksum(data), g["x_checksum"][0], rtol=1e-9)
+    xs, xq = O.split_shot_query(data, 5, 1, 15)
+    with torch.no_grad():
+        logits = O.meta_baseline_forward(sd_w1, xs, xq)[0]
+    close(logits, g["logits"][0], atol=1e-3)
+    assert np.array_equal(logits.argmax(-1).numpy(), g["logits"][0].argmax(-1))
+
+
+def test_index_utils_bit_exact(golden_dir):
+    g = load(golden_dir, "index_utils.npz")
+    for (way, shot, query, ep) in [(5, 1, 15, 1), (5, 5, 15, 2), (10, 1, 5, 8), (3, 2, 1, 4)]:
+        n = ep * way * (shot + query)
+        ids = torch.arange(n).view(n, 1, 1, 1).float()
+        s, q = O.split_shot_query(ids, way, shot, query, ep)
+        key = f"{way}_{shot}_{query}_{ep}"
+        assert np.array_equal(s.flatten().long().numpy(), g["shot_" + key])
+        assert np.array_equal(q.flatten().long().numpy(), g["query_" + key])
+        lab = O.make_nk_label(way, query, ep)
+        assert lab.dtype == torch.int64 and np.array_equal(lab.numpy(), g["label_" + key])
+    gl = torch.Generator().manual_seed(5)
+    f3, p3 = torch.randn(2, 7, 16, generator=gl), torch.randn(2, 3, 16, generator=gl)
+    for metric in ("dot", "cos", "sqr"):
+        close(O.compute_logits(f3, p3, metric, 2.5), g["logits3_" + metric], atol=1e-5)
+        close(O.compute_logits(f3[0], p3[0], metric, 2.5), g["logits2_" + metric], atol=1e-5)
+
+
+def draw_dp_masks(seed, rate, batch):
+    """Replays the reference's DropPath draws (visformer.py:89-97) in forward order under `seed`."""
+    rates = O.drop_path_rates(rate)
+    torch.manual_seed(seed)
+    names = [f"stage1.{i}" for i in range(4)] + [f"stage2.{i}" for i in range(2)] + [f"stage3.{i}" for i in range(3)]
+    masks = {}
+    for bi, name in enumerate(names):
+        if rates[bi] <= 0:
+            continue
+        n = 1 if name.startswith("stage1") else 2
+        masks[name] = [torch.floor((1 - rates[bi]) + torch.rand(batch, 1, 1, 1)) for _ in range(n)]
+    return masks
+
+
+@pytest.mark.parametrize("tag,rate", [("dp0", 0.0), ("dp05", 0.5)])
+def test_train_step(golden_dir, sd_w1, tag, rate):
+    g = load(golden_dir, f"train_step_{tag}.npz")
+    way, shot, query, ep = 3, 1, 2, 2
+    data = O.make_episode_images(500, ep * way, shot + query)
+    np.testing.assert_allclose(_checksum(data), g["x_checksum"], rtol=1e-9)
+    xs, xq = O.split_shot_query(data, way, shot, query, ep)
+    label = O.make_nk_label(way, query, ep)
+    params = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v)
+              for k, v in sd_w1.items()}
+    st = O.BNState()
+    masks = draw_dp_masks(77, rate, data.shape[0]) if rate > 0 else None
+    logits = O.meta_baseline_forward(params, xs, xq, training=True, bn_state=st, drop_path_rate=rate,
+                                     dp_masks=masks).view(-1, way)
+    loss = O.cross_entropy(logits, label)
+    loss.backward()
+    close(logits.detach(), g["logits"], atol=2e-3)
+    assert abs(loss.item() - float(g["loss"])) < 2e-3 * max(1.0, abs(float(g["loss"])))
+    zero_grad = {"encoder.patch_embed2.proj.bias", "encoder.patch_embed2.norm.bn.bias",
+                 "encoder.patch_embed3.proj.bias", "encoder.patch_embed3.norm.bn.bias"}
+    checked = 0
+    for k in g.files:
+        if k.startswith("grad."):
+            name = k[5:]
+            gr = params[name].grad
+            if name in zero_grad:          # analytically zero under batch-stat BN: absolute tolerance only
+                assert gr.abs().max().item() < 1e-5
+                continue
+            ref = torch.as_tensor(g[k])
+            rel = (gr - ref).norm().item() / (ref.norm().item() + 1e-12)
+            assert rel < 2e-2, (name, rel)
+            checked += 1
+        elif k.startswith("bn."):
+            name = k[3:]
+            close(st.updates[name[len("encoder."):]], g[k], atol=1e-4)
+    assert checked > 40
+
+
+def test_sun_head(golden_dir):
+    g = load(golden_dir, "sun_head.npz")
+    sd = O.randomize_bn(O.init_token_label_state_dict(12345), seed=7)
+    np.testing.assert_allclose(sd_checksum(sd), g["sd_checksum"], rtol=1e-9)
+    x = O.make_episode_images(101, 2, 2)
+    with torch.no_grad():
+        yt_s, y_s, tok = O.token_label_forward(sd, x)
+        yt_t, _, _ = O.token_label_forward(sd, x, is_teacher=True)
+    assert tuple(yt_s.stride()) == tuple(g["y_token_student_stride"])      # NCHW view of NHWC memory
+    close(yt_s, g["y_token_student"])
+    close(y_s, g["y_student"])
+    close(tok, g["token_student"])
+    close(yt_t, g["y_token_teacher"])
+    gl = torch.Generator().manual_seed(11)
+    t_logits = torch.randn(8, 5, 5, 64, generator=gl).permute(0, 3, 1, 2)
+    soft = O.generate_softlabel(t_logits, k=5, bp=10)
+    assert np.array_equal(soft.numpy(), g["soft_label"])                    # bit-exact selection + constants
+    bg = soft[:, 1] > 0.5
+    assert int((soft.sum(1) < 1.5).sum()) == 8 * 10 and bool(bg[soft.sum(1) < 1.5].all())   # bg rows hot at col 1
+    s_logits = torch.randn(8, 5, 5, 65, generator=gl).permute(0, 3, 1, 2)
+    ce = O.soft_target_cross_entropy(s_logits.permute(0, 2, 3, 1).reshape(-1, 65), soft)
+    assert abs(ce.item() - float(g["soft_ce"])) < 1e-4
+    total = O.sun_loss(yt_s, y_s, torch.tensor([3, 3, 40, 40]), torch.as_tensor(g["soft_label_e2e"]))
+    assert abs(total.item() - float(g["sun_loss"])) < 1e-3 * float(g["sun_loss"])
