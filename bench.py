@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""Benchmark of the SUN episodic Visformer hot path (BASELINE.json metric: 5-way episodes/sec, eval).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]           product arm (native sm_100a kernels)
+  python bench.py --impl reference [...]                        reference arm: the CPU oracle port on host cores
+
+A "step" = one pass of the eval hot path over one batch of synthetic episodes per GPU:
+EPISODES_PER_GPU (75 = 600 episodes / 8 GPUs, BASELINE.json configs[1]) 5-way 5-shot 15-query episodes of
+100 images 3x80x80, through models.make('meta-baseline', encoder='visformer_micro_80') in eval mode.
+Episodes are independent: ranks shard them with no data-path collective ("scaling": "weak").
+Prints ONE JSON line on rank 0 (contract in the task description).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "few-shot-vit_b200"), os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+WAY, SHOT, QUERY = 5, 5, 15
+IMGS_PER_EPISODE = WAY * (SHOT + QUERY)           # 100
+EPISODES_PER_GPU = 75                             # 600 / 8
+CHUNK = 25                                        # episodes per forward call (2500 images)
+FLOP_PER_IMAGE = 2_030_615_400
+FLOP_PER_EPISODE = IMGS_PER_EPISODE * FLOP_PER_IMAGE + 2 * (WAY * QUERY) * WAY * 512
+LAUNCHES_PER_FORWARD = 45                         # 44 encoder kernels (csrc/api.cu schedule) + 1 episode-head kernel
+METRIC = "5-way 5-shot Visformer episodic eval throughput"
+UNIT = "episodes/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return p["bf16_tflops"], p["bf16_tflops_sustained"], p["hbm_gbs"], "measured"
+    return 1590.0, 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=5)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def device_episodes(n_episodes, seed, device):
+    """Class-structured synthetic episodes generated on the device: x = p_c + 0.5 n  (miniImageNet-shaped)."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    protos = torch.randn(n_episodes, WAY, 1, 3, 80, 80, generator=g, device=device)
+    noise = torch.randn(n_episodes, WAY, SHOT + QUERY, 3, 80, 80, generator=g, device=device)
+    return (protos + 0.5 * noise).reshape(n_episodes * IMGS_PER_EPISODE, 3, 80, 80)
+
+
+def cpu_oracle_eps_per_s(min_seconds, max_episodes):
+    """The reference algorithm (oracle port, torch fp32) on the host cores: episodes/s on a bounded sample."""
+    import torch
+    import sun_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    sd = O.calibrate_bn(O.init_meta_baseline_state_dict(12345))
+    data = O.make_episode_images(1, WAY, SHOT + QUERY)
+    xs, xq = O.split_shot_query(data, WAY, SHOT, QUERY)
+    with torch.no_grad():
+        O.meta_baseline_forward(sd, xs, xq)            # warm-up
+        n, t0 = 0, time.perf_counter()
+        while n < max_episodes and (n == 0 or time.perf_counter() - t0 < min_seconds):
+            O.meta_baseline_forward(sd, xs, xq)
+            n += 1
+        dt = time.perf_counter() - t0
+    return n / dt, n, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    import sun_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    sd = O.calibrate_bn(O.init_meta_baseline_state_dict(12345))
+    data = O.make_episode_images(1, WAY, SHOT + QUERY)
+    xs, xq = O.split_shot_query(data, WAY, SHOT, QUERY)
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 1)):
+            O.meta_baseline_forward(sd, xs, xq)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            O.meta_baseline_forward(sd, xs, xq)
+        dt = time.perf_counter() - t0
+    v = args.steps / dt
+    sample = f"{args.steps} steps x 1 episode (100 images) of the same 5-way 5-shot workload, fp32, torch CPU"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "5-way 5-shot 15-query visformer_micro_80 meta-baseline eval, 1 episode per step (CPU sample)"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def time_dominant_kernel(model_state, device, peaks_tf):
+    """Roofline of the dominant launch: stem conv3 (3x3, 128->128 on 40x40; 23 % of the encoder FLOPs) through
+    sunb_gemm at the bench's chunk size, CUDA events on the launching stream, inputs larger than L2."""
+    import ctypes as C
+    import torch
+    from sunb200 import native as N, packing
+    B = CHUNK * IMGS_PER_EPISODE
+    P = packing.pack_encoder({k[len("encoder."):]: v for k, v in model_state.items() if k.startswith("encoder.")})
+    a2 = torch.randn(B, 40, 40, 128, device=device).bfloat16()          # 1 GB, far larger than the 126 MB L2
+    idn = torch.randn(B * 1600, 128, device=device).bfloat16()
+    out = torch.empty(B * 1600, 128, device=device, dtype=torch.bfloat16)
+    d = N.GemmDesc()
+    d.M, d.N, d.K, d.taps, d.groups = B * 1600, 128, 128, 9, 1
+    d.a_mode, d.H, d.W, d.bw, d.bh = 1, 40, 40, 8, 8
+    d.A, d.lda, d.Wt, d.ldw = a2.data_ptr(), 128, P["stem_w3"].data_ptr(), 128
+    d.bias, d.bias_mod, d.act = P["stem_b3"].data_ptr(), 1, 1
+    d.resid, d.ldr, d.rows_per_img = idn.data_ptr(), 128, 1
+    d.out, d.ldc = out.data_ptr(), 128
+    st = N.current_stream()
+    for _ in range(3):
+        N.check(N.lib().sunb_gemm(C.byref(d), 0, st), "sunb_gemm")
+    reps = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        N.check(N.lib().sunb_gemm(C.byref(d), 0, st), "sunb_gemm")
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    flops = 2.0 * B * 1600 * 128 * 128 * 9
+    achieved = flops / (ms * 1e-3) / 1e12
+    return {"bound": "tensor", "kernel": "gemm_tc_kernel<128> (stem conv3 implicit GEMM, M=%d N=128 K=9x128)" % (B * 1600),
+            "achieved": achieved, "peak": peaks_tf, "unit": "TFLOP/s", "frac": achieved / peaks_tf, "traffic": None,
+            "ms_per_launch": ms, "flops_per_launch": flops}
+
+
+def run_product(args):
+    import torch
+    import torch.distributed as dist
+    import models
+    import utils.few_shot as fs
+    import sun_oracle as O
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py product arm needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    burst_tf, sustained_tf, hbm_gbs, peak_src = load_peaks()
+
+    sd = O.calibrate_bn(O.init_meta_baseline_state_dict(12345))        # random-init, BN-calibrated (W1)
+    model = models.make("meta-baseline", encoder="visformer_micro_80", encoder_args={})
+    model.load_state_dict(sd)
+    model = model.to(device).eval()
+
+    n_chunks = EPISODES_PER_GPU // CHUNK
+    # device-resident inputs for `value` (576 MB per step >> 126 MB L2, no flush needed)
+    dev_chunks = [device_episodes(CHUNK, 1000 * rank + c, device) for c in range(n_chunks)]
+    # pinned host inputs for `e2e`
+    host_chunks = [c.cpu().pin_memory() for c in dev_chunks]
+    label = fs.make_nk_label(WAY, QUERY, CHUNK).to(device)
+
+    def step_device():
+        outs = []
+        for c in range(n_chunks):
+            xs, xq = fs.split_shot_query(dev_chunks[c], WAY, SHOT, QUERY, ep_per_batch=CHUNK)
+            outs.append(model(xs, xq))
+        return outs
+
+    stage = [torch.empty_like(dev_chunks[0]) for _ in range(2)]
+    host_out = torch.empty(n_chunks, CHUNK, WAY * QUERY, WAY, dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        for c in range(n_chunks):
+            buf = stage[c % 2]
+            buf.copy_(host_chunks[c], non_blocking=True)                 # H2D inside the timed region
+            xs, xq = fs.split_shot_query(buf, WAY, SHOT, QUERY, ep_per_batch=CHUNK)
+            host_out[c].copy_(model(xs, xq), non_blocking=True)          # D2H of the step's result (logits)
+        torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            outs = step_device()
+        with ClockSampler(local) as clk:
+            ms_total = timed(step_device, args.steps)
+        clocks = clk.summary()
+        for _ in range(2):
+            step_e2e()
+        ms_e2e = timed(step_e2e, args.steps)
+        # sanity: accuracy of the last step's logits on the class-structured episodes (not part of the timing)
+        acc = (outs[0].reshape(-1, WAY).argmax(1) == label).float().mean().item()
+
+    episodes = world * EPISODES_PER_GPU * args.steps
+    value = episodes / (ms_total * 1e-3)
+    e2e_value = episodes / (ms_e2e * 1e-3)
+    h2d = EPISODES_PER_GPU * IMGS_PER_EPISODE * 3 * 80 * 80 * 4
+    d2h = EPISODES_PER_GPU * WAY * QUERY * WAY * 4
+
+    if rank == 0:
+        roof = time_dominant_kernel(sd, device, burst_tf)
+        roof["peak_source"] = f"{peak_src} burst bf16 (MEASURED_PEAKS.json)"
+        cpu_v, cpu_n, cpu_dt = cpu_oracle_eps_per_s(min_seconds=10.0, max_episodes=20)
+        path_tf = value / world * FLOP_PER_EPISODE / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "5-way 5-shot 15-query visformer_micro_80 meta-baseline eval (BASELINE.json configs[1]), "
+                                   f"{EPISODES_PER_GPU} episodes/GPU/step in chunks of {CHUNK}, random-init BN-calibrated weights",
+                       "episodes_per_gpu_per_step": EPISODES_PER_GPU, "images_per_episode": IMGS_PER_EPISODE,
+                       "l2_policy": "inputs larger than L2 (576 MB of fp32 images per step)", "parallelism": f"episode-sharded x{world}"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": LAUNCHES_PER_FORWARD * n_chunks * args.steps,
+            "clocks": clocks,
+            "roofline": roof,
+            "path_roofline": {"achieved": path_tf, "peak": sustained_tf, "unit": "TFLOP/s", "frac": path_tf / sustained_tf,
+                              "note": "whole eval step per GPU: 203.06 GFLOP/episode algorithmic vs sustained bf16 peak"},
+            "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                             "sample": f"{cpu_n} episodes (100 images each) of the same workload in {cpu_dt:.1f} s, oracle port, torch fp32"},
+            "sanity_acc": acc,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="sunb200", choices=["sunb200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_product(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,165 @@
+// Shared declarations for the sunb200 kernels (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing: no C++ exceptions cross the C ABI; every entry point returns an int code and
+// leaves a message for sunb_last_error().
+// ---------------------------------------------------------------------------------------------
+enum SunbStatus { SUNB_OK = 0, SUNB_ERR_ARG = -1, SUNB_ERR_CUDA = -2, SUNB_ERR_WORKSPACE = -3, SUNB_ERR_DRIVER = -4 };
+
+void sunb_set_error(const char* fmt, ...);
+
+#define SUNB_CHECK_CUDA(expr)                                                                  \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            sunb_set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #expr,               \
+                           cudaGetErrorString(_e));                                            \
+            return SUNB_ERR_CUDA;                                                              \
+        }                                                                                      \
+    } while (0)
+
+#define SUNB_REQUIRE(cond, ...)                                                                \
+    do {                                                                                       \
+        if (!(cond)) {                                                                         \
+            sunb_set_error(__VA_ARGS__);                                                       \
+            return SUNB_ERR_ARG;                                                               \
+        }                                                                                      \
+    } while (0)
+
+#define SUNB_TRY(expr)                                                                         \
+    do {                                                                                       \
+        int _s = (expr);                                                                       \
+        if (_s != SUNB_OK) return _s;                                                          \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// GEMM / implicit-GEMM problem description shared by the tcgen05 kernel and the SIMT checker kernel
+//   C[m, g*c_goff + n] = epilogue( sum_{tap, k} A_tap[m, g*a_goff + k] * Wt[(g*taps + tap)*N + n, k] )
+// a_mode 0: A_tap[m,:] = A[m,:]                        (1x1 conv / linear; taps == 1)
+// a_mode 1: 3x3 conv, pad 1, stride 1 over an NHWC image [B,H,W,C]; A_tap[m,:] = pixel shifted by
+//           (tap/3-1, tap%3-1), zero outside the image.  Output tiles are built from (bw x bh)-pixel
+//           sub-boxes so that every 128-row tile is a set of complete spatial boxes.
+// ---------------------------------------------------------------------------------------------
+enum { ACT_NONE = 0, ACT_LRELU = 1, ACT_GELU = 2 };
+enum { MAP_IDENT = 0, MAP_S2D = 1 };   // output row mapping: identity, or 2x2 space-to-depth of an oH x oW raster
+
+struct GemmParams {
+    int M, N, K;          // rows, output columns per group, reduction length per tap (real, un-padded)
+    int taps, groups;
+    int a_goff, c_goff;
+    int a_mode, H, W, bw, bh;
+    // operands (raw pointers: SIMT kernel + tensor-map creation)
+    const bf16* A; int lda;          // 2-D mode: row stride in elements.  conv mode: lda = channels per pixel
+    const bf16* Wt; int ldw;         // weights, K-major rows of ldw elements
+    // epilogue
+    const float* bias; int bias_mod;      // bias[(m % bias_mod) * bias_ld + col]; bias_mod == 1 -> plain per-column bias
+    int bias_ld;
+    int act;
+    const bf16* resid; int ldr;           // added before the activation; indexed with the raster row m
+    const float* row_scale; int rows_per_img;   // optional per-image scale of the accumulator (DropPath)
+    bf16* out; int ldc;                   // bf16 output (nullable)
+    float* out_f32; int ldc_f32;          // fp32 output (nullable)
+    int out_map, oH, oW;
+};
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+    if (act == ACT_LRELU) return v > 0.f ? v : 0.1f * v;
+    if (act == ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+    return v;
+}
+
+// raster row of tile-row r (conv mode tiles are made of (bw x bh) sub-boxes)
+__device__ __forceinline__ int conv_tile_row_to_pixel(const GemmParams& p, int tile, int r) {
+    const int box = p.bw * p.bh;
+    const int nsub = 128 / box;
+    const int tiles_x = p.W / p.bw, spi = tiles_x * (p.H / p.bh);
+    const int st = tile * nsub + r / box;
+    const int rr = r % box;
+    const int img = st / spi, rem = st % spi;
+    const int y = (rem / tiles_x) * p.bh + rr / p.bw;
+    const int x = (rem % tiles_x) * p.bw + rr % p.bw;
+    return (img * p.H + y) * p.W + x;
+}
+
+__device__ __forceinline__ int map_out_row(const GemmParams& p, int m) {
+    if (p.out_map == MAP_S2D) {
+        const int hw = p.oH * p.oW;
+        const int img = m / hw, rem = m % hw;
+        const int y = rem / p.oW, x = rem % p.oW;
+        return ((img * (p.oH / 2) + y / 2) * (p.oW / 2) + x / 2) * 4 + (y & 1) * 2 + (x & 1);
+    }
+    return m;
+}
+
+// Epilogue for NC consecutive columns [col, col+NC) of raster row m of group g.  v = fp32 accumulators.
+template <int NC>
+__device__ __forceinline__ void epilogue_row(const GemmParams& p, int g, int m, int col, float* v) {
+    if (m >= p.M) return;
+    const int ncol = min(NC, p.N - col);
+    if (ncol <= 0) return;
+    const int gcol = g * p.c_goff + col;
+    const float rs = p.row_scale ? p.row_scale[m / p.rows_per_img] : 1.f;
+    const float* bias = p.bias ? p.bias + (size_t)(m % p.bias_mod) * p.bias_ld + gcol : nullptr;
+    const bf16* res = p.resid ? p.resid + (size_t)m * p.ldr + gcol : nullptr;
+    const bool full = (ncol == NC);
+    if (res) {
+        if (full && (NC % 8 == 0) && ((((size_t)res) & 15) == 0)) {
+#pragma unroll
+            for (int i = 0; i < NC; i += 8) {
+                uint4 u = *reinterpret_cast<const uint4*>(res + i);
+                const bf16* h = reinterpret_cast<const bf16*>(&u);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[i + j] = v[i + j] * rs + __bfloat162float(h[j]);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NC; ++i)
+                if (i < ncol) v[i] = v[i] * rs + __bfloat162float(res[i]);
+        }
+    } else if (p.row_scale) {
+#pragma unroll
+        for (int i = 0; i < NC; ++i) v[i] *= rs;
+    }
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+        float b = (bias && i < ncol) ? bias[i] : 0.f;
+        v[i] = act_apply(v[i] + b, p.act);
+    }
+    const int orow = map_out_row(p, m);
+    if (p.out) {
+        bf16* o = p.out + (size_t)orow * p.ldc + gcol;
+        if (full && (NC % 8 == 0) && ((((size_t)o) & 15) == 0)) {
+#pragma unroll
+            for (int i = 0; i < NC; i += 8) {
+                uint4 u;
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[i + 2 * j], v[i + 2 * j + 1]);
+                *reinterpret_cast<uint4*>(o + i) = u;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NC; ++i)
+                if (i < ncol) o[i] = __float2bfloat16(v[i]);
+        }
+    }
+    if (p.out_f32) {
+        float* o = p.out_f32 + (size_t)orow * p.ldc_f32 + gcol;
+#pragma unroll
+        for (int i = 0; i < NC; ++i)
+            if (i < ncol) o[i] = v[i];
+    }
+}
+
+// launchers (gemm_tc.cu / gemm_simt.cu)
+int sunb_launch_gemm_tc(const GemmParams& p, cudaStream_t stream);
+int sunb_launch_gemm_simt(const GemmParams& p, cudaStream_t stream);
+int sunb_launch_gemm(const GemmParams& p, cudaStream_t stream);   // dispatch (tcgen05 unless SUNB_GEMM=simt)

@@ -1,0 +1,155 @@
+"""Visformer encoder shim: the reference's module tree (identical state_dict names and shapes) whose
+forward runs on the native sm_100a kernels through the C ABI (sunb_encoder_forward).
+
+Reference: test_phase/models/visformer.py:291-462 (class), :482-487 (factory 'visformer_micro_80');
+output variants: pooled only (test_phase :462), (dense, pooled) (sun_meta_training/models/visformer.py:464),
+dense only (meta_tuning_sun_d/Models/models/visformer.py:461).
+
+The sub-modules below are parameter containers (they keep `.train()/.eval()`, `freeze_bn`, optimizers,
+`state_dict()/load_state_dict()` and DataParallel replication working); they never execute a torch forward.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from .models import register
+from sunb200.engine import EncoderEngine
+
+IMG, STEM_CH, EMBED, DEPTH, HEADS, GROUPS = 80, 64, 256, (4, 2, 3), 6, 8
+
+
+class _Holder(nn.Module):
+    def forward(self, *a, **k):      # pragma: no cover - guard against accidental eager execution
+        raise RuntimeError("sunb200 parameter container: the encoder forward runs in the native kernels")
+
+
+def _conv(cin, cout, k, stride=1, padding=0, groups=1, bias=False):
+    return nn.Conv2d(cin, cout, k, stride=stride, padding=padding, groups=groups, bias=bias)
+
+
+class BatchNorm(_Holder):
+    def __init__(self, dim):
+        super().__init__()
+        self.bn = nn.BatchNorm2d(dim, eps=1e-5, momentum=0.1, track_running_stats=True)
+
+
+class ConvBlock(_Holder):
+    """Stem (visformer.py:202-239)."""
+
+    def __init__(self, cin, hidden, planes):
+        super().__init__()
+        self.conv1 = _conv(cin, hidden, 3, stride=2, padding=1)
+        self.bn1 = nn.BatchNorm2d(hidden)
+        self.conv2 = _conv(hidden, planes, 3, padding=1)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.conv3 = _conv(planes, planes, 3, padding=1)
+        self.bn3 = nn.BatchNorm2d(planes)
+        self.downsample = nn.Sequential(_conv(cin, planes, 3, stride=2, padding=1), nn.BatchNorm2d(planes))
+
+
+class Mlp(_Holder):
+    def __init__(self, dim, hidden, spatial_conv):
+        super().__init__()
+        if spatial_conv:
+            hidden = dim * 2                      # visformer.py:136-141 with group >= 2
+        self.conv1 = _conv(dim, hidden, 1)
+        if spatial_conv:
+            self.conv2 = _conv(hidden, hidden, 3, padding=1, groups=GROUPS)
+        self.conv3 = _conv(hidden, dim, 1)
+
+
+class Attention(_Holder):
+    def __init__(self, dim, ratio=1.0):
+        super().__init__()
+        self.head_dim = round(dim // HEADS * ratio)
+        self.qkv = _conv(dim, self.head_dim * HEADS * 3, 1)
+        self.proj = _conv(self.head_dim * HEADS, dim, 1)
+
+
+class Block(_Holder):
+    def __init__(self, dim, attn, spatial_conv, drop_path):
+        super().__init__()
+        self.drop_prob = float(drop_path)
+        if attn:
+            self.norm1 = BatchNorm(dim)
+            self.attn = Attention(dim)
+        self.norm2 = BatchNorm(dim)
+        self.mlp = Mlp(dim, dim * 4, spatial_conv)
+
+
+class PatchEmbed(_Holder):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.proj = nn.Conv2d(cin, cout, kernel_size=2, stride=2)
+        self.norm = BatchNorm(cout)
+
+
+class Visformer(nn.Module):
+    """'visformer_micro_80' with output selection: output='pooled' | 'both' | 'dense'."""
+
+    def __init__(self, drop_path_rate=0.0, output="pooled"):
+        super().__init__()
+        assert output in ("pooled", "both", "dense")
+        self.output = output
+        self.out_dim = EMBED * 2
+        self.drop_path_rate = float(drop_path_rate)
+        dpr = [x.item() for x in torch.linspace(0, drop_path_rate, sum(DEPTH))]
+        d1, d2, d3 = EMBED // 2, EMBED, EMBED * 2
+        self.pos_embed1 = nn.Parameter(torch.zeros(1, d1, 20, 20))
+        self.pos_embed2 = nn.Parameter(torch.zeros(1, d2, 10, 10))
+        self.pos_embed3 = nn.Parameter(torch.zeros(1, d3, 5, 5))
+        self.stem = ConvBlock(3, STEM_CH, d1)
+        self.stage1 = nn.ModuleList([Block(d1, False, True, dpr[i]) for i in range(DEPTH[0])])
+        self.patch_embed2 = PatchEmbed(d1, d2)
+        self.stage2 = nn.ModuleList([Block(d2, True, False, dpr[DEPTH[0] + i]) for i in range(DEPTH[1])])
+        self.patch_embed3 = PatchEmbed(d2, d3)
+        self.stage3 = nn.ModuleList([Block(d3, True, False, dpr[DEPTH[0] + DEPTH[1] + i]) for i in range(DEPTH[2])])
+        self.norm = BatchNorm(d3)
+        self._reset_parameters()
+        self._engine = EncoderEngine()
+
+    def _reset_parameters(self):
+        """Reference init distributions (visformer.py:398-422, conv_init=True)."""
+        for p in (self.pos_embed1, self.pos_embed2, self.pos_embed3):
+            nn.init.trunc_normal_(p, std=0.02, a=-2.0, b=2.0)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.ones_(m.weight)
+                nn.init.zeros_(m.bias)
+
+    def _bn_in_eval(self):
+        return all(not m.training for m in self.modules() if isinstance(m, nn.BatchNorm2d))
+
+    def forward(self, x, taps=None):
+        if not self._bn_in_eval() or (self.training and self.drop_path_rate > 0):
+            raise NotImplementedError(
+                "sunb200: the train-mode encoder path (batch-statistics BatchNorm, DropPath, backward) is not built "
+                "yet; call .eval() for episodic evaluation.  There is deliberately no PyTorch fallback.")
+        state = dict(self.state_dict(keep_vars=True))
+        out = self._engine.forward(state, x, want_dense=self.output != "pooled", taps=taps)
+        pooled = out["pooled"]
+        if self.output == "pooled":
+            return pooled
+        dense = out["dense"].permute(0, 3, 1, 2)       # NCHW view of NHWC memory (token_label.py:50 permutes it back)
+        return (dense, pooled) if self.output == "both" else dense
+
+
+@register("visformer_micro_80")
+def visformer_small_80(**kwargs):
+    return Visformer(**kwargs)
+
+
+@register("visformer")          # north_star spelling; SUN-D's --backbone value
+def visformer(**kwargs):
+    return Visformer(**kwargs)
+
+
+@register("visformer_micro_80_dense")     # (dense, pooled) variant used by sun_meta_training
+def visformer_small_80_dense(**kwargs):
+    kwargs.setdefault("output", "both")
+    return Visformer(**kwargs)

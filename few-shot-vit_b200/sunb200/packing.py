@@ -1,0 +1,202 @@
+"""Weight packing for the eval-mode encoder: BatchNorm folding, layout permutation, bf16 conversion.
+
+Pure torch tensor algebra (device agnostic), so the folding / layout logic is unit-tested on the CPU against
+the oracle (`emulate_forward`) before any kernel runs.  Layouts match include/sunb200.h (SunbEncoderWeights).
+
+Folding rules:
+  norm -> 1x1 conv (blocks):  conv(BN(x)) = (W diag(s)) x + W t         s = gamma/sqrt(var+eps), t = beta - mean*s
+  conv -> BN (stem, PatchEmbed): BN(conv(x)+b) = diag(s) W x + (s (b - mean) + beta)
+Reference: test_phase/models/visformer.py:118-124 (BatchNorm), :254-262 (Block), :209-216 (stem), :276-287 (PatchEmbed).
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+import torch
+import torch.nn.functional as F
+
+HEADS = 6
+BN_EPS = 1e-5
+DEPTH = (4, 2, 3)
+
+
+def bn_affine(sd: Dict[str, torch.Tensor], p: str):
+    """Eval-mode BatchNorm as y = x*s + t."""
+    s = sd[p + ".weight"].float() / torch.sqrt(sd[p + ".running_var"].float() + BN_EPS)
+    t = sd[p + ".bias"].float() - sd[p + ".running_mean"].float() * s
+    return s, t
+
+
+def _conv3x3_taps(w: torch.Tensor) -> torch.Tensor:
+    """[N, C, 3, 3] -> [9, N, C] with tap = ky*3 + kx."""
+    return w.permute(2, 3, 0, 1).reshape(9, w.shape[0], w.shape[1]).contiguous()
+
+
+def _grouped_pairs(w: torch.Tensor, groups: int = 8) -> torch.Tensor:
+    """Grouped 3x3 weight [256, 32, 3, 3] (8 groups) -> [4 pairs][9 taps][64 n][64 k] block-diagonal."""
+    n_out, cpg = w.shape[0], w.shape[1]
+    opg = n_out // groups
+    pairs = groups // 2
+    out = torch.zeros(pairs, 9, 2 * opg, 2 * cpg, dtype=w.dtype, device=w.device)
+    taps = w.permute(2, 3, 0, 1).reshape(9, n_out, cpg)
+    for g in range(groups):
+        p, h = g // 2, g % 2
+        out[p, :, h * opg:(h + 1) * opg, h * cpg:(h + 1) * cpg] = taps[:, g * opg:(g + 1) * opg, :]
+    return out.contiguous()
+
+
+def _pad_cols(w: torch.Tensor, mult: int = 8) -> torch.Tensor:
+    k = w.shape[1]
+    kp = (k + mult - 1) // mult * mult
+    return w if kp == k else F.pad(w, (0, kp - k))
+
+
+def pack_encoder(sd: Dict[str, torch.Tensor], prefix: str = "", wdtype: torch.dtype = torch.bfloat16) -> Dict[str, torch.Tensor]:
+    """state_dict (reference names) -> dict of packed tensors keyed like SunbEncoderWeights fields.
+    `wdtype=torch.float32` keeps GEMM weights in fp32 (CPU emulation tests)."""
+    g = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)} if prefix else sd
+    P: Dict[str, torch.Tensor] = {}
+
+    def w2d(name):
+        return g[name].float().flatten(1)
+
+    # stem: conv -> BN folds (scale output rows)
+    s, t = bn_affine(g, "stem.bn1")
+    P["stem_w1"] = (w2d("stem.conv1.weight") * s[:, None]).contiguous()
+    P["stem_b1"] = t.contiguous()
+    s, t = bn_affine(g, "stem.downsample.1")
+    P["stem_wd"] = (w2d("stem.downsample.0.weight") * s[:, None]).contiguous()
+    P["stem_bd"] = t.contiguous()
+    s, t = bn_affine(g, "stem.bn2")
+    P["stem_w2"] = _conv3x3_taps(g["stem.conv2.weight"].float() * s[:, None, None, None]).to(wdtype)
+    P["stem_b2"] = t.contiguous()
+    s, t = bn_affine(g, "stem.bn3")
+    P["stem_w3"] = _conv3x3_taps(g["stem.conv3.weight"].float() * s[:, None, None, None]).to(wdtype)
+    P["stem_b3"] = t.contiguous()
+    P["pos1"] = g["pos_embed1"][0].float().permute(1, 2, 0).reshape(400, 128).contiguous()
+
+    for i in range(DEPTH[0]):
+        b = f"stage1.{i}."
+        s, t = bn_affine(g, b + "norm2.bn")
+        w1 = w2d(b + "mlp.conv1.weight")
+        P[f"s1.{i}.w1"] = (w1 * s[None, :]).to(wdtype).contiguous()
+        P[f"s1.{i}.b1"] = (w1 @ t).contiguous()
+        P[f"s1.{i}.w2"] = _grouped_pairs(g[b + "mlp.conv2.weight"].float()).to(wdtype)
+        P[f"s1.{i}.w3"] = w2d(b + "mlp.conv3.weight").to(wdtype).contiguous()
+
+    for stage, depth, hw in (("2", DEPTH[1], 100), ("3", DEPTH[2], 25)):
+        pe = f"patch_embed{stage}."
+        s, t = bn_affine(g, pe + "norm.bn")
+        w = g[pe + "proj.weight"].float() * s[:, None, None, None]            # [N, C, 2, 2]
+        P[f"pe{stage}_w"] = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(wdtype).contiguous()   # k = (dy, dx, c)
+        bias = g[pe + "proj.bias"].float() * s + t                             # s*(b - mean) + beta
+        pos = g[f"pos_embed{stage}"][0].float()                                # [N, h, w]
+        P[f"pe{stage}_bias"] = (bias[None, :] + pos.permute(1, 2, 0).reshape(hw, -1)).contiguous()
+        for i in range(depth):
+            b = f"stage{stage}.{i}."
+            s, t = bn_affine(g, b + "norm1.bn")
+            wq = w2d(b + "attn.qkv.weight")
+            P[f"s{stage}.{i}.wqkv"] = (wq * s[None, :]).to(wdtype).contiguous()
+            P[f"s{stage}.{i}.bqkv"] = (wq @ t).contiguous()
+            P[f"s{stage}.{i}.wproj"] = _pad_cols(w2d(b + "attn.proj.weight")).to(wdtype).contiguous()
+            s, t = bn_affine(g, b + "norm2.bn")
+            w1 = w2d(b + "mlp.conv1.weight")
+            P[f"s{stage}.{i}.w1"] = (w1 * s[None, :]).to(wdtype).contiguous()
+            P[f"s{stage}.{i}.b1"] = (w1 @ t).contiguous()
+            P[f"s{stage}.{i}.w3"] = w2d(b + "mlp.conv3.weight").to(wdtype).contiguous()
+    s, t = bn_affine(g, "norm.bn")
+    P["final_scale"], P["final_shift"] = s.contiguous(), t.contiguous()
+    return P
+
+
+def to_struct(P: Dict[str, torch.Tensor]):
+    """Packed dict (CUDA tensors) -> ctypes SunbEncoderWeights.  The dict must outlive the struct."""
+    from . import native as N
+    w = N.EncoderWeights()
+    for f in ("stem_w1", "stem_b1", "stem_wd", "stem_bd", "stem_w2", "stem_b2", "stem_w3", "stem_b3", "pos1",
+              "pe2_w", "pe2_bias", "pe3_w", "pe3_bias", "final_scale", "final_shift"):
+        setattr(w, f, P[f].data_ptr())
+    for i in range(4):
+        for f in ("w1", "b1", "w2", "w3"):
+            setattr(w.s1[i], f, P[f"s1.{i}.{f}"].data_ptr())
+    for stage, arr, depth in (("2", w.s2, 2), ("3", w.s3, 3)):
+        for i in range(depth):
+            for f in ("wqkv", "bqkv", "wproj", "w1", "b1", "w3"):
+                setattr(arr[i], f, P[f"s{stage}.{i}.{f}"].data_ptr())
+    return w
+
+
+# ------------------------------------------------------------------------------------------------------
+# Torch emulation of the packed plan (same operand layouts and row mappings as csrc/api.cu).  Used only by
+# the CPU tests to validate folding/layout; it is not a product path.
+# ------------------------------------------------------------------------------------------------------
+def _gelu(x):
+    return 0.5 * x * (1.0 + torch.erf(x * 0.70710678118654752))
+
+
+def _conv3x3_nhwc(x: torch.Tensor, taps: torch.Tensor) -> torch.Tensor:
+    """x [B,H,W,C], taps [9,N,C] -> [B,H,W,N]: nine shifted GEMMs with zero padding (the kernel's K loop)."""
+    B, H, W, C = x.shape
+    xp = F.pad(x, (0, 0, 1, 1, 1, 1))
+    out = torch.zeros(B, H, W, taps.shape[1], dtype=x.dtype)
+    for tap in range(9):
+        dy, dx = tap // 3, tap % 3
+        out += xp[:, dy:dy + H, dx:dx + W, :] @ taps[tap].t()
+    return out
+
+
+def _s2d(x: torch.Tensor) -> torch.Tensor:
+    """[B,H,W,C] raster -> [B*(H/2)*(W/2), 4*C] rows in the kernel's MAP_S2D order, k = (dy, dx, c)."""
+    B, H, W, C = x.shape
+    return x.reshape(B, H // 2, 2, W // 2, 2, C).permute(0, 1, 3, 2, 4, 5).reshape(B * (H // 2) * (W // 2), 4 * C)
+
+
+def emulate_forward(P: Dict[str, torch.Tensor], x: torch.Tensor, taps: Dict[str, torch.Tensor] = None):
+    """fp32 emulation of sunb_encoder_forward from packed weights.  Returns (dense NHWC [B,5,5,512], pooled)."""
+    f = {k: v.float() for k, v in P.items()}
+    B = x.shape[0]
+    a1 = F.conv2d(x, f["stem_w1"].reshape(64, 3, 3, 3), f["stem_b1"], stride=2, padding=1)
+    a1 = F.leaky_relu(a1, 0.1).permute(0, 2, 3, 1)
+    idn = F.conv2d(x, f["stem_wd"].reshape(128, 3, 3, 3), f["stem_bd"], stride=2, padding=1).permute(0, 2, 3, 1)
+    a2 = F.leaky_relu(_conv3x3_nhwc(a1, f["stem_w2"]) + f["stem_b2"], 0.1)
+    c3 = F.leaky_relu(_conv3x3_nhwc(a2, f["stem_w3"]) + f["stem_b3"] + idn, 0.1)
+    s1 = c3.reshape(B, 20, 2, 20, 2, 128).amax(dim=(2, 4)) + f["pos1"].reshape(1, 20, 20, 128)
+
+    def tap(name, t):
+        if taps is not None:
+            taps[name] = t.clone()
+    tap("stem", s1)
+    for i in range(4):
+        h1 = _gelu(s1 @ f[f"s1.{i}.w1"].t() + f[f"s1.{i}.b1"])
+        h2 = torch.empty_like(h1)
+        for p in range(4):
+            h2[..., p * 64:(p + 1) * 64] = _gelu(_conv3x3_nhwc(h1[..., p * 64:(p + 1) * 64], f[f"s1.{i}.w2"][p]))
+        s1 = s1 + h2 @ f[f"s1.{i}.w3"].t()
+        tap(f"stage1.{i}", s1)
+    t = _s2d(s1) @ f["pe2_w"].t()
+    t = (t.reshape(B, 100, 256) + f["pe2_bias"]).reshape(B, 10, 10, 256)
+    tap("patch_embed2", t)
+
+    def attn_block(t, pre, d):
+        Bb, H, W, Cc = t.shape
+        S = H * W
+        x2 = t.reshape(Bb * S, Cc)
+        qkv = x2 @ f[pre + "wqkv"].t() + f[pre + "bqkv"]
+        qkv = qkv.reshape(Bb, S, 3, HEADS, d).permute(2, 0, 3, 1, 4)
+        pr = torch.softmax(qkv[0] @ qkv[1].transpose(-1, -2) * d ** -0.5, dim=-1)
+        ao = (pr @ qkv[2]).permute(0, 2, 1, 3).reshape(Bb * S, HEADS * d)
+        x2 = x2 + ao @ f[pre + "wproj"][:, : HEADS * d].t()
+        hid = _gelu(x2 @ f[pre + "w1"].t() + f[pre + "b1"])
+        return (x2 + hid @ f[pre + "w3"].t()).reshape(Bb, H, W, Cc)
+
+    for i in range(2):
+        t = attn_block(t, f"s2.{i}.", 42)
+        tap(f"stage2.{i}", t)
+    t = _s2d(t) @ f["pe3_w"].t()
+    t = (t.reshape(B, 25, 512) + f["pe3_bias"]).reshape(B, 5, 5, 512)
+    tap("patch_embed3", t)
+    for i in range(3):
+        t = attn_block(t, f"s3.{i}.", 85)
+        tap(f"stage3.{i}", t)
+    dense = t * f["final_scale"] + f["final_shift"]
+    return dense, dense.mean(dim=(1, 2))

@@ -1,0 +1,150 @@
+/* sunb200 -- C ABI of the B200-native SUN / Visformer episodic hot path.
+ *
+ * Drop-in boundary.  The reference (DongSky/few-shot-vit) is pure PyTorch and has no FFI of its own; every
+ * FLOP of its hot path is executed by torch.nn modules.  Each entry point below replaces the device work of
+ * the reference function cited beside it (paths relative to the reference checkout).  The Python shims in
+ * few-shot-vit_b200/models/ keep the reference's module API (models.make / forward signatures / state_dict
+ * names) and call these functions through ctypes; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - plain C types only: device pointers, sizes, a CUDA stream passed as void* (cudaStream_t).
+ *   - every function is asynchronous and stream-ordered; it returns 0 on success or a negative SunbStatus.
+ *     sunb_last_error() returns a thread-local message for the last failure.  No exceptions cross the ABI.
+ *   - the caller owns all memory (PyTorch's caching allocator in the shims); the library allocates nothing.
+ *   - "bf16" buffers are raw uint16 bfloat16 bit patterns; activations are NHWC.
+ *   - sm_100a only.  There is no CPU fallback.
+ */
+#ifndef SUNB200_H
+#define SUNB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SUNB_ABI_VERSION 1
+
+int sunb_abi_version(void);
+const char* sunb_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Generic GEMM / implicit GEMM with fused epilogue (tcgen05 + TMEM + TMA).
+ * Replaces nn.Conv2d 1x1 / 3x3 (+ folded BatchNorm, bias, GELU / LeakyReLU, residual add) as used in
+ * test_phase/models/visformer.py:144-163 (Mlp), :175-191 (Attention.qkv/proj), :209-214 (stem conv2/conv3),
+ * :276-287 (PatchEmbed) and nn.Linear in sun_meta_training/models/classifier.py:27-35.
+ *   C[m, g*c_goff + n] = act( rs[m / rows_per_img] * sum_{tap,k} A_tap[m, g*a_goff + k] * W[(g*taps + tap)*N + n, k]
+ *                             + resid[m, g*c_goff + n] + bias[(m % bias_mod)*bias_ld + g*c_goff + n] )
+ * a_mode 0: plain rows (taps = 1).  a_mode 1: 3x3 / pad 1 / stride 1 convolution over NHWC [B,H,W,lda]
+ * (taps = 9, tap = (dy+1)*3 + (dx+1)); tiles are built from bw x bh pixel boxes (bw*bh divides 128).
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct SunbGemmDesc {
+    int32_t M, N, K;
+    int32_t taps, groups;
+    int32_t a_goff, c_goff;
+    int32_t a_mode, H, W, bw, bh;
+    const void* A;          /* bf16 */
+    int32_t lda;
+    const void* Wt;         /* bf16, K-major rows of ldw elements */
+    int32_t ldw;
+    const float* bias;
+    int32_t bias_mod, bias_ld;
+    int32_t act;            /* 0 none, 1 LeakyReLU(0.1), 2 GELU(erf) */
+    const void* resid;      /* bf16, nullable */
+    int32_t ldr;
+    const float* row_scale; /* per-image scale of the accumulator (DropPath mask / keep), nullable */
+    int32_t rows_per_img;
+    void* out;              /* bf16, nullable */
+    int32_t ldc;
+    float* out_f32;         /* nullable */
+    int32_t ldc_f32;
+    int32_t out_map, oH, oW; /* 0 identity; 1 = 2x2 space-to-depth of an oH x oW raster (feeds PatchEmbed) */
+} SunbGemmDesc;
+
+/* impl: 0 = tcgen05 kernel (product path), 1 = SIMT cross-check kernel (tests only) */
+int sunb_gemm(const SunbGemmDesc* desc, int impl, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Encoder: Visformer.forward of 'visformer_micro_80' in eval mode, BatchNorm folded
+ * (test_phase/models/visformer.py:424-462; sun_meta_training/models/visformer.py:464 for the dense output).
+ * All weight buffers are produced by few-shot-vit_b200/sunb200/packing.py (layouts documented there).
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct SunbConvMlpW {        /* stage-1 Block: norm2 folded into conv1 */
+    const void* w1; const float* b1; /* bf16 [256][128], fp32 [256] */
+    const void* w2;                  /* bf16 grouped 3x3 as 4 channel pairs: [4][9][64][64] block-diagonal */
+    const void* w3;                  /* bf16 [128][256] */
+} SunbConvMlpW;
+
+typedef struct SunbAttnBlockW {      /* stage-2/3 Block: norm1 folded into qkv, norm2 into mlp.conv1 */
+    const void* wqkv; const float* bqkv;   /* bf16 [3*6*d][C], fp32 [3*6*d] */
+    const void* wproj;                     /* bf16 [C][ld_inner], ld_inner = round_up(6*d, 8) */
+    const void* w1; const float* b1;       /* bf16 [4C][C], fp32 [4C] */
+    const void* w3;                        /* bf16 [C][4C] */
+} SunbAttnBlockW;
+
+typedef struct SunbEncoderWeights {
+    const float* stem_w1; const float* stem_b1;    /* fp32 [64][27] (BN1 folded), [64] */
+    const float* stem_wd; const float* stem_bd;    /* fp32 [128][27] (downsample BN folded), [128] */
+    const void* stem_w2; const float* stem_b2;     /* bf16 [9][128][64], fp32 [128] */
+    const void* stem_w3; const float* stem_b3;     /* bf16 [9][128][128], fp32 [128] */
+    const float* pos1;                             /* fp32 [400][128] (NHWC) */
+    SunbConvMlpW s1[4];
+    const void* pe2_w; const float* pe2_bias;      /* bf16 [256][4*128] k=(dy,dx,c); fp32 [100][256] = bias*bn + pos2 */
+    SunbAttnBlockW s2[2];
+    const void* pe3_w; const float* pe3_bias;      /* bf16 [512][4*256]; fp32 [25][512] */
+    SunbAttnBlockW s3[3];
+    const float* final_scale; const float* final_shift;   /* fp32 [512] each */
+} SunbEncoderWeights;
+
+/* optional copies of the residual stream after each layer boundary (bf16 NHWC), for the per-layer tests */
+typedef struct SunbEncoderTaps {
+    void* stem;          /* [B,20,20,128] after pos_embed1 */
+    void* stage1[4];     /* [B,20,20,128] */
+    void* patch_embed2;  /* [B,10,10,256] */
+    void* stage2[2];
+    void* patch_embed3;  /* [B,5,5,512] */
+    void* stage3[3];
+} SunbEncoderTaps;
+
+int sunb_encoder_workspace_bytes(int B, size_t* bytes);
+
+/* x: fp32 NCHW [B,3,80,80].  pooled: fp32 [B,512].  dense (nullable): fp32 NHWC [B,5,5,512] after the final BN.
+ * dense_bf16 / pooled_bf16 (nullable): bf16 copies that feed the SUN classifier GEMMs. */
+int sunb_encoder_forward(const SunbEncoderWeights* w, const float* x, int B, void* workspace, size_t workspace_bytes,
+                         float* pooled, float* dense, void* dense_bf16, void* pooled_bf16, const SunbEncoderTaps* taps,
+                         void* stream);
+
+/* Attention core (visformer.py:183-190).  qkv bf16 [B*S, ld_qkv] with channels (qkv, head, d); out bf16 [B*S, ld_out]. */
+int sunb_attention(const void* qkv, void* out, int B, int S, int d, int heads, int ld_qkv, int ld_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Episode head: MetaBaseline (test_phase/models/meta_baseline.py:36-46) and utils.compute_logits
+ * (test_phase/utils/__init__.py:78-101).  metric: 0 dot, 1 cos, 2 sqr.
+ *   feat_shot fp32 [E, way, shot, D]; feat_query fp32 [E, Q, D]; logits fp32 [E, Q, way].
+ *   temp: device scalar if temp_dev != NULL (the learnable nn.Parameter), else temp_host.
+ * sunb_logits_ce_acc: out[0] = F.cross_entropy mean, out[1] = utils.compute_acc (test_few_shot.py:89-90).
+ * ------------------------------------------------------------------------------------------------- */
+int sunb_episode_logits(const float* feat_shot, const float* feat_query, float* logits, int E, int way, int shot, int Q,
+                        int D, int metric, const float* temp_dev, float temp_host, void* stream);
+int sunb_logits_ce_acc(const float* logits, const int64_t* label, int R, int W, float* out2, void* stream);
+int sunb_hard_ce_backward(const float* logits, const int64_t* label, int R, int W, const float* gout, float gscale,
+                          float* dlogits, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * SUN local head.
+ *   sunb_softlabel: generate_softlabel (sun_meta_training/offline.py:57-76), bug-compatible (background column 1).
+ *     logits element (b, c, p) at logits[b*sb + c*sc + p*sp]; out fp32 [B*hw, n_cls+1].
+ *   sunb_soft_ce_forward/backward: SoftTargetCrossEntropy (offline.py:34-45).  row_loss: scratch fp32 [R].
+ * ------------------------------------------------------------------------------------------------- */
+int sunb_softlabel(const float* logits, int64_t sb, int64_t sc, int64_t sp, int B, int n_cls, int hw, int k, int bp,
+                   double smoothing, float* out, void* stream);
+int sunb_soft_ce_forward(const float* x, int ldx, const float* target, int ldt, int R, int Rt, int C, float* row_loss,
+                         float* loss, void* stream);
+int sunb_soft_ce_backward(const float* x, int ldx, const float* target, int ldt, int R, int Rt, int C, const float* gout,
+                          float gscale, float* dx, int lddx, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SUNB200_H */

@@ -1,0 +1,139 @@
+"""-m gpu: the whole eval path through the drop-in module API against the CPU oracle and the golden files
+written by the real reference (tests/golden/, oracle/make_golden.py).
+
+Tolerances (stated per north_star): bf16 operands / fp32 accumulation vs the fp32 reference.
+  layer boundaries : relative L2 error <= 3e-2 (grows with depth; bf16 has an 8-bit mantissa, 20+ GEMMs deep)
+  cosine logits    : max |delta| <= 0.25 on a -2.2 ... 7.2 range (BASELINE.md section 5 measured 0.13 for bf16 autocast)
+  argmax           : >= 99.9 % of queries on the BN-calibrated, class-structured fixture
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import models  # noqa: E402
+import utils  # noqa: E402
+import utils.few_shot as fs  # noqa: E402
+import sun_oracle as O  # noqa: E402
+from gpu_helpers import rel_err, max_err  # noqa: E402
+
+LAYER_TOL = 3e-2
+
+
+def make_model(sd, **kw):
+    m = models.make("meta-baseline", encoder="visformer_micro_80", encoder_args=kw)
+    m.load_state_dict(sd)
+    return m.cuda().eval()
+
+
+def test_layer_boundaries_vs_oracle_and_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "encoder_eval_wr.npz"))
+    sd = O.randomize_bn(O.init_meta_baseline_state_dict(12345), seed=7)
+    m = make_model(sd)
+    x = O.make_episode_images(101, 2, 2)
+    taps_o = {}
+    with torch.no_grad():
+        dense_o, pooled_o = O.encoder_forward(sd, x, "encoder.", taps=taps_o)
+        taps = {}
+        pooled = m.encoder(x.cuda(), taps=taps)
+    torch.cuda.synchronize()
+    report = []
+    for name, ref in taps_o.items():
+        e = rel_err(taps[name].float().cpu(), ref.permute(0, 2, 3, 1))
+        report.append((name, e))
+    report.append(("pooled", rel_err(pooled.cpu(), pooled_o)))
+    report.append(("pooled_vs_golden", rel_err(pooled.cpu(), torch.as_tensor(g["pooled"]))))
+    print("\n".join(f"{n:18s} rel_l2 {e:.3e}" for n, e in report))
+    bad = [(n, e) for n, e in report if not e < LAYER_TOL]
+    assert not bad, bad
+
+
+def test_small_episode_logits_vs_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "episode_small_wr.npz"))
+    sd = O.randomize_bn(O.init_meta_baseline_state_dict(12345), seed=7)
+    m = make_model(sd)
+    data = O.make_episode_images(202, 5, 4).cuda()
+    xs, xq = fs.split_shot_query(data, 5, 1, 3, ep_per_batch=1)
+    with torch.no_grad():
+        logits = m(xs, xq)
+    assert logits.shape == (1, 15, 5) and logits.dtype == torch.float32
+    assert max_err(logits.cpu(), torch.as_tensor(g["logits"])) < 0.06      # cos logits ~9.8; BASELINE.md: 0.056 for bf16
+    label = fs.make_nk_label(5, 3, 1)
+    assert np.array_equal(label.numpy(), g["label"])                       # index work: bit-exact
+
+
+def test_full_episode_argmax_w1(golden_dir):
+    g = np.load(os.path.join(golden_dir, "episode_full_w1.npz"))
+    sd = O.calibrate_bn(O.init_meta_baseline_state_dict(12345))
+    m = make_model(sd)
+    agree = total = 0
+    worst = 0.0
+    for ep in range(2):
+        data = O.make_episode_images(300 + ep, 5, 16).cuda()
+        xs, xq = fs.split_shot_query(data, 5, 1, 15, ep_per_batch=1)
+        with torch.no_grad():
+            logits = m(xs, xq)[0].cpu()
+        ref = torch.as_tensor(g["logits"][ep])
+        worst = max(worst, max_err(logits, ref))
+        agree += int((logits.argmax(-1) == ref.argmax(-1)).sum())
+        total += ref.shape[0]
+    print(f"argmax agreement {agree}/{total}, max |dlogit| {worst:.4f}")
+    assert worst < 0.25
+    assert agree / total >= 0.999
+
+
+def test_batched_episodes_match_single(golden_dir):
+    """E episodes in one call == the same episodes one by one (episodes are independent in eval mode)."""
+    sd = O.calibrate_bn(O.init_meta_baseline_state_dict(12345))
+    m = make_model(sd)
+    eps = [O.make_episode_images(300 + e, 5, 16) for e in range(3)]
+    data = torch.cat(eps).cuda()
+    xs, xq = fs.split_shot_query(data, 5, 1, 15, ep_per_batch=3)
+    with torch.no_grad():
+        batched = m(xs, xq).cpu()
+        for e in range(3):
+            s1, q1 = fs.split_shot_query(eps[e].cuda(), 5, 1, 15, ep_per_batch=1)
+            single = m(s1, q1)[0].cpu()
+            assert torch.equal(batched[e], single)
+
+
+def test_five_shot_episode(golden_dir):
+    sd = O.calibrate_bn(O.init_meta_baseline_state_dict(12345))
+    m = make_model(sd)
+    data = O.make_episode_images(700, 5, 20)
+    xs, xq = O.split_shot_query(data, 5, 5, 15)
+    with torch.no_grad():
+        ref = O.meta_baseline_forward(sd, xs, xq)
+        out = m(xs.cuda(), xq.cuda()).cpu()
+    assert max_err(out, ref) < 0.25
+    assert (out.argmax(-1) == ref.argmax(-1)).float().mean().item() >= 0.999
+
+
+def test_token_label_model(golden_dir):
+    g = np.load(os.path.join(golden_dir, "sun_head.npz"))
+    sd = O.randomize_bn(O.init_token_label_state_dict(12345), seed=7)
+    t = models.make("token-label", encoder="visformer_micro_80", encoder_args={}, classifier="linear-classifier",
+                    classifier_args={"n_classes": 64})
+    t.load_state_dict(sd)
+    t = t.cuda().eval()
+    x = O.make_episode_images(101, 2, 2).cuda()
+    with torch.no_grad():
+        yt, y, tok = t(x)
+        yt_t, _, _ = t(x, True)
+    assert tuple(yt.shape) == (4, 65, 5, 5) and tuple(yt.stride()) == tuple(g["y_token_student_stride"])
+    assert rel_err(yt.cpu(), torch.as_tensor(g["y_token_student"])) < LAYER_TOL
+    assert rel_err(yt_t.cpu(), torch.as_tensor(g["y_token_teacher"])) < LAYER_TOL
+    assert rel_err(y.cpu(), torch.as_tensor(g["y_student"])) < LAYER_TOL
+    assert rel_err(tok.cpu(), torch.as_tensor(g["token_student"])) < LAYER_TOL
+    # the reference's stride contract: permute(0,2,3,1).view(-1, C) must work on the returned tensor
+    flat = yt.permute(0, 2, 3, 1).view(-1, 65)
+    assert flat.shape == (100, 65)
+
+
+def test_train_mode_fails_loudly():
+    m = models.make("meta-baseline", encoder="visformer_micro_80", encoder_args={}).cuda().train()
+    with pytest.raises(NotImplementedError):
+        m.encoder(torch.zeros(2, 3, 80, 80, device="cuda"))

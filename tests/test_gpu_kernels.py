@@ -1,0 +1,178 @@
+"""-m gpu: every kernel behind the C ABI against a torch fp32 reference of the same op on the same bf16-rounded
+inputs (tolerances cover only fp32 summation order and the final bf16 rounding of the output)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from gpu_helpers import run_gemm, act_ref, rel_err, max_err  # noqa: E402
+from sunb200 import native as N, engine  # noqa: E402
+import sun_oracle as O  # noqa: E402
+
+DEV = "cuda"
+BF16_OUT = 6e-3      # relative L2 tolerance for bf16 outputs
+F32_OUT = 2e-4
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("M,Nn,K,act,use_bias,use_res", [
+    (256, 128, 64, 0, False, False),
+    (300, 256, 128, 2, True, False),        # ragged M, GELU, bias
+    (1000, 756, 256, 0, True, False),       # qkv: ragged N
+    (1000, 256, 252, 0, False, True),       # proj: K tail (TMA zero fill), residual
+    (500, 512, 510, 0, False, True),
+    (2000, 1024, 256, 2, True, False),
+    (2000, 256, 1024, 0, False, True),
+    (128, 65, 512, 0, True, False),         # SUN local classifier shape (odd N)
+])
+def test_gemm_plain(impl, M, Nn, K, act, use_bias, use_res):
+    lda = (K + 7) // 8 * 8
+    A = torch.zeros(M, lda, device=DEV, dtype=torch.bfloat16)
+    A[:, :K] = rnd(M, K, seed=1).bfloat16()
+    A[:, K:] = float("nan")                      # padding columns must never be read
+    Wt = torch.zeros(Nn, lda, device=DEV, dtype=torch.bfloat16)
+    Wt[:, :K] = rnd(Nn, K, seed=2, scale=K ** -0.5).bfloat16()
+    Wt[:, K:] = float("nan")
+    bias = rnd(Nn, seed=3) if use_bias else None
+    ldc = (Nn + 7) // 8 * 8
+    resid = rnd(M, ldc, seed=4).bfloat16() if use_res else None
+    out = run_gemm(A, Wt, M, Nn, K, impl=impl, bias=bias, act=act, resid=resid, out_cols=ldc)
+    ref = A[:, :K].float() @ Wt[:, :K].float().t()
+    if use_res:
+        ref = ref + resid[:, :Nn].float()
+    if use_bias:
+        ref = ref + bias
+    ref = act_ref(ref, act)
+    assert rel_err(out[:, :Nn], ref) < BF16_OUT
+    if ldc > Nn:
+        assert (out[:, Nn:] == 0).all()          # columns past N untouched
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["simt", "tcgen05"])
+def test_gemm_f32_out_and_bias_table(impl):
+    M, Nn, K = 400, 256, 512
+    A = rnd(M, K, seed=5).bfloat16()
+    Wt = rnd(Nn, K, seed=6, scale=K ** -0.5).bfloat16()
+    table = rnd(100, Nn, seed=7)
+    out = run_gemm(A, Wt, M, Nn, K, impl=impl, bias=table, bias_mod=100, out_f32=True)
+    ref = A.float() @ Wt.float().t() + table.repeat(4, 1)
+    assert rel_err(out, ref) < F32_OUT
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["simt", "tcgen05"])
+def test_gemm_row_scale_and_s2d(impl):
+    B, H, Wd, Cc, K = 3, 10, 10, 256, 128
+    M = B * H * Wd
+    A = rnd(M, K, seed=8).bfloat16()
+    Wt = rnd(Cc, K, seed=9, scale=K ** -0.5).bfloat16()
+    resid = rnd(M, Cc, seed=10).bfloat16()
+    rs = torch.tensor([0.0, 2.0, 1.0], device=DEV)
+    out = run_gemm(A, Wt, M, Cc, K, impl=impl, resid=resid, row_scale=rs, rows_per_img=H * Wd, out_map=1, oHW=(H, Wd))
+    ref = (A.float() @ Wt.float().t()) * rs.repeat_interleave(H * Wd)[:, None] + resid.float()
+    ref = ref.reshape(B, H // 2, 2, Wd // 2, 2, Cc).permute(0, 1, 3, 2, 4, 5).reshape(M, Cc)
+    assert rel_err(out, ref) < BF16_OUT
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("B,H,Cin,Cout,box", [(3, 40, 64, 128, 8), (2, 40, 128, 128, 8), (5, 20, 64, 64, 4)])
+def test_conv3x3(impl, B, H, Cin, Cout, box):
+    x = rnd(B, H, H, Cin, seed=11).bfloat16()
+    w = rnd(Cout, Cin, 3, 3, seed=12, scale=(9 * Cin) ** -0.5)
+    taps = w.permute(2, 3, 0, 1).reshape(9 * Cout, Cin).bfloat16().contiguous()
+    bias = rnd(Cout, seed=13)
+    resid = rnd(B * H * H, Cout, seed=14).bfloat16()
+    out = run_gemm(x, taps, B * H * H, Cout, Cin, impl=impl, taps=9, conv=(H, H, box, box), bias=bias, act=1, resid=resid)
+    wq = taps.float().reshape(3, 3, Cout, Cin).permute(2, 3, 0, 1)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wq, padding=1).permute(0, 2, 3, 1).reshape(-1, Cout)
+    ref = F.leaky_relu(ref + resid.float() + bias, 0.1)
+    assert rel_err(out, ref) < BF16_OUT
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["simt", "tcgen05"])
+def test_grouped_conv_pairs(impl):
+    from sunb200 import packing
+    B, H = 3, 20
+    x = rnd(B, H, H, 256, seed=15).bfloat16()
+    w = rnd(256, 32, 3, 3, seed=16, scale=(9 * 32) ** -0.5)
+    pairs = packing._grouped_pairs(w).bfloat16().reshape(4 * 9 * 64, 64).contiguous()
+    out = run_gemm(x, pairs, B * H * H, 64, 64, impl=impl, taps=9, groups=4, a_goff=64, c_goff=64,
+                   conv=(H, H, 4, 4), act=2)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.bfloat16().float(), padding=1, groups=8)
+    ref = act_ref(ref, 2).permute(0, 2, 3, 1).reshape(-1, 256)
+    assert rel_err(out, ref) < BF16_OUT
+
+
+@pytest.mark.parametrize("S,d,C", [(100, 42, 256), (25, 85, 512)])
+def test_attention(S, d, C):
+    B, heads = 5, 6
+    inner = heads * d
+    ld_qkv = (3 * inner + 7) // 8 * 8
+    qkv = torch.full((B * S, ld_qkv), float("nan"), device=DEV, dtype=torch.bfloat16)
+    qkv[:, : 3 * inner] = rnd(B * S, 3 * inner, seed=17).bfloat16()
+    out = torch.zeros(B * S, C, device=DEV, dtype=torch.bfloat16)
+    N.check(N.lib().sunb_attention(qkv.data_ptr(), out.data_ptr(), B, S, d, heads, ld_qkv, C, N.current_stream()), "attention")
+    torch.cuda.synchronize()
+    t = qkv[:, : 3 * inner].float().reshape(B, S, 3, heads, d).permute(2, 0, 3, 1, 4)
+    p = torch.softmax(t[0] @ t[1].transpose(-1, -2) * d ** -0.5, dim=-1)
+    ref = (p @ t[2]).permute(0, 2, 1, 3).reshape(B * S, inner)
+    assert rel_err(out[:, :inner], ref) < BF16_OUT
+    assert (out[:, inner:] == 0).all()
+
+
+@pytest.mark.parametrize("metric", ["cos", "dot", "sqr"])
+def test_episode_logits(metric):
+    E, way, shot, Q, D = 3, 5, 5, 75, 512
+    fs, fq = rnd(E, way, shot, D, seed=18), rnd(E, Q, D, seed=19)
+    temp = torch.tensor(10.0, device=DEV)
+    out = engine.episode_logits(fs, fq, temp, metric)
+    ref = O.compute_logits(fq.cpu(), fs.cpu().mean(2), metric, 10.0)
+    assert max_err(out.cpu(), ref) < 2e-4 * max(1.0, ref.abs().max().item())
+
+
+def test_ce_and_acc():
+    logits, label = rnd(75, 5, seed=20), torch.randint(0, 5, (75,), generator=torch.Generator().manual_seed(1)).to(DEV)
+    out = engine.ce_and_acc(logits, label).cpu()
+    assert abs(out[0].item() - F.cross_entropy(logits, label).item()) < 1e-5
+    assert out[1].item() == pytest.approx((logits.argmax(1) == label).float().mean().item())
+
+
+def test_softlabel_bit_exact(golden_dir):
+    import numpy as np, os
+    g = np.load(os.path.join(golden_dir, "sun_head.npz"))
+    gl = torch.Generator().manual_seed(11)
+    t_logits = torch.randn(8, 5, 5, 64, generator=gl).to(DEV).permute(0, 3, 1, 2)     # NHWC-backed NCHW view
+    soft = engine.generate_softlabel(t_logits, k=5, bp=10)
+    assert np.array_equal(soft.cpu().numpy(), g["soft_label"])
+    soft2 = engine.generate_softlabel(t_logits.contiguous(), k=5, bp=10)                # NCHW-contiguous input
+    assert np.array_equal(soft2.cpu().numpy(), g["soft_label"])
+    for (k, bp) in [(3, 10), (1, 0), (5, 25), (64, 3)]:
+        ref = O.generate_softlabel(t_logits.cpu(), k=k, bp=bp)
+        assert torch.equal(engine.generate_softlabel(t_logits, k=k, bp=bp).cpu(), ref), (k, bp)
+
+
+def test_soft_ce_forward_backward(golden_dir):
+    import numpy as np, os
+    g = np.load(os.path.join(golden_dir, "sun_head.npz"))
+    gl = torch.Generator().manual_seed(11)
+    torch.randn(8, 5, 5, 64, generator=gl)
+    s_logits = torch.randn(8, 5, 5, 65, generator=gl).reshape(-1, 65)
+    soft = torch.as_tensor(g["soft_label"])
+    x = s_logits.to(DEV).requires_grad_(True)
+    loss = engine.soft_target_cross_entropy(x, soft.to(DEV))
+    assert abs(loss.item() - float(g["soft_ce"])) < 1e-4
+    (loss * 0.5).backward()
+    xr = s_logits.clone().requires_grad_(True)
+    (O.soft_target_cross_entropy(xr, soft) * 0.5).backward()
+    assert max_err(x.grad.cpu(), xr.grad) < 1e-6
+    # tiled target (rows of x an integer multiple of target rows, offline.py:41-43)
+    x2 = torch.cat([s_logits, s_logits * 0.5]).to(DEV)
+    l2 = engine.soft_target_cross_entropy(x2, soft.to(DEV))
+    assert abs(l2.item() - O.soft_target_cross_entropy(x2.cpu(), soft).item()) < 1e-4

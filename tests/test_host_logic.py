@@ -1,0 +1,101 @@
+"""CPU tests of the host-side logic: packing maths, registry/state_dict contract, C-ABI surface."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import sun_oracle as O
+from sunb200 import native as N, packing
+
+
+def test_packing_folds_match_oracle():
+    """BN-folded, re-laid-out weights re-applied with plain torch fp32 ops == oracle layer outputs."""
+    sd = O.randomize_bn(O.init_meta_baseline_state_dict(12345), seed=7)
+    x = O.make_episode_images(101, 2, 1)
+    taps_o, taps_e = {}, {}
+    with torch.no_grad():
+        dense, pooled = O.encoder_forward(sd, x, "encoder.", taps=taps_o)
+        P = packing.pack_encoder(sd, "encoder.", wdtype=torch.float32)
+        d2, p2 = packing.emulate_forward(P, x, taps_e)
+    for k, ref in taps_o.items():
+        ref = ref.permute(0, 2, 3, 1)
+        err = (taps_e[k] - ref).abs().max().item() / (ref.abs().max().item() + 1e-12)
+        assert err < 5e-4, (k, err)      # fp32 re-association only (raw-init activations reach ~550)
+    assert (p2 - pooled).abs().max().item() / pooled.abs().max().item() < 5e-4
+    assert (d2 - dense.permute(0, 2, 3, 1)).abs().max().item() / dense.abs().max().item() < 5e-4
+
+
+def test_packed_layouts():
+    sd = O.init_encoder_state_dict(3)
+    P = packing.pack_encoder(sd)
+    assert P["stem_w2"].shape == (9, 128, 64) and P["stem_w2"].dtype == torch.bfloat16
+    assert P["s1.0.w2"].shape == (4, 9, 64, 64)
+    blk = P["s1.0.w2"].float()
+    assert (blk[:, :, :32, 32:] == 0).all() and (blk[:, :, 32:, :32] == 0).all()      # block-diagonal pairs
+    assert P["s2.0.wqkv"].shape == (756, 256) and P["s3.0.wqkv"].shape == (1530, 512)
+    assert P["s2.0.wproj"].shape == (256, 256) and (P["s2.0.wproj"][:, 252:] == 0).all()
+    assert P["s3.0.wproj"].shape == (512, 512) and (P["s3.0.wproj"][:, 510:] == 0).all()
+    assert P["pe2_w"].shape == (256, 512) and P["pe2_bias"].shape == (100, 256)
+    assert P["pe3_w"].shape == (512, 1024) and P["pe3_bias"].shape == (25, 512)
+    for k, v in P.items():
+        assert v.is_contiguous(), k
+
+
+def test_registry_and_state_dict_contract():
+    import models
+    m = models.make("meta-baseline", encoder="visformer_micro_80", encoder_args={"drop_path_rate": 0.5})
+    ref = O.init_meta_baseline_state_dict(1)
+    got = m.state_dict()
+    assert list(got.keys()) == list(ref.keys())
+    for k in ref:
+        assert tuple(got[k].shape) == tuple(ref[k].shape), k
+    assert m.encoder.out_dim == 512
+    assert sum(p.numel() for p in m.parameters()) == 12_531_393
+    m.load_state_dict(ref)
+    assert models.make(None) is None
+    assert {"meta-baseline", "visformer_micro_80", "visformer", "classifier", "linear-classifier", "nn-classifier",
+            "token-label"} <= set(models.models)
+    ck = {"model": "meta-baseline", "model_args": {"encoder": "visformer_micro_80", "encoder_args": {}}, "model_sd": ref}
+    m2 = models.load(ck)
+    assert torch.equal(m2.state_dict()["encoder.stem.conv1.weight"], ref["encoder.stem.conv1.weight"])
+    # encoder hand-over used by test_few_shot.py:57-63 and train_meta.py:124-126
+    m3 = models.make("meta-baseline", encoder=None)
+    m3.encoder = m2.encoder
+    m.encoder.load_state_dict(m2.encoder.state_dict())
+    import utils
+    utils.freeze_bn(m)
+    assert all(not b.training for b in m.modules() if isinstance(b, torch.nn.BatchNorm2d))
+
+
+def test_index_utils_match_oracle():
+    import utils.few_shot as fs
+    for (way, shot, query, ep) in [(5, 1, 15, 1), (5, 5, 15, 2), (10, 1, 5, 8), (3, 2, 1, 4), (1, 1, 1, 1)]:
+        n = ep * way * (shot + query)
+        ids = torch.arange(n).view(n, 1, 1, 1).float()
+        s, q = fs.split_shot_query(ids, way, shot, query, ep)
+        so, qo = O.split_shot_query(ids, way, shot, query, ep)
+        assert torch.equal(s, so) and torch.equal(q, qo)
+        assert torch.equal(fs.make_nk_label(way, query, ep), O.make_nk_label(way, query, ep))
+
+
+def test_cpu_tensors_fail_loudly():
+    import utils
+    with pytest.raises(RuntimeError):
+        utils.compute_logits(torch.zeros(1, 2, 4), torch.zeros(1, 3, 4))
+
+
+def test_c_abi_exports_every_declared_symbol():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "sunb200.h")).read()
+    declared = set(re.findall(r"\b(sunb_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(N.SIGNATURES), declared ^ set(N.SIGNATURES)
+    assert os.path.exists(N.LIB_PATH), "libsunb200.so missing: run __graft_entry__.build()"
+    lib = ctypes.CDLL(N.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert N.lib().sunb_abi_version() == 1
+    # struct layouts mirror the header (sizes are what the C compiler produces for these field lists)
+    assert ctypes.sizeof(N.ConvMlpW) == 32 and ctypes.sizeof(N.AttnBlockW) == 48
+    assert ctypes.sizeof(N.EncoderWeights) == 9 * 8 + 4 * 32 + 16 + 2 * 48 + 16 + 3 * 48 + 16
