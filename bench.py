@@ -143,7 +143,7 @@ def time_dominant_kernel(model_state, device, peaks_tf):
     import torch
     from sunb200 import native as N, packing
     B = CHUNK * IMGS_PER_EPISODE
-    P = packing.pack_encoder({k[len("encoder."):]: v for k, v in model_state.items() if k.startswith("encoder.")})
+    P = packing.pack_encoder({k[len("encoder."):]: v.to(device) for k, v in model_state.items() if k.startswith("encoder.")})
     a2 = torch.randn(B, 40, 40, 128, device=device).bfloat16()          # 1 GB, far larger than the 126 MB L2
     idn = torch.randn(B * 1600, 128, device=device).bfloat16()
     out = torch.empty(B * 1600, 128, device=device, dtype=torch.bfloat16)
@@ -195,7 +195,8 @@ def run_product(args):
     model.load_state_dict(sd)
     model = model.to(device).eval()
 
-    n_chunks = EPISODES_PER_GPU // CHUNK
+    profile_mode = os.environ.get("SUNB_BENCH_PROFILE") == "1"      # short run for ncu: one chunk, no side measurements
+    n_chunks = 1 if profile_mode else EPISODES_PER_GPU // CHUNK
     # device-resident inputs for `value` (576 MB per step >> 126 MB L2, no flush needed)
     dev_chunks = [device_episodes(CHUNK, 1000 * rank + c, device) for c in range(n_chunks)]
     # pinned host inputs for `e2e`
@@ -244,6 +245,10 @@ def run_product(args):
         with ClockSampler(local) as clk:
             ms_total = timed(step_device, args.steps)
         clocks = clk.summary()
+        if profile_mode:
+            if rank == 0:
+                print(json.dumps({"profile_mode": True, "ms_per_chunk": ms_total / args.steps}))
+            return
         for _ in range(2):
             step_e2e()
         ms_e2e = timed(step_e2e, args.steps)
