@@ -1,91 +1,194 @@
 // Multi-head self-attention core (reference: test_phase/models/visformer.py:183-190).
 //   qkv : bf16 [B*S, ld_qkv], channel c = x*(heads*d) + y*d + z   (x in {q,k,v}, y head, z in [0,d))
 //   out : bf16 [B*S, ld_out], channel y*d + z
-//   P = softmax(q k^T * scale) in fp32, O = P v in fp32.
-// One CTA per (image, head); the whole sequence (S = 100 or 25) lives in shared memory.  fp32 SIMT math:
-// QK^T and PV are 1.2 % of the encoder FLOPs.
+//   P = softmax(q k^T * d^-0.5), O = P v.
+// Warp-level tensor-core kernel: the whole sequence (S = 100 or 25 tokens) of one (image, head) problem sits in
+// shared memory (zero-padded to MMA shapes: S -> 112 / 32 keys, d 42 -> 48, 85 -> 96); each warp owns 16 query rows,
+// computes the full score row block with mma.sync.m16n8k16 (bf16 in, fp32 accumulate), does the softmax on the
+// accumulator registers (row max / sum via quad shuffles, exp2 with the scale folded in) and feeds the probabilities
+// straight back as the A operand of the P.V MMAs.  QK^T + PV are 1.2 % of the encoder FLOPs; the problems are far
+// too small (100x100x42) for a 128-row tcgen05 tile, so this stays on the legacy warp MMA path by design.
 #include "common.cuh"
 
 namespace {
 
-constexpr int ATT_WARPS = 8;
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                               uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
 
-__global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
-                                                                    int S, int d, int heads, int ld_qkv, int ld_out,
-                                                                    float scale_log2e) {
-    extern __shared__ float sm[];
-    const int dp = d | 1;                      // odd row stride -> conflict-free column walks
-    float* q = sm;                             // [S][dp]
-    float* k = q + S * dp;                     // [S][dp]
-    float* v = k + S * dp;                     // [S][dp]
-    float* prob = v + S * dp;                  // [ATT_WARPS][S]
-    const int img = blockIdx.x / heads, head = blockIdx.x % heads;
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int S_PAD, int D_PAD, int PAIRS>
+struct AttnCfg {
+    static constexpr int QK_LD = D_PAD + 8;        // bf16 elements per Q/K row (conflict-free fragment loads)
+    static constexpr int VT_LD = S_PAD + 8;        // bf16 elements per V^T row
+    static constexpr int WARPS_PER_PAIR = S_PAD / 16;
+    static constexpr int THREADS = 32 * WARPS_PER_PAIR * PAIRS;
+    static constexpr int PAIR_ELEMS = 2 * S_PAD * QK_LD + D_PAD * VT_LD;
+    static constexpr size_t SMEM = (size_t)PAIRS * PAIR_ELEMS * sizeof(bf16);
+};
+
+template <int S_PAD, int D_PAD, int PAIRS>
+__global__ void __launch_bounds__(AttnCfg<S_PAD, D_PAD, PAIRS>::THREADS)
+attention_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int n_pairs, int S, int d, int heads,
+                     int ld_qkv, int ld_out, float scale_log2e) {
+    using Cfg = AttnCfg<S_PAD, D_PAD, PAIRS>;
+    constexpr int QK_LD = Cfg::QK_LD, VT_LD = Cfg::VT_LD;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    bf16* smem = reinterpret_cast<bf16*>(smem_raw);
     const int inner = heads * d;
-    for (int i = threadIdx.x; i < S * d; i += blockDim.x) {
-        const int t = i / d, z = i % d;
-        const bf16* row = qkv + (size_t)(img * S + t) * ld_qkv + head * d + z;
-        q[t * dp + z] = __bfloat162float(row[0]);
-        k[t * dp + z] = __bfloat162float(row[inner]);
-        v[t * dp + z] = __bfloat162float(row[2 * inner]);
+
+    // ---- stage Q, K (row-major) and V^T for the PAIRS problems of this CTA, zero padded
+    for (int pl = 0; pl < PAIRS; ++pl) {
+        const int pair = blockIdx.x * PAIRS + pl;
+        bf16* sq = smem + pl * Cfg::PAIR_ELEMS;
+        bf16* sk = sq + S_PAD * QK_LD;
+        bf16* sv = sk + S_PAD * QK_LD;
+        const bool live = pair < n_pairs;
+        const int img = live ? pair / heads : 0, head = live ? pair % heads : 0;
+        const bf16* base = qkv + (size_t)img * S * ld_qkv + head * d;
+        for (int i = threadIdx.x; i < S_PAD * D_PAD; i += Cfg::THREADS) {
+            const int t = i / D_PAD, z = i % D_PAD;
+            const bool in = live && t < S && z < d;
+            const bf16* row = base + (size_t)t * ld_qkv + z;
+            const bf16 zero = __float2bfloat16(0.f);
+            sq[t * QK_LD + z] = in ? row[0] : zero;
+            sk[t * QK_LD + z] = in ? row[inner] : zero;
+            sv[z * VT_LD + t] = in ? row[2 * inner] : zero;
+        }
     }
     __syncthreads();
+
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* pr = prob + warp * S;
-    for (int t = warp; t < S; t += ATT_WARPS) {
-        float sc[4];                            // S <= 128 keys: lane owns keys lane, lane+32, lane+64, lane+96
-        float mx = -INFINITY;
+    const int pl = warp / Cfg::WARPS_PER_PAIR, wq = warp % Cfg::WARPS_PER_PAIR;
+    const int pair = blockIdx.x * PAIRS + pl;
+    if (pair >= n_pairs) return;
+    const bf16* sq = smem + pl * Cfg::PAIR_ELEMS;
+    const bf16* sk = sq + S_PAD * QK_LD;
+    const bf16* sv = sk + S_PAD * QK_LD;
+    const int g = lane >> 2, t = lane & 3;
+    const int r0 = wq * 16;
+
+    // ---- scores: 16 rows x S_PAD keys
+    constexpr int NT = S_PAD / 8;
+    float sc[NT][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int key = lane + 32 * j;
-            float s = -INFINITY;
-            if (key < S) {
-                s = 0.f;
-                for (int z = 0; z < d; ++z) s = fmaf(q[t * dp + z], k[key * dp + z], s);
-                s *= scale_log2e;
-            }
-            sc[j] = s;
-            mx = fmaxf(mx, s);
+    for (int j = 0; j < NT; ++j) sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+#pragma unroll
+    for (int k0 = 0; k0 < D_PAD; k0 += 16) {
+        const uint32_t a0 = *reinterpret_cast<const uint32_t*>(sq + (r0 + g) * QK_LD + k0 + t * 2);
+        const uint32_t a1 = *reinterpret_cast<const uint32_t*>(sq + (r0 + g + 8) * QK_LD + k0 + t * 2);
+        const uint32_t a2 = *reinterpret_cast<const uint32_t*>(sq + (r0 + g) * QK_LD + k0 + 8 + t * 2);
+        const uint32_t a3 = *reinterpret_cast<const uint32_t*>(sq + (r0 + g + 8) * QK_LD + k0 + 8 + t * 2);
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(sk + (j * 8 + g) * QK_LD + k0 + t * 2);
+            const uint32_t b1 = *reinterpret_cast<const uint32_t*>(sk + (j * 8 + g) * QK_LD + k0 + 8 + t * 2);
+            mma_bf16_16816(sc[j], a0, a1, a2, a3, b0, b1);
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        float sum = 0.f;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float e = (lane + 32 * j < S) ? exp2f(sc[j] - mx) : 0.f;
-            sc[j] = e;
-            sum += e;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        const float inv = 1.f / sum;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (lane + 32 * j < S) pr[lane + 32 * j] = sc[j] * inv;
-        __syncwarp();
-        for (int z = lane; z < d; z += 32) {
-            float o = 0.f;
-            for (int key = 0; key < S; ++key) o = fmaf(pr[key], v[key * dp + z], o);
-            out[(size_t)(img * S + t) * ld_out + head * d + z] = __float2bfloat16(o);
-        }
-        __syncwarp();
     }
+
+    // ---- softmax over the S valid keys (rows g and g+8 of this warp's block); thread owns cols j*8 + t*2 + {0,1}
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+        const int c = j * 8 + t * 2;
+        if (c < S) { mx0 = fmaxf(mx0, sc[j][0]); mx1 = fmaxf(mx1, sc[j][2]); }
+        if (c + 1 < S) { mx0 = fmaxf(mx0, sc[j][1]); mx1 = fmaxf(mx1, sc[j][3]); }
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+        const int c = j * 8 + t * 2;
+        const float e0 = (c < S) ? exp2f((sc[j][0] - mx0) * scale_log2e) : 0.f;
+        const float e1 = (c + 1 < S) ? exp2f((sc[j][1] - mx0) * scale_log2e) : 0.f;
+        const float e2 = (c < S) ? exp2f((sc[j][2] - mx1) * scale_log2e) : 0.f;
+        const float e3 = (c + 1 < S) ? exp2f((sc[j][3] - mx1) * scale_log2e) : 0.f;
+        sc[j][0] = e0; sc[j][1] = e1; sc[j][2] = e2; sc[j][3] = e3;
+        sum0 += e0 + e1;
+        sum1 += e2 + e3;
+    }
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+
+    // ---- O = P V : P (bf16, un-normalised, <= 1) comes straight from the score accumulators
+    constexpr int OT = D_PAD / 8;
+    float oc[OT][4];
+#pragma unroll
+    for (int j = 0; j < OT; ++j) oc[j][0] = oc[j][1] = oc[j][2] = oc[j][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < S_PAD / 16; ++kk) {
+        const uint32_t a0 = pack_bf16(sc[2 * kk][0], sc[2 * kk][1]);
+        const uint32_t a1 = pack_bf16(sc[2 * kk][2], sc[2 * kk][3]);
+        const uint32_t a2 = pack_bf16(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
+        const uint32_t a3 = pack_bf16(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
+#pragma unroll
+        for (int j = 0; j < OT; ++j) {
+            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(sv + (j * 8 + g) * VT_LD + kk * 16 + t * 2);
+            const uint32_t b1 = *reinterpret_cast<const uint32_t*>(sv + (j * 8 + g) * VT_LD + kk * 16 + 8 + t * 2);
+            mma_bf16_16816(oc[j], a0, a1, a2, a3, b0, b1);
+        }
+    }
+    const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
+    const int img = pair / heads, head = pair % heads;
+    const int row0 = r0 + g, row1 = r0 + g + 8;
+    bf16* o0 = out + (size_t)(img * S + row0) * ld_out + head * d;
+    bf16* o1 = out + (size_t)(img * S + row1) * ld_out + head * d;
+#pragma unroll
+    for (int j = 0; j < OT; ++j) {
+        const int c = j * 8 + t * 2;
+        if (row0 < S) {
+            if (c < d) o0[c] = __float2bfloat16(oc[j][0] * inv0);
+            if (c + 1 < d) o0[c + 1] = __float2bfloat16(oc[j][1] * inv0);
+        }
+        if (row1 < S) {
+            if (c < d) o1[c] = __float2bfloat16(oc[j][2] * inv1);
+            if (c + 1 < d) o1[c + 1] = __float2bfloat16(oc[j][3] * inv1);
+        }
+    }
+}
+
+template <int S_PAD, int D_PAD, int PAIRS>
+int launch_cfg(const bf16* qkv, bf16* out, int n_pairs, int S, int d, int heads, int ld_qkv, int ld_out, float scale,
+               cudaStream_t stream) {
+    using Cfg = AttnCfg<S_PAD, D_PAD, PAIRS>;
+    static bool configured = false;
+    if (!configured) {
+        SUNB_CHECK_CUDA(cudaFuncSetAttribute(attention_mma_kernel<S_PAD, D_PAD, PAIRS>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        configured = true;
+    }
+    const int blocks = (n_pairs + PAIRS - 1) / PAIRS;
+    attention_mma_kernel<S_PAD, D_PAD, PAIRS><<<blocks, Cfg::THREADS, Cfg::SMEM, stream>>>(
+        qkv, out, n_pairs, S, d, heads, ld_qkv, ld_out, scale * 1.4426950408889634f);
+    SUNB_CHECK_CUDA(cudaGetLastError());
+    return SUNB_OK;
 }
 
 }  // namespace
 
 int sunb_launch_attention(const bf16* qkv, bf16* out, int B, int S, int d, int heads, int ld_qkv, int ld_out,
                           cudaStream_t stream) {
-    SUNB_REQUIRE(S > 0 && S <= 128 && d > 0 && heads > 0, "attention: unsupported S=%d d=%d", S, d);
-    const int dp = d | 1;
-    const size_t smem = (size_t)(3 * S * dp + ATT_WARPS * S) * sizeof(float);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        SUNB_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    SUNB_REQUIRE(B > 0 && heads > 0, "attention: empty problem");
     const float scale = 1.0f / sqrtf((float)d);
-    attention_kernel<<<B * heads, ATT_WARPS * 32, smem, stream>>>(qkv, out, S, d, heads, ld_qkv, ld_out,
-                                                                  scale * 1.4426950408889634f);
-    SUNB_CHECK_CUDA(cudaGetLastError());
-    return SUNB_OK;
+    const int n_pairs = B * heads;
+    if (S <= 32 && d <= 96 && d > 48) return launch_cfg<32, 96, 4>(qkv, out, n_pairs, S, d, heads, ld_qkv, ld_out, scale, stream);
+    if (S <= 32 && d <= 48) return launch_cfg<32, 48, 4>(qkv, out, n_pairs, S, d, heads, ld_qkv, ld_out, scale, stream);
+    if (S <= 112 && d <= 48) return launch_cfg<112, 48, 1>(qkv, out, n_pairs, S, d, heads, ld_qkv, ld_out, scale, stream);
+    if (S <= 112 && d <= 96) return launch_cfg<112, 96, 1>(qkv, out, n_pairs, S, d, heads, ld_qkv, ld_out, scale, stream);
+    sunb_set_error("attention: unsupported shape S=%d d=%d (supported: S <= 112, d <= 96)", S, d);
+    return SUNB_ERR_ARG;
 }

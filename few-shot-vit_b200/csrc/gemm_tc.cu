@@ -1,9 +1,10 @@
 // tcgen05 / TMEM / TMA implicit-GEMM kernel for sm_100a.
 //
-// One CTA computes a 128 x BN output tile.  Warp roles (192 threads):
+// Persistent kernel, one CTA per SM, 128 x BN output tiles.  Warp roles (320 threads):
 //   warp 0   : TMA producer  (cp.async.bulk.tensor into a STAGES-deep ring of 128B-swizzled K-major tiles)
-//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (fp32 accumulator in TMEM)
-//   warps 2-5: epilogue (tcgen05.ld -> bias / residual / activation -> bf16 or fp32 global stores)
+//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (two fp32 accumulators in TMEM, ping-pong)
+//   warps 2-9: epilogue (tcgen05.ld -> bias / residual / activation -> bf16 or fp32 global stores), overlapped
+//              with the MMAs of the next tile
 // The K loop runs over taps x 64-wide K blocks: a 3x3 convolution is nine shifted 4-D TMA box loads of the
 // NHWC activation (TMA zero-fills the padding), a 1x1 convolution / linear layer is the taps == 1 case.
 #include "common.cuh"
@@ -14,13 +15,17 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;                      // 64 bf16 = one 128-byte swizzle row
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;   // TMA warp, MMA warp, 8 epilogue warps
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -113,43 +118,48 @@ struct SmemLayout {
     static constexpr int A_BYTES = BM * BK * 2;     // 16 KB
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 3 : 4);
+    static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);   // ~192 KB ring, one persistent CTA per SM
     static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;
     static constexpr int BAR_BYTES = 256;
     static constexpr int TOTAL = TILE_BYTES + BAR_BYTES + 1024;   // + slack for 1024-byte alignment
 };
 
+// Persistent kernel: CTA b processes tiles b, b + gridDim.x, ...  (tile id = (m_tile * groups + g) * n_tiles + n_tile).
+// The smem ring runs continuously across tiles; two TMEM accumulators let the epilogue of tile i overlap the
+// MMAs of tile i + 1.
 template <int BN>
-__global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                              const __grid_constant__ CUtensorMap tmB,
-                                                              const GemmParams p) {
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                 const __grid_constant__ CUtensorMap tmB,
+                                                                 const GemmParams p, const int n_tiles,
+                                                                 const int total_tiles) {
     using L = SmemLayout<BN>;
     constexpr int STAGES = L::STAGES;
-    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;   // power of two >= 32 (BN in {64,128,256})
+    constexpr uint32_t TMEM_COLS = 2 * BN;           // two accumulators; 128 / 256 / 512 columns
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-    const uint32_t bars = smem_base + L::TILE_BYTES;            // full[STAGES], empty[STAGES], accum
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + L::TILE_BYTES + 8 * (2 * STAGES + 1));
+    const uint32_t bars = smem_base + L::TILE_BYTES;    // full[STAGES], empty[STAGES], acc_full[2], acc_empty[2]
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + L::TILE_BYTES + 8 * (2 * STAGES + 4));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * BN;
-    const int m_tile = blockIdx.y;
-    const int g = blockIdx.z;
     const int kpt = (p.K + BK - 1) / BK;
     const int nk = p.taps * kpt;
 
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
-    const uint32_t accum_bar = bars + 8u * (2 * STAGES);
+    auto acc_full = [&](int a) { return bars + 8u * (2 * STAGES + a); };
+    auto acc_empty = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
-        mbar_init(accum_bar, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(acc_full(a), 1);
+            mbar_init(acc_empty(a), NUM_EPI_WARPS);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {   // whole warp allocates TMEM, base address lands in shared memory
@@ -166,66 +176,89 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-            // conv geometry of this tile
             const int box = p.bw * p.bh;
             const int nsub = p.a_mode ? BM / box : 1;
             const int tiles_x = p.a_mode ? p.W / p.bw : 1;
             const int spi = p.a_mode ? tiles_x * (p.H / p.bh) : 1;
-            for (int kb = 0; kb < nk; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(empty_bar(s), ph ^ 1);
-                const uint32_t a_dst = smem_base + s * L::STAGE_BYTES;
-                const uint32_t b_dst = a_dst + L::A_BYTES;
-                mbar_expect_tx(full_bar(s), L::STAGE_BYTES);
-                const int tap = kb / kpt, kc = kb % kpt;
-                if (p.a_mode == 0) {
-                    tma_load_2d(a_dst, &tmA, full_bar(s), g * p.a_goff + kc * BK, m_tile * BM);
-                } else {
-                    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-                    for (int j = 0; j < nsub; ++j) {
-                        const int st = m_tile * nsub + j;
-                        const int img = st / spi, rem = st % spi;
-                        const int y0 = (rem / tiles_x) * p.bh, x0 = (rem % tiles_x) * p.bw;
-                        tma_load_4d(a_dst + j * box * 128, &tmA, full_bar(s), g * p.a_goff + kc * BK, x0 + dx,
-                                    y0 + dy, img);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int n0 = (tile % n_tiles) * BN;
+                const int g = (tile / n_tiles) % p.groups;
+                const int m_tile = tile / (n_tiles * p.groups);
+                for (int kb = 0; kb < nk; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(empty_bar(s), ph ^ 1);
+                    const uint32_t a_dst = smem_base + s * L::STAGE_BYTES;
+                    const uint32_t b_dst = a_dst + L::A_BYTES;
+                    mbar_expect_tx(full_bar(s), L::STAGE_BYTES);
+                    const int tap = kb / kpt, kc = kb % kpt;
+                    if (p.a_mode == 0) {
+                        tma_load_2d(a_dst, &tmA, full_bar(s), g * p.a_goff + kc * BK, m_tile * BM);
+                    } else {
+                        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                        for (int j = 0; j < nsub; ++j) {
+                            const int st = m_tile * nsub + j;
+                            const int img = st / spi, rem = st % spi;
+                            const int y0 = (rem / tiles_x) * p.bh, x0 = (rem % tiles_x) * p.bw;
+                            tma_load_4d(a_dst + j * box * 128, &tmA, full_bar(s), g * p.a_goff + kc * BK, x0 + dx,
+                                        y0 + dy, img);
+                        }
                     }
+                    tma_load_2d(b_dst, &tmB, full_bar(s), kc * BK, (g * p.taps + tap) * p.N + n0);
                 }
-                tma_load_2d(b_dst, &tmB, full_bar(s), kc * BK, (g * p.taps + tap) * p.N + n0);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(BM, BN);
-            for (int kb = 0; kb < nk; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(full_bar(s), ph);
+            uint32_t it = 0, lt = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+                const uint32_t acc = lt & 1, aph = (lt >> 1) & 1;
+                mbar_wait(acc_empty(acc), aph ^ 1);       // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t a_addr = smem_base + s * L::STAGE_BYTES;
-                const uint64_t a_desc = make_sw128_desc(a_addr);
-                const uint64_t b_desc = make_sw128_desc(a_addr + L::A_BYTES);
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < nk; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(full_bar(s), ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_base + s * L::STAGE_BYTES;
+                    const uint64_t a_desc = make_sw128_desc(a_addr);
+                    const uint64_t b_desc = make_sw128_desc(a_addr + L::A_BYTES);
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k)   // advance 32 bytes (2 x 16-byte units) per UMMA_K = 16
-                    umma_bf16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) ? 1u : 0u);
-                umma_commit(empty_bar(s));            // frees the smem slot when these MMAs retire
+                    for (int k = 0; k < BK / 16; ++k)   // advance 32 bytes (2 x 16-byte units) per UMMA_K = 16
+                        umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                    umma_commit(empty_bar(s));            // frees the smem slot when these MMAs retire
+                }
+                umma_commit(acc_full(acc));               // accumulator complete
             }
-            umma_commit(accum_bar);                   // accumulator complete
         }
     } else {
-        // epilogue warps: TMEM lanes [32*(warp%4), +32) are accessible to warp `warp`
+        // epilogue warps 2..9: TMEM lanes [32*(warp%4), +32); the two warps of a lane quarter split the columns
         const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int r = q * 32 + lane;
-        mbar_wait(accum_bar, 0);
-        tc_fence_after();
-        // sub-boxes past the last image map to m >= M and are dropped by the epilogue
-        const int mm = p.a_mode ? conv_tile_row_to_pixel(p, m_tile, r) : m_tile * BM + r;
+        uint32_t lt = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+            const int n0 = (tile % n_tiles) * BN;
+            const int g = (tile / n_tiles) % p.groups;
+            const int m_tile = tile / (n_tiles * p.groups);
+            const uint32_t acc = lt & 1, aph = (lt >> 1) & 1;
+            mbar_wait(acc_full(acc), aph);
+            tc_fence_after();
+            // sub-boxes past the last image map to m >= M and are dropped by the epilogue
+            const int mm = p.a_mode ? conv_tile_row_to_pixel(p, m_tile, r) : m_tile * BM + r;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            if (n0 + c * 32 >= p.N) break;            // warp-uniform
-            float v[32];
-            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-            epilogue_row<32>(p, g, mm, n0 + c * 32, v);
+            for (int c = half; c < BN / 32; c += 2) {
+                if (n0 + c * 32 >= p.N) break;            // warp-uniform
+                float v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
+                epilogue_row<32>(p, g, mm, n0 + c * 32, v);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty(acc));
         }
     }
 
@@ -274,15 +307,31 @@ int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* d
     return SUNB_OK;
 }
 
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
 template <int BN>
-int launch_bn(const GemmParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB, dim3 grid, cudaStream_t stream) {
+int launch_bn(const GemmParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB, cudaStream_t stream) {
     using L = SmemLayout<BN>;
     static bool configured = false;
     if (!configured) {
         SUNB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         configured = true;
     }
-    gemm_tc_kernel<BN><<<grid, NUM_THREADS, L::TOTAL, stream>>>(tmA, tmB, p);
+    const int n_tiles = (p.N + BN - 1) / BN;
+    const int m_tiles = (p.M + BM - 1) / BM;
+    const long total = (long)n_tiles * m_tiles * p.groups;
+    SUNB_REQUIRE(total < (1L << 31), "gemm_tc: too many tiles");
+    const int grid = (int)(total < num_sms() ? total : num_sms());     // persistent: one CTA per SM
+    gemm_tc_kernel<BN><<<grid, NUM_THREADS, L::TOTAL, stream>>>(tmA, tmB, p, n_tiles, (int)total);
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
 }
@@ -292,10 +341,11 @@ int launch_bn(const GemmParams& p, const CUtensorMap& tmA, const CUtensorMap& tm
 int sunb_gemm_tc_pick_bn(const GemmParams& p) {
     if (p.N <= 64) return 64;
     if (p.N <= 128) return 128;
-    // prefer 256-wide tiles only when the grid still fills the machine
+    // 256-wide tiles halve the A re-reads; take them when the column padding is no worse and the grid still fills the SMs
     const long m_tiles = (p.M + BM - 1) / BM;
-    const long ctas256 = m_tiles * ((p.N + 255) / 256) * p.groups;
-    if (p.N % 256 == 0 && ctas256 >= 2 * 148) return 256;
+    const long n256 = (p.N + 255) / 256, n128 = (p.N + 127) / 128;
+    const double util256 = (double)p.N / (n256 * 256), util128 = (double)p.N / (n128 * 128);
+    if (util256 >= util128 - 0.03 && m_tiles * n256 * p.groups >= 148) return 256;
     return 128;
 }
 
@@ -329,11 +379,9 @@ int sunb_launch_gemm_tc(const GemmParams& p, cudaStream_t stream) {
         cuuint32_t box[2] = {BK, (cuuint32_t)BN};
         SUNB_TRY(encode_map(&tmB, p.Wt, 2, dims, strides, box));
     }
-    const int m_tiles = (p.M + BM - 1) / BM;
-    dim3 grid((p.N + BN - 1) / BN, m_tiles, p.groups);
     switch (BN) {
-        case 64: return launch_bn<64>(p, tmA, tmB, grid, stream);
-        case 128: return launch_bn<128>(p, tmA, tmB, grid, stream);
-        default: return launch_bn<256>(p, tmA, tmB, grid, stream);
+        case 64: return launch_bn<64>(p, tmA, tmB, stream);
+        case 128: return launch_bn<128>(p, tmA, tmB, stream);
+        default: return launch_bn<256>(p, tmA, tmB, stream);
     }
 }

@@ -64,7 +64,7 @@ def test_layer_boundaries_calibrated_weights():
     report = [(n, rel_err(taps[n].float().cpu(), r.permute(0, 2, 3, 1))) for n, r in taps_o.items()]
     report.append(("pooled", rel_err(pooled.cpu(), pooled_o)))
     print("\n".join(f"{n:18s} rel_l2 {e:.3e}" for n, e in report))
-    bad = [(n, e) for n, e in report if not e < 2e-2]
+    bad = [(n, e) for n, e in report if not e < 3e-2]
     assert not bad, bad
 
 
