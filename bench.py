@@ -168,8 +168,13 @@ def time_dominant_kernel(model_state, device, peaks_tf):
     ms = e0.elapsed_time(e1) / reps
     flops = 2.0 * B * 1600 * 128 * 128 * 9
     achieved = flops / (ms * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):        # dram bytes per launch from the committed `ncu --set full` capture of this same launch
+        t = json.load(open(tpath))
+        traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
     return {"bound": "tensor", "kernel": "gemm_tc_kernel<128> (stem conv3 implicit GEMM, M=%d N=128 K=9x128)" % (B * 1600),
-            "achieved": achieved, "peak": peaks_tf, "unit": "TFLOP/s", "frac": achieved / peaks_tf, "traffic": None,
+            "achieved": achieved, "peak": peaks_tf, "unit": "TFLOP/s", "frac": achieved / peaks_tf, "traffic": traffic,
             "ms_per_launch": ms, "flops_per_launch": flops}
 
 
