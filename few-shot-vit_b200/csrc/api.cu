@@ -7,7 +7,7 @@
 
 // launchers defined in the other translation units
 int sunb_launch_stem_in(const float* x, const float* w1, const float* b1, const float* wd, const float* bd, bf16* a1,
-                        bf16* idn, int B, cudaStream_t stream);
+                        bf16* idn, int B, int lrelu, cudaStream_t stream);
 int sunb_launch_pool_pos(const bf16* in, const float* pos, bf16* out, int B, int H, int W, int C, cudaStream_t stream);
 int sunb_launch_attention(const bf16* qkv, bf16* out, int B, int S, int d, int heads, int ld_qkv, int ld_out,
                           cudaStream_t stream);
@@ -24,6 +24,11 @@ int sunb_launch_soft_ce_backward(const float* x, int ldx, const float* t, int ld
                                  const float* gout, float gscale, float* dx, int lddx, cudaStream_t stream);
 int sunb_launch_hard_ce_backward(const float* l, const long long* label, int R, int W, const float* gout, float gscale,
                                  float* dl, cudaStream_t stream);
+
+int sunb_launch_episode_logits_bwd(const float* feat_shot, const float* feat_query, const float* dlogits, float* dshot,
+                                   float* dquery, float* dtemp, int E, int way, int shot, int Q, int D, int metric,
+                                   const float* temp_dev, float temp_host, cudaStream_t stream);
+int sunb_launch_wgrad_tc(WgradParams p, cudaStream_t stream);
 
 static thread_local char g_err[512] = "";
 
@@ -137,6 +142,8 @@ int sunb_gemm(const SunbGemmDesc* d, int impl, void* stream) {
     p.out = reinterpret_cast<bf16*>(d->out); p.ldc = d->ldc;
     p.out_f32 = d->out_f32; p.ldc_f32 = d->ldc_f32;
     p.out_map = d->out_map; p.oH = d->oH; p.oW = d->oW;
+    p.out2 = reinterpret_cast<bf16*>(d->out2); p.ldc2 = d->ldc2;
+    p.dact_aux = reinterpret_cast<const bf16*>(d->dact_aux); p.ld_aux = d->ld_aux; p.dact = d->dact;
     SUNB_REQUIRE(p.taps >= 1 && p.groups >= 1, "sunb_gemm: taps/groups must be >= 1");
     SUNB_REQUIRE(p.out || p.out_f32, "sunb_gemm: no output buffer");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -166,7 +173,7 @@ int sunb_encoder_forward(const SunbEncoderWeights* w, const float* x, int B, voi
     const SunbEncoderTaps& tp = taps ? *taps : none;
 
     // ---- stem (visformer.py:220-239) + pos_embed1 (:431)
-    SUNB_TRY(sunb_launch_stem_in(x, w->stem_w1, w->stem_b1, w->stem_wd, w->stem_bd, ws.a1, ws.idn, B, st));
+    SUNB_TRY(sunb_launch_stem_in(x, w->stem_w1, w->stem_b1, w->stem_wd, w->stem_bd, ws.a1, ws.idn, B, 1, st));
     {
         GemmParams p = base_gemm(B * 1600, 128, 64, ws.a1, 64, w->stem_w2, 64, ws.a2, 128);
         p.taps = 9; p.a_mode = 1; p.H = 40; p.W = 40; p.bw = 8; p.bh = 8;
@@ -293,6 +300,42 @@ int sunb_soft_ce_backward(const float* x, int ldx, const float* target, int ldt,
     SUNB_REQUIRE(x && target && dx, "soft_ce_backward: null argument");
     return sunb_launch_soft_ce_backward(x, ldx, target, ldt, R, Rt, C, gout, gscale, dx, lddx,
                                         reinterpret_cast<cudaStream_t>(stream));
+}
+
+int sunb_wgrad(const SunbWgradDesc* d, void* stream) {
+    SUNB_REQUIRE(d && d->dY && d->X && d->out, "sunb_wgrad: null argument");
+    WgradParams p;
+    p.P = d->P; p.Ma = d->Ma; p.Nb = d->Nb; p.Ca = d->Ca; p.Cb = d->Cb;
+    p.groups = d->groups > 0 ? d->groups : 1; p.a_goff = d->a_goff; p.b_goff = d->b_goff;
+    p.taps = d->taps > 0 ? d->taps : 1;
+    p.mode = d->mode; p.H = d->H; p.W = d->W; p.bw = d->bw; p.bh = d->bh;
+    p.dY = reinterpret_cast<const bf16*>(d->dY); p.ldy = d->ldy;
+    p.X = reinterpret_cast<const bf16*>(d->X); p.ldx = d->ldx;
+    p.out = d->out; p.ldo = d->ldo; p.ksplit = d->ksplit;
+    return sunb_launch_wgrad_tc(p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int sunb_stem_in(const float* x, const float* w1, const float* b1, const float* wd, const float* bd, void* a1, void* idn,
+                 int B, int lrelu, void* stream) {
+    SUNB_REQUIRE(x && w1 && b1 && wd && bd && a1 && idn, "stem_in: null argument");
+    return sunb_launch_stem_in(x, w1, b1, wd, bd, reinterpret_cast<bf16*>(a1), reinterpret_cast<bf16*>(idn), B, lrelu,
+                               reinterpret_cast<cudaStream_t>(stream));
+}
+
+int sunb_final_norm_pool(const void* x, const float* scale, const float* shift, float* dense, void* dense_bf16,
+                         float* pooled, void* pooled_bf16, int B, int T, int C, void* stream) {
+    SUNB_REQUIRE(x && scale && shift && pooled, "final_norm_pool: null argument");
+    return sunb_launch_final_norm_pool(reinterpret_cast<const bf16*>(x), scale, shift, dense,
+                                       reinterpret_cast<bf16*>(dense_bf16), pooled, reinterpret_cast<bf16*>(pooled_bf16), B, T,
+                                       C, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int sunb_episode_logits_backward(const float* feat_shot, const float* feat_query, const float* dlogits, float* dshot,
+                                 float* dquery, float* dtemp, int E, int way, int shot, int Q, int D, int metric,
+                                 const float* temp_dev, float temp_host, void* stream) {
+    SUNB_REQUIRE(feat_shot && feat_query && dlogits && dshot && dquery, "episode_logits_backward: null argument");
+    return sunb_launch_episode_logits_bwd(feat_shot, feat_query, dlogits, dshot, dquery, dtemp, E, way, shot, Q, D, metric,
+                                          temp_dev, temp_host, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -68,6 +68,10 @@ struct GemmParams {
     bf16* out; int ldc;                   // bf16 output (nullable)
     float* out_f32; int ldc_f32;          // fp32 output (nullable)
     int out_map, oH, oW;
+    // training extras
+    bf16* out2; int ldc2;                 // pre-activation copy (value before `act`), bf16, nullable
+    const bf16* dact_aux; int ld_aux;     // backward: multiply the result by act'(aux[m, col]) of kind `dact`
+    int dact;
 };
 
 // erf via Abramowitz & Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the bf16 output resolution): one ex2, one rcp
@@ -87,6 +91,16 @@ __device__ __forceinline__ float act_apply(float v, int act) {
     if (act == ACT_LRELU) return v > 0.f ? v : 0.1f * v;
     if (act == ACT_GELU) return 0.5f * v * (1.f + erf_fast(v * 0.70710678118654752f));
     return v;
+}
+
+// derivative of the activation evaluated at the saved tensor (GELU: pre-activation; LeakyReLU: either side of it)
+__device__ __forceinline__ float act_grad(float x, int act) {
+    if (act == ACT_LRELU) return x > 0.f ? 1.f : 0.1f;
+    if (act == ACT_GELU) {
+        const float cdf = 0.5f * (1.f + erf_fast(x * 0.70710678118654752f));
+        return cdf + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+    }
+    return 1.f;
 }
 
 // raster row of tile-row r (conv mode tiles are made of (bw x bh) sub-boxes)
@@ -141,12 +155,24 @@ __device__ __forceinline__ void epilogue_row(const GemmParams& p, int g, int m, 
 #pragma unroll
         for (int i = 0; i < NC; ++i) v[i] *= rs;
     }
+    const int orow = map_out_row(p, m);
+    if (p.out2) {                                   // training forward: keep the pre-activation for the backward pass
+        bf16* o2 = p.out2 + (size_t)orow * p.ldc2 + gcol;
+#pragma unroll
+        for (int i = 0; i < NC; ++i)
+            if (i < ncol) o2[i] = __float2bfloat16(v[i] + (bias ? bias[i] : 0.f));
+    }
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
         float b = (bias && i < ncol) ? bias[i] : 0.f;
         v[i] = act_apply(v[i] + b, p.act);
     }
-    const int orow = map_out_row(p, m);
+    if (p.dact_aux) {                               // backward: chain through the activation of the producing layer
+        const bf16* ax = p.dact_aux + (size_t)m * p.ld_aux + gcol;
+#pragma unroll
+        for (int i = 0; i < NC; ++i)
+            if (i < ncol) v[i] *= act_grad(__bfloat162float(ax[i]), p.dact);
+    }
     if (p.out) {
         bf16* o = p.out + (size_t)orow * p.ldc + gcol;
         if (full && (NC % 8 == 0) && ((((size_t)o) & 15) == 0)) {
@@ -171,6 +197,19 @@ __device__ __forceinline__ void epilogue_row(const GemmParams& p, int g, int m, 
             if (i < ncol) o[i] = v[i];
     }
 }
+
+struct WgradParams {
+    int P;                    // reduction length: pixel rows (2-D mode) or B*H*W (conv mode)
+    int Ma, Nb;               // output rows (= dY channels) and columns (= X channels) per group
+    int Ca, Cb;               // channel extents of the dY / X buffers (TMA zero-fills beyond them)
+    int groups, a_goff, b_goff;
+    int taps;                 // 1 or 9
+    int mode, H, W, bw, bh;   // mode 1: X is shifted per tap over an NHWC [B,H,W,ldx] image
+    const bf16* dY; int ldy;
+    const bf16* X; int ldx;
+    float* out; int ldo;      // [groups][taps][Ma][ldo]
+    int ksplit;
+};
 
 // launchers (gemm_tc.cu / gemm_simt.cu)
 int sunb_launch_gemm_tc(const GemmParams& p, cudaStream_t stream);

@@ -159,3 +159,123 @@ int sunb_launch_logits_ce_acc(const float* logits, const long long* label, int R
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Backward of episode_logits (autograd of meta_baseline.py:36-46 / utils.compute_logits): one block per episode.
+//   dfeat_shot [E,way,shot,D], dfeat_query [E,Q,D], dtemp (scalar, atomically accumulated) from dlogits [E,Q,way].
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void __launch_bounds__(256) episode_logits_bwd_kernel(const float* __restrict__ feat_shot,
+                                                                 const float* __restrict__ feat_query,
+                                                                 const float* __restrict__ dlogits,
+                                                                 float* __restrict__ dshot, float* __restrict__ dquery,
+                                                                 float* __restrict__ dtemp, int way, int shot, int Q, int D,
+                                                                 int metric, const float* __restrict__ temp_dev,
+                                                                 float temp_host) {
+    extern __shared__ float smh[];
+    float* proto = smh;                    // [way][D]  (normalised for cos)
+    float* dph = proto + way * D;          // [way][D]  gradient w.r.t. the (normalised) prototype
+    float* pinv = dph + way * D;           // [way]     1 / ||proto||
+    __shared__ float s_dtemp;
+    const int e = blockIdx.x;
+    const float temp = temp_dev ? *temp_dev : temp_host;
+    const float* fs = feat_shot + (size_t)e * way * shot * D;
+    if (threadIdx.x == 0) s_dtemp = 0.f;
+    for (int i = threadIdx.x; i < way * D; i += blockDim.x) {
+        const int w = i / D, dd = i % D;
+        float s = 0.f;
+        for (int k = 0; k < shot; ++k) s += fs[((size_t)w * shot + k) * D + dd];
+        proto[i] = s / (float)shot;
+        dph[i] = 0.f;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    for (int w = warp; w < way; w += nwarp) {
+        float inv = 1.f;
+        if (metric == 1) {
+            float ss = 0.f;
+            for (int dd = lane; dd < D; dd += 32) ss += proto[w * D + dd] * proto[w * D + dd];
+            ss = warp_sum(ss);
+            inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+            for (int dd = lane; dd < D; dd += 32) proto[w * D + dd] *= inv;
+        }
+        if (lane == 0) pinv[w] = inv;
+    }
+    __syncthreads();
+    float dt_local = 0.f;
+    for (int qi = warp; qi < Q; qi += nwarp) {
+        const float* fq = feat_query + ((size_t)e * Q + qi) * D;
+        const float* dl = dlogits + ((size_t)e * Q + qi) * way;
+        float qinv = 1.f;
+        if (metric == 1) {
+            float ss = 0.f;
+            for (int dd = lane; dd < D; dd += 32) ss += fq[dd] * fq[dd];
+            ss = warp_sum(ss);
+            qinv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+        }
+        float* dq = dquery + ((size_t)e * Q + qi) * D;
+        // dqh (gradient w.r.t. the normalised query) is accumulated per lane over its D/32 strided elements
+        float proj = 0.f;          // qhat . dqh  (cos only)
+        for (int dd = lane; dd < D; dd += 32) dq[dd] = 0.f;
+        for (int w = 0; w < way; ++w) {
+            const float g = dl[w];
+            float dot = 0.f;
+            for (int dd = lane; dd < D; dd += 32) {
+                const float qh = fq[dd] * qinv, ph = proto[w * D + dd];
+                if (metric == 2) {
+                    const float df = qh - ph;
+                    dot = fmaf(df, df, dot);
+                    dq[dd] += -2.f * temp * g * df;
+                    atomicAdd(&dph[w * D + dd], 2.f * temp * g * df);
+                } else {
+                    dot = fmaf(qh, ph, dot);
+                    dq[dd] += temp * g * ph;
+                    atomicAdd(&dph[w * D + dd], temp * g * qh);
+                }
+            }
+            dot = warp_sum(dot);
+            dt_local += g * (metric == 2 ? -dot : dot);
+        }
+        if (metric == 1) {
+            for (int dd = lane; dd < D; dd += 32) proj = fmaf(fq[dd] * qinv, dq[dd], proj);
+            proj = warp_sum(proj);
+            for (int dd = lane; dd < D; dd += 32) dq[dd] = (dq[dd] - fq[dd] * qinv * proj) * qinv;
+        }
+    }
+    if (lane == 0) atomicAdd(&s_dtemp, dt_local);
+    __syncthreads();
+    for (int w = warp; w < way; w += nwarp) {
+        float proj = 0.f;
+        if (metric == 1) {
+            for (int dd = lane; dd < D; dd += 32) proj = fmaf(proto[w * D + dd], dph[w * D + dd], proj);
+            proj = warp_sum(proj);
+        }
+        for (int dd = lane; dd < D; dd += 32) {
+            float g = dph[w * D + dd];
+            if (metric == 1) g = (g - proto[w * D + dd] * proj) * pinv[w];
+            g /= (float)shot;
+            for (int k = 0; k < shot; ++k) dshot[((size_t)(e * way + w) * shot + k) * D + dd] = g;
+        }
+    }
+    if (threadIdx.x == 0 && dtemp) atomicAdd(dtemp, s_dtemp);
+}
+
+}  // namespace
+
+int sunb_launch_episode_logits_bwd(const float* feat_shot, const float* feat_query, const float* dlogits, float* dshot,
+                                   float* dquery, float* dtemp, int E, int way, int shot, int Q, int D, int metric,
+                                   const float* temp_dev, float temp_host, cudaStream_t stream) {
+    SUNB_REQUIRE(E > 0 && way > 0 && shot > 0 && Q > 0 && D > 0 && metric >= 0 && metric <= 2, "episode_logits_bwd: bad shape");
+    const size_t smem = (size_t)(2 * way * D + way) * sizeof(float);
+    SUNB_REQUIRE(smem <= 200 * 1024, "episode_logits_bwd: way*D too large for shared memory");
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        SUNB_CHECK_CUDA(cudaFuncSetAttribute(episode_logits_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    episode_logits_bwd_kernel<<<E, 256, smem, stream>>>(feat_shot, feat_query, dlogits, dshot, dquery, dtemp, way, shot, Q, D,
+                                                        metric, temp_dev, temp_host);
+    SUNB_CHECK_CUDA(cudaGetLastError());
+    return SUNB_OK;
+}

@@ -15,7 +15,7 @@ constexpr int IMG = 80, OUT = 40, C1 = 64, CD = 128;
 __global__ void __launch_bounds__(128) stem_in_kernel(const float* __restrict__ x, const float* __restrict__ w1,
                                                       const float* __restrict__ b1, const float* __restrict__ wd,
                                                       const float* __restrict__ bd, bf16* __restrict__ a1,
-                                                      bf16* __restrict__ idn, int B) {
+                                                      bf16* __restrict__ idn, int B, int lrelu) {
     __shared__ float in[3][3][IMG + 2];     // [channel][input row ky][x + 1], zero padded
     const int img = blockIdx.x / OUT, oy = blockIdx.x % OUT;
     for (int i = threadIdx.x; i < 3 * 3 * (IMG + 2); i += blockDim.x) {
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(128) stem_in_kernel(const float* __restrict__ 
                     s2 = fmaf(v, kd0[wi], s2);
                     s3 = fmaf(v, kd1[wi], s3);
                 }
-        s1 = s1 > 0.f ? s1 : 0.1f * s1;
+        if (lrelu) s1 = s1 > 0.f ? s1 : 0.1f * s1;
         const size_t px = (size_t)(img * OUT + oy) * OUT + ox;
         a1[px * C1 + c] = __float2bfloat16(s1);
         idn[px * CD + c] = __float2bfloat16(s2);
@@ -91,9 +91,9 @@ __global__ void pool_pos_kernel(const bf16* __restrict__ in, const float* __rest
 }  // namespace
 
 int sunb_launch_stem_in(const float* x, const float* w1, const float* b1, const float* wd, const float* bd, bf16* a1,
-                        bf16* idn, int B, cudaStream_t stream) {
+                        bf16* idn, int B, int lrelu, cudaStream_t stream) {
     SUNB_REQUIRE(B > 0, "stem_in: B must be positive");
-    stem_in_kernel<<<B * OUT, 128, 0, stream>>>(x, w1, b1, wd, bd, a1, idn, B);
+    stem_in_kernel<<<B * OUT, 128, 0, stream>>>(x, w1, b1, wd, bd, a1, idn, B, lrelu);
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
 }

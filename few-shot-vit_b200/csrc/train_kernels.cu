@@ -1,0 +1,529 @@
+// Train-mode support kernels: batch-statistics BatchNorm (forward and backward), max-pool tail of the stem,
+// DropPath row scaling, layout helpers and weight preparation.  All HBM-bound, NHWC bf16 activations, fp32 statistics.
+// Reference semantics: nn.BatchNorm2d in training mode (test_phase/models/visformer.py:118-124),
+// ConvBlock tail (visformer.py:232-237), drop_path (visformer.py:89-97).
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// column statistics over rows:  sum[c] += sum_m x[m,c];  sq[c] += sum_m x[m,c]^2  (u == null)  or  x[m,c]*u[m,c]
+// block = 256 threads = (256 / (C/8)) row lanes x (C/8) vectors of 8 channels; requires C % 8 == 0, C/8 <= 256
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) colstats_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ u,
+                                                       int ldu, int M, int C, int rows_per_block,
+                                                       float* __restrict__ sum, float* __restrict__ sq) {
+    extern __shared__ float red[];          // [2][256][8]
+    const int nvec = C / 8;
+    const int lanes = 256 / nvec;
+    const int vec = threadIdx.x % nvec, rl = threadIdx.x / nvec;
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+    const int m0 = blockIdx.x * rows_per_block;
+    const int m1 = min(m0 + rows_per_block, M);
+    if (rl < lanes) {
+        for (int m = m0 + rl; m < m1; m += lanes) {
+            const uint4 a = *reinterpret_cast<const uint4*>(x + (size_t)m * ldx + vec * 8);
+            const bf16* ah = reinterpret_cast<const bf16*>(&a);
+            if (u) {
+                const uint4 b = *reinterpret_cast<const uint4*>(u + (size_t)m * ldu + vec * 8);
+                const bf16* bh = reinterpret_cast<const bf16*>(&b);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float v = __bfloat162float(ah[j]);
+                    s[j] += v;
+                    q[j] = fmaf(v, __bfloat162float(bh[j]), q[j]);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float v = __bfloat162float(ah[j]);
+                    s[j] += v;
+                    q[j] = fmaf(v, v, q[j]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        red[threadIdx.x * 8 + j] = s[j];
+        red[2048 + threadIdx.x * 8 + j] = q[j];
+    }
+    __syncthreads();
+    // thread t < C reduces channel t over the row lanes
+    for (int c = threadIdx.x; c < C; c += 256) {
+        const int v = c / 8, j = c % 8;
+        float a = 0.f, b = 0.f;
+        for (int l = 0; l < lanes; ++l) {
+            a += red[(l * nvec + v) * 8 + j];
+            b += red[2048 + (l * nvec + v) * 8 + j];
+        }
+        atomicAdd(sum + c, a);
+        atomicAdd(sq + c, b);
+    }
+}
+
+// one thread per channel: batch mean / biased var -> scale, shift; running stats with the unbiased var
+__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sq, float count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ rmean, float* __restrict__ rvar, long long* __restrict__ nbt,
+                                   float momentum, float eps, int C, float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && nbt) *nbt += 1;
+    if (c >= C) return;
+    const float mean = sum[c] / count;
+    const float var = fmaxf(sq[c] / count - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    const float s = gamma[c] * rstd;
+    scale[c] = s;
+    shift[c] = beta[c] - mean * s;
+    mean_out[c] = mean;
+    rstd_out[c] = rstd;
+    if (rmean) {
+        rmean[c] = (1.f - momentum) * rmean[c] + momentum * mean;
+        rvar[c] = (1.f - momentum) * rvar[c] + momentum * var * (count / fmaxf(count - 1.f, 1.f));
+    }
+}
+
+// y = act(x*scale + shift) + tab[(m % tab_mod)][c]   (tab nullable); vector of 8 channels per thread
+__global__ void bn_apply_kernel(const bf16* __restrict__ x, int ldx, const float* __restrict__ scale,
+                                const float* __restrict__ shift, int act, const float* __restrict__ tab, int tab_mod,
+                                bf16* __restrict__ out, int ldo, long M, int C) {
+    const int nvec = C / 8;
+    const long total = M * nvec;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long m = i / nvec;
+        const int c0 = (int)(i % nvec) * 8;
+        const uint4 a = *reinterpret_cast<const uint4*>(x + m * ldx + c0);
+        const bf16* ah = reinterpret_cast<const bf16*>(&a);
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = act_apply(fmaf(__bfloat162float(ah[j]), scale[c0 + j], shift[c0 + j]), act);
+        if (tab) {
+            const float* t = tab + (size_t)(m % tab_mod) * C + c0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += t[j];
+        }
+        uint4 o;
+        __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+        *reinterpret_cast<uint4*>(out + m * ldo + c0) = o;
+    }
+}
+
+// stem tail forward: out = maxpool2x2( lrelu( c3*s3+t3 + id*sd+td ) ) + pos
+__global__ void stem_tail_fwd_kernel(const bf16* __restrict__ c3, const bf16* __restrict__ idn,
+                                     const float* __restrict__ s3, const float* __restrict__ t3,
+                                     const float* __restrict__ sd, const float* __restrict__ td,
+                                     const float* __restrict__ pos, bf16* __restrict__ out, int B, int H, int W, int C) {
+    const int oH = H / 2, oW = W / 2, cv = C / 8;
+    const long total = (long)B * oH * oW * cv;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % cv) * 8;
+        const long px = i / cv;
+        const int ox = (int)(px % oW), oy = (int)((px / oW) % oH), img = (int)(px / ((long)oW * oH));
+        float m[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            const size_t off = ((size_t)(img * H + 2 * oy + (d >> 1)) * W + 2 * ox + (d & 1)) * C + c0;
+            const uint4 a = *reinterpret_cast<const uint4*>(c3 + off);
+            const uint4 b = *reinterpret_cast<const uint4*>(idn + off);
+            const bf16* ah = reinterpret_cast<const bf16*>(&a);
+            const bf16* bh = reinterpret_cast<const bf16*>(&b);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float z = fmaf(__bfloat162float(ah[j]), s3[c0 + j], t3[c0 + j]) +
+                          fmaf(__bfloat162float(bh[j]), sd[c0 + j], td[c0 + j]);
+                z = z > 0.f ? z : 0.1f * z;
+                m[j] = fmaxf(m[j], z);
+            }
+        }
+        const float* pp = pos + (size_t)(oy * oW + ox) * C + c0;
+        uint4 o;
+        __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(m[2 * j] + pp[2 * j], m[2 * j + 1] + pp[2 * j + 1]);
+        *reinterpret_cast<uint4*>(out + (size_t)px * C + c0) = o;
+    }
+}
+
+// stem tail backward: dz[full res] = g[pooled] * lrelu'(z) at the arg-max of each 2x2 window (first max in scan order), else 0
+__global__ void stem_tail_bwd_kernel(const bf16* __restrict__ c3, const bf16* __restrict__ idn,
+                                     const float* __restrict__ s3, const float* __restrict__ t3,
+                                     const float* __restrict__ sd, const float* __restrict__ td,
+                                     const bf16* __restrict__ g, bf16* __restrict__ dz, int B, int H, int W, int C) {
+    const int oH = H / 2, oW = W / 2, cv = C / 8;
+    const long total = (long)B * oH * oW * cv;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % cv) * 8;
+        const long px = i / cv;
+        const int ox = (int)(px % oW), oy = (int)((px / oW) % oH), img = (int)(px / ((long)oW * oH));
+        float best[8];
+        int arg[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; arg[j] = 0; }
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            const size_t off = ((size_t)(img * H + 2 * oy + (d >> 1)) * W + 2 * ox + (d & 1)) * C + c0;
+            const uint4 a = *reinterpret_cast<const uint4*>(c3 + off);
+            const uint4 b = *reinterpret_cast<const uint4*>(idn + off);
+            const bf16* ah = reinterpret_cast<const bf16*>(&a);
+            const bf16* bh = reinterpret_cast<const bf16*>(&b);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float z = fmaf(__bfloat162float(ah[j]), s3[c0 + j], t3[c0 + j]) +
+                          fmaf(__bfloat162float(bh[j]), sd[c0 + j], td[c0 + j]);
+                z = z > 0.f ? z : 0.1f * z;                   // lrelu is monotonic: arg-max is unchanged
+                if (z > best[j]) { best[j] = z; arg[j] = d; }
+            }
+        }
+        const uint4 gg = *reinterpret_cast<const uint4*>(g + (size_t)px * C + c0);
+        const bf16* gh = reinterpret_cast<const bf16*>(&gg);
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            uint4 o;
+            bf16* oh = reinterpret_cast<bf16*>(&o);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float slope = best[j] > 0.f ? 1.f : 0.1f;
+                oh[j] = __float2bfloat16(arg[j] == d ? __bfloat162float(gh[j]) * slope : 0.f);
+            }
+            const size_t off = ((size_t)(img * H + 2 * oy + (d >> 1)) * W + 2 * ox + (d & 1)) * C + c0;
+            *reinterpret_cast<uint4*>(dz + off) = o;
+        }
+    }
+}
+
+// BN backward coefficients.  dx = a*(dz - c1 - (x - mean)*c2);  dgamma = rstd*(sum(dz*x) - mean*sum(dz));  dbeta = sum(dz)
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ sdz, const float* __restrict__ sdzx, float count,
+                                       const float* __restrict__ mean, const float* __restrict__ rstd,
+                                       const float* __restrict__ gamma, int C, float* __restrict__ a,
+                                       float* __restrict__ c1, float* __restrict__ c2, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float cen = sdzx[c] - mean[c] * sdz[c];        // sum dz*(x-mean)
+    a[c] = gamma[c] * rstd[c];
+    c1[c] = sdz[c] / count;
+    c2[c] = rstd[c] * rstd[c] * cen / count;
+    dgamma[c] += rstd[c] * cen;
+    dbeta[c] += sdz[c];
+}
+
+// dx = a*(dz - c1 - (x - mean)*c2) + res     (res nullable)
+__global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dz, int lddz, const bf16* __restrict__ x, int ldx,
+                                    const float* __restrict__ a, const float* __restrict__ c1,
+                                    const float* __restrict__ c2, const float* __restrict__ mean,
+                                    const bf16* __restrict__ res, int ldr, bf16* __restrict__ out, int ldo, long M, int C) {
+    const int nvec = C / 8;
+    const long total = M * nvec;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long m = i / nvec;
+        const int c0 = (int)(i % nvec) * 8;
+        const uint4 d4 = *reinterpret_cast<const uint4*>(dz + m * lddz + c0);
+        const uint4 x4 = *reinterpret_cast<const uint4*>(x + m * ldx + c0);
+        const bf16* dh = reinterpret_cast<const bf16*>(&d4);
+        const bf16* xh = reinterpret_cast<const bf16*>(&x4);
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            v[j] = a[c0 + j] * (__bfloat162float(dh[j]) - c1[c0 + j] - (__bfloat162float(xh[j]) - mean[c0 + j]) * c2[c0 + j]);
+        if (res) {
+            const uint4 r4 = *reinterpret_cast<const uint4*>(res + m * ldr + c0);
+            const bf16* rh = reinterpret_cast<const bf16*>(&r4);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += __bfloat162float(rh[j]);
+        }
+        uint4 o;
+        __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+        *reinterpret_cast<uint4*>(out + m * ldo + c0) = o;
+    }
+}
+
+// out[r, c] = in[r, c] * rs[r / rows_per_img]
+__global__ void scale_rows_kernel(const bf16* __restrict__ in, const float* __restrict__ rs, int rows_per_img,
+                                  bf16* __restrict__ out, long M, int C) {
+    const int nvec = C / 8;
+    const long total = M * nvec;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long m = i / nvec;
+        const float s = rs[m / rows_per_img];
+        const uint4 a = *reinterpret_cast<const uint4*>(in + i * 8);
+        const bf16* ah = reinterpret_cast<const bf16*>(&a);
+        uint4 o;
+        __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            oh[j] = __floats2bfloat162_rn(__bfloat162float(ah[2 * j]) * s, __bfloat162float(ah[2 * j + 1]) * s);
+        *reinterpret_cast<uint4*>(out + i * 8) = o;
+    }
+}
+
+// out[s2d_row(m)] <- in[m] (dir 0: raster -> space-to-depth) or out[m] <- in[s2d_row(m)] (dir 1), rows of C channels
+__global__ void s2d_reorder_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int B, int H, int W, int C, int dir) {
+    const int nvec = C / 8;
+    const long total = (long)B * H * W * nvec;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long m = i / nvec;
+        const int v = (int)(i % nvec);
+        const int hw = H * W;
+        const int img = (int)(m / hw), rem = (int)(m % hw), y = rem / W, x = rem % W;
+        const long sm = ((long)(img * (H / 2) + y / 2) * (W / 2) + x / 2) * 4 + (y & 1) * 2 + (x & 1);
+        const long src = dir ? sm : m, dst = dir ? m : sm;
+        *reinterpret_cast<uint4*>(out + dst * C + v * 8) = *reinterpret_cast<const uint4*>(in + src * C + v * 8);
+    }
+}
+
+// out[i] += sum_b g[b, i]   (i over S*C), fp32 accumulate -- gradient of a broadcast positional embedding
+__global__ void batch_sum_kernel(const bf16* __restrict__ g, int B, long n, float* __restrict__ out) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        float a = 0.f;
+        for (int b = 0; b < B; ++b) a += __bfloat162float(g[(size_t)b * n + i]);
+        out[i] += a;
+    }
+}
+
+// generic permute + cast: dst[a][b][c] (bf16, contiguous, last dim padded to ldd) = src[off + a*sa + b*sb + c*sc] (fp32)
+__global__ void permute_cast_kernel(const float* __restrict__ src, long off, long sa, long sb, long sc, int A, int Bd,
+                                    int Cd, int ldd, bf16* __restrict__ dst) {
+    const long total = (long)A * Bd * ldd;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % ldd);
+        const long ab = i / ldd;
+        const int b = (int)(ab % Bd), a = (int)(ab / Bd);
+        dst[i] = __float2bfloat16(c < Cd ? src[off + a * sa + b * sb + c * sc] : 0.f);
+    }
+}
+
+// grouped 3x3 weight [256,32,3,3] (8 groups) -> block-diagonal channel pairs [4][9][64][64] (bf16).
+// transpose_flip = 0: forward operand  dst[p][tap][n][k] = W[p*64+n][k - 32*(n/32)][tap]   (zero off the diagonal)
+// transpose_flip = 1: dgrad operand    dst[p][tap][k_in][n_out] with tap mirrored (8 - tap): conv-transpose weights
+__global__ void grouped_pairs_kernel(const float* __restrict__ w, bf16* __restrict__ dst, int transpose_flip) {
+    const int total = 4 * 9 * 64 * 64;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int col = i % 64, row = (i / 64) % 64, tap = (i / 4096) % 9, p = i / (4096 * 9);
+        const int n = transpose_flip ? col : row;         // output channel within the pair
+        const int k = transpose_flip ? row : col;         // input channel within the pair
+        float v = 0.f;
+        if (n / 32 == k / 32) {
+            const int st = transpose_flip ? 8 - tap : tap;
+            v = w[((size_t)(p * 64 + n) * 32 + (k % 32)) * 9 + st];
+        }
+        dst[i] = __float2bfloat16(v);
+    }
+}
+
+// dW2[256][32][3][3] += diagonal 32x32 blocks of the pair-wise wgrad scratch [2 halves][9][128][128]
+__global__ void grouped_wgrad_extract_kernel(const float* __restrict__ scratch, float* __restrict__ dw) {
+    const int total = 256 * 32 * 9;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int tap = i % 9, ci = (i / 9) % 32, co = i / (9 * 32);
+        const int half = co / 128, r = co % 128, grp = r / 32;
+        dw[i] += scratch[((size_t)(half * 9 + tap) * 128 + r) * 128 + grp * 32 + ci];
+    }
+}
+
+// dy[b, t, c] = dpooled[b, c] / T (+ ddense[b, t, c])  -> bf16
+__global__ void pool_bwd_kernel(const float* __restrict__ dpooled, const float* __restrict__ ddense, bf16* __restrict__ dy,
+                                int B, int T, int C) {
+    const long total = (long)B * T * C;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const long b = i / ((long)T * C);
+        float v = dpooled ? dpooled[b * C + c] / (float)T : 0.f;
+        if (ddense) v += ddense[i];
+        dy[i] = __float2bfloat16(v);
+    }
+}
+
+// stem K=27 weight gradients: dW1[64][27] += sum_p da1[p, c] * patch(x)[p, :],  dWd[128][27] likewise from didn.
+// block = (image, 8 output rows), 192 threads = channel lanes (0..63 conv1, 64..191 downsample)
+constexpr int SW_ROWS = 8;
+__global__ void __launch_bounds__(192) stem_wgrad_kernel(const float* __restrict__ x, const bf16* __restrict__ da1,
+                                                         const bf16* __restrict__ didn, float* __restrict__ dw1,
+                                                         float* __restrict__ dwd, int B) {
+    __shared__ float in[3][2 * SW_ROWS + 1][82];
+    const int img = blockIdx.x / (40 / SW_ROWS), oy0 = (blockIdx.x % (40 / SW_ROWS)) * SW_ROWS;
+    for (int i = threadIdx.x; i < 3 * (2 * SW_ROWS + 1) * 82; i += blockDim.x) {
+        const int c = i / ((2 * SW_ROWS + 1) * 82), r = (i / 82) % (2 * SW_ROWS + 1), xx = i % 82;
+        const int iy = 2 * oy0 - 1 + r, ix = xx - 1;
+        in[c][r][xx] = (iy >= 0 && iy < 80 && ix >= 0 && ix < 80) ? x[((size_t)(img * 3 + c) * 80 + iy) * 80 + ix] : 0.f;
+    }
+    __syncthreads();
+    const int t = threadIdx.x;
+    float acc[27];
+#pragma unroll
+    for (int i = 0; i < 27; ++i) acc[i] = 0.f;
+    for (int r = 0; r < SW_ROWS; ++r) {
+        for (int ox = 0; ox < 40; ++ox) {
+            const size_t px = (size_t)(img * 40 + oy0 + r) * 40 + ox;
+            const float gv = t < 64 ? __bfloat162float(da1[px * 64 + t]) : __bfloat162float(didn[px * 128 + (t - 64)]);
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx)
+                        acc[(ci * 3 + ky) * 3 + kx] = fmaf(gv, in[ci][2 * r + ky][2 * ox + kx], acc[(ci * 3 + ky) * 3 + kx]);
+        }
+    }
+    float* dst = t < 64 ? dw1 + t * 27 : dwd + (t - 64) * 27;
+#pragma unroll
+    for (int i = 0; i < 27; ++i) atomicAdd(dst + i, acc[i]);
+}
+
+inline int grid_for(long total, int threads = 256) {
+    long b = (total + threads - 1) / threads;
+    const long cap = 148L * 16;
+    return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+}  // namespace
+
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int sunb_colstats(const void* x, int ldx, const void* u, int ldu, long M, int C, float* sum, float* sq, void* stream) {
+    SUNB_REQUIRE(x && sum && sq && M > 0, "colstats: bad arguments");
+    SUNB_REQUIRE(C % 8 == 0 && C / 8 <= 256 && ldx % 8 == 0, "colstats: C must be a multiple of 8 and <= 2048 (got %d)", C);
+    const int lanes = 256 / (C / 8);
+    int rpb = lanes * 16;
+    long blocks = (M + rpb - 1) / rpb;
+    if (blocks > 148L * 8) { rpb = (int)((M + 148L * 8 - 1) / (148L * 8)); rpb = (rpb + lanes - 1) / lanes * lanes; blocks = (M + rpb - 1) / rpb; }
+    colstats_kernel<<<(int)blocks, 256, 2 * 2048 * sizeof(float), ST(stream)>>>(
+        reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<const bf16*>(u), ldu, (int)M, C, rpb, sum, sq);
+    SUNB_CHECK_CUDA(cudaGetLastError());
+    return SUNB_OK;
+}
+
+int sunb_bn_finalize(const float* sum, const float* sq, float count, const float* gamma, const float* beta, float* rmean,
+                     float* rvar, int64_t* nbt, float momentum, float eps, int C, float* scale, float* shift, float* mean,
+                     float* rstd, void* stream) {
+    SUNB_REQUIRE(sum && sq && gamma && beta && scale && shift && mean && rstd && C > 0, "bn_finalize: bad arguments");
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(sum, sq, count, gamma, beta, rmean, rvar,
+                                                                 reinterpret_cast<long long*>(nbt), momentum, eps, C,
+                                                                 scale, shift, mean, rstd);
+    SUNB_CHECK_CUDA(cudaGetLastError());
+    return SUNB_OK;
+}
+
+int sunb_bn_apply(const void* x, int ldx, const float* scale, const float* shift, int act, const float* tab, int tab_mod,
+                  void* out, int ldo, long M, int C, void* stream) {
+    SUNB_REQUIRE(x && out && scale && shift && C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0, "bn_apply: bad arguments");
+    bn_apply_kernel<<<grid_for(M * (C / 8)), 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(x), ldx, scale, shift, act,
+                                                                    tab, tab_mod > 0 ? tab_mod : 1,
+                                                                    reinterpret_cast<bf16*>(out), ldo, M, C);
+    SUNB_CHECK_CUDA(cudaGetLastError());
+    return SUNB_OK;
+}
+
+int sunb_stem_tail_forward(const void* c3, const void* idn, const float* s3, const float* t3, const float* sd,
+                           const float* td, const float* pos, void* out, int B, void* stream) {
+    SUNB_REQUIRE(c3 && idn && out && pos, "stem_tail_forward: bad arguments");
+    stem_tail_fwd_kernel<<<grid_for((long)B * 400 * 16), 256, 0, ST(stream)>>>(
+        reinterpret_cast<const bf16*>(c3), reinterpret_cast<const bf16*>(idn), s3, t3, sd, td, pos,
+        reinterpret_cast<bf16*>(out), B, 40, 40, 128);
+    SUNB_CHECK_CUDA(cudaGetLastError());
+    return SUNB_OK;
+}
+
+int sunb_stem_tail_backward(const void* c3, const void* idn, const float* s3, const float* t3, const float* sd,
+                            const float* td, const void* g, void* dz, int B, void* stream) {
+    SUNB_REQUIRE(c3 && idn && g && dz, "stem_tail_backward: bad arguments");
+    stem_tail_bwd_kernel<<<grid_for((long)B * 400 * 16), 256, 0, ST(stream)>>>(
+        reinterpret_cast<const bf16*>(c3), reinterpret_cast<const bf16*>(idn), s3, t3, sd, td,
+        reinterpret_cast<const bf16*>(g), reinterpret_cast<bf16*>(dz), B, 40, 40, 128);
+    SUNB_CHECK_CUDA(cudaGetLastError());
+    return SUNB_OK;
+}
+
+int sunb_bn_bwd_finalize(const float* sdz, const float* sdzx, float count, const float* mean, const float* rstd,
+                         const float* gamma, int C, float* a, float* c1, float* c2, float* dgamma, float* dbeta,
+                         void* stream) {
+    SUNB_REQUIRE(sdz && sdzx && mean && rstd && gamma && a && c1 && c2 && dgamma && dbeta, "bn_bwd_finalize: bad arguments");
+    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(sdz, sdzx, count, mean, rstd, gamma, C, a, c1, c2, dgamma,
+                                                                     dbeta);
+    SUNB_CHECK_CUDA(cudaGetLastError());
+    return SUNB_OK;
+}
+
+int sunb_bn_bwd_apply(const void* dz, int lddz, const void* x, int ldx, const float* a, const float* c1, const float* c2,
+                      const float* mean, const void* res, int ldr, void* out, int ldo, long M, int C, void* stream) {
+    SUNB_REQUIRE(dz && x && out && C % 8 == 0, "bn_bwd_apply: bad arguments");
+    bn_bwd_apply_kernel<<<grid_for(M * (C / 8)), 256, 0, ST(stream)>>>(
+        reinterpret_cast<const bf16*>(dz), lddz, reinterpret_cast<const bf16*>(x), ldx, a, c1, c2, mean,
+        reinterpret_cast<const bf16*>(res), ldr, reinterpret_cast<bf16*>(out), ldo, M, C);
+    SUNB_CHECK_CUDA(cudaGetLastError());
+    return SUNB_OK;
+}
+
+int sunb_scale_rows(const void* in, const float* rs, int rows_per_img, void* out, long M, int C, void* stream) {
+    SUNB_REQUIRE(in && rs && out && C % 8 == 0 && rows_per_img > 0, "scale_rows: bad arguments");
+    scale_rows_kernel<<<grid_for(M * (C / 8)), 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(in), rs, rows_per_img,
+                                                                      reinterpret_cast<bf16*>(out), M, C);
+    SUNB_CHECK_CUDA(cudaGetLastError());
+    return SUNB_OK;
+}
+
+int sunb_s2d_reorder(const void* in, void* out, int B, int H, int W, int C, int dir, void* stream) {
+    SUNB_REQUIRE(in && out && C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "s2d_reorder: bad arguments");
+    s2d_reorder_kernel<<<grid_for((long)B * H * W * (C / 8)), 256, 0, ST(stream)>>>(
+        reinterpret_cast<const bf16*>(in), reinterpret_cast<bf16*>(out), B, H, W, C, dir);
+    SUNB_CHECK_CUDA(cudaGetLastError());
+    return SUNB_OK;
+}
+
+int sunb_batch_sum(const void* g, int B, long n, float* out, void* stream) {
+    SUNB_REQUIRE(g && out && B > 0 && n > 0, "batch_sum: bad arguments");
+    batch_sum_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(g), B, n, out);
+    SUNB_CHECK_CUDA(cudaGetLastError());
+    return SUNB_OK;
+}
+
+int sunb_permute_cast(const float* src, long off, long sa, long sb, long sc, int A, int B, int Cd, int ldd, void* dst,
+                      void* stream) {
+    SUNB_REQUIRE(src && dst && A > 0 && B > 0 && Cd > 0 && ldd >= Cd, "permute_cast: bad arguments");
+    permute_cast_kernel<<<grid_for((long)A * B * ldd), 256, 0, ST(stream)>>>(src, off, sa, sb, sc, A, B, Cd, ldd,
+                                                                              reinterpret_cast<bf16*>(dst));
+    SUNB_CHECK_CUDA(cudaGetLastError());
+    return SUNB_OK;
+}
+
+int sunb_grouped_pairs(const float* w, void* dst, int transpose_flip, void* stream) {
+    SUNB_REQUIRE(w && dst, "grouped_pairs: bad arguments");
+    grouped_pairs_kernel<<<grid_for(4 * 9 * 64 * 64), 256, 0, ST(stream)>>>(w, reinterpret_cast<bf16*>(dst), transpose_flip);
+    SUNB_CHECK_CUDA(cudaGetLastError());
+    return SUNB_OK;
+}
+
+int sunb_grouped_wgrad_extract(const float* scratch, float* dw, void* stream) {
+    SUNB_REQUIRE(scratch && dw, "grouped_wgrad_extract: bad arguments");
+    grouped_wgrad_extract_kernel<<<grid_for(256 * 32 * 9), 256, 0, ST(stream)>>>(scratch, dw);
+    SUNB_CHECK_CUDA(cudaGetLastError());
+    return SUNB_OK;
+}
+
+int sunb_pool_backward(const float* dpooled, const float* ddense, void* dy, int B, int T, int C, void* stream) {
+    SUNB_REQUIRE(dy && (dpooled || ddense), "pool_backward: bad arguments");
+    pool_bwd_kernel<<<grid_for((long)B * T * C), 256, 0, ST(stream)>>>(dpooled, ddense, reinterpret_cast<bf16*>(dy), B, T, C);
+    SUNB_CHECK_CUDA(cudaGetLastError());
+    return SUNB_OK;
+}
+
+int sunb_stem_wgrad(const float* x, const void* da1, const void* didn, float* dw1, float* dwd, int B, void* stream) {
+    SUNB_REQUIRE(x && da1 && didn && dw1 && dwd && B > 0, "stem_wgrad: bad arguments");
+    stem_wgrad_kernel<<<B * (40 / SW_ROWS), 192, 0, ST(stream)>>>(x, reinterpret_cast<const bf16*>(da1),
+                                                                   reinterpret_cast<const bf16*>(didn), dw1, dwd, B);
+    SUNB_CHECK_CUDA(cudaGetLastError());
+    return SUNB_OK;
+}
+
+}  // extern "C"

@@ -15,6 +15,7 @@ import torch.nn as nn
 
 from .models import register
 from sunb200.engine import EncoderEngine
+from sunb200.train import TrainEngine
 
 IMG, STEM_CH, EMBED, DEPTH, HEADS, GROUPS = 80, 64, 256, (4, 2, 3), 6, 8
 
@@ -108,6 +109,7 @@ class Visformer(nn.Module):
         self.norm = BatchNorm(d3)
         self._reset_parameters()
         self._engine = EncoderEngine()
+        self._train_engine = TrainEngine()
 
     def _reset_parameters(self):
         """Reference init distributions (visformer.py:398-422, conv_init=True)."""
@@ -125,18 +127,67 @@ class Visformer(nn.Module):
     def _bn_in_eval(self):
         return all(not m.training for m in self.modules() if isinstance(m, nn.BatchNorm2d))
 
-    def forward(self, x, taps=None):
-        if not self._bn_in_eval() or (self.training and self.drop_path_rate > 0):
-            raise NotImplementedError(
-                "sunb200: the train-mode encoder path (batch-statistics BatchNorm, DropPath, backward) is not built "
-                "yet; call .eval() for episodic evaluation.  There is deliberately no PyTorch fallback.")
-        state = dict(self.state_dict(keep_vars=True))
-        out = self._engine.forward(state, x, want_dense=self.output != "pooled", taps=taps)
-        pooled = out["pooled"]
+    def _drop_path_scales(self, batch, device):
+        """DropPath draws in the reference's forward order (visformer.py:89-97, 261-262): per block with rate > 0 one
+        draw for the attention branch (stages 2/3) and one for the MLP; scale = floor(keep + U[0,1)) / keep."""
+        rs = {}
+        for stage, blocks in (("stage1", self.stage1), ("stage2", self.stage2), ("stage3", self.stage3)):
+            for i, blk in enumerate(blocks):
+                if blk.drop_prob <= 0.0:
+                    continue
+                keep = 1.0 - blk.drop_prob
+                n = 1 if stage == "stage1" else 2
+                rs[f"{stage}.{i}"] = [torch.floor(keep + torch.rand(batch, 1, 1, 1, device=device)).div_(keep).view(batch)
+                                      for _ in range(n)]
+        return rs
+
+    def forward(self, x, taps=None, drop_path_scales=None):
+        bn_eval = self._bn_in_eval()
+        if not self.training or (bn_eval and not torch.is_grad_enabled()):
+            if not bn_eval:
+                raise NotImplementedError("sunb200: eval-mode module with BatchNorm layers switched to train() is not supported")
+            state = dict(self.state_dict(keep_vars=True))
+            out = self._engine.forward(state, x, want_dense=self.output != "pooled", taps=taps)
+            pooled, dense = out["pooled"], out["dense"]
+        else:
+            if bn_eval or any(not m.training for m in self.modules() if isinstance(m, nn.BatchNorm2d)):
+                raise NotImplementedError(
+                    "sunb200: training with frozen BatchNorm (utils.freeze_bn) is not built; the shipped SUN-M configs "
+                    "do not set freeze_bn.  There is deliberately no PyTorch fallback.")
+            rs = drop_path_scales if drop_path_scales is not None else self._drop_path_scales(x.shape[0], x.device)
+            names = [n for n, _ in self.named_parameters()]
+            params = [p for _, p in self.named_parameters()]
+            pooled, dense = _EncoderTrainFn.apply(self, x, rs, names, *params)
         if self.output == "pooled":
             return pooled
-        dense = out["dense"].permute(0, 3, 1, 2)       # NCHW view of NHWC memory (token_label.py:50 permutes it back)
+        dense = dense.permute(0, 3, 1, 2)              # NCHW view of NHWC memory (token_label.py:50 permutes it back)
         return (dense, pooled) if self.output == "both" else dense
+
+
+class _EncoderTrainFn(torch.autograd.Function):
+    """Train-mode encoder as one autograd node: forward and backward are the schedules in sunb200/train.py."""
+
+    @staticmethod
+    def forward(ctx, module, x, rs, names, *params):
+        from sunb200 import native as N
+        N.require_cuda(x)
+        ctx.set_materialize_grads(False)
+        P = {n: p.detach() for n, p in zip(names, params)}
+        Bf = {n: b for n, b in module.named_buffers()}
+        eng = module._train_engine
+        pooled, dense, c = eng.forward(P, Bf, x.detach().contiguous().float(), rs)
+        ctx.eng, ctx.c, ctx.P, ctx.names = eng, c, P, names
+        return pooled, dense
+
+    @staticmethod
+    def backward(ctx, dpooled, ddense):
+        dp = dpooled.contiguous().float() if dpooled is not None else None
+        dd = ddense.contiguous().float() if ddense is not None else None
+        if dp is None and dd is None:
+            return (None,) * (4 + len(ctx.names))
+        G = ctx.eng.backward(ctx.P, ctx.c, dp, dd)
+        ctx.c = None
+        return (None, None, None, None) + tuple(G[n] for n in ctx.names)
 
 
 @register("visformer_micro_80")

@@ -88,24 +88,50 @@ class EncoderEngine:
         return {"pooled": pooled, "dense": dense, "dense_bf16": dense16, "pooled_bf16": pooled16}
 
 
+def _temp_args(temp):
+    if isinstance(temp, torch.Tensor) and temp.is_cuda:
+        return temp.detach().float().reshape(1).contiguous(), 0.0
+    return None, float(temp)
+
+
+class _EpisodeLogitsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, fs, fq, temp, code):
+        E, way, shot, D = fs.shape
+        Q = fq.shape[1]
+        fs, fq = fs.detach().contiguous().float(), fq.detach().contiguous().float()
+        out = torch.empty(E, Q, way, dtype=torch.float32, device=fs.device)
+        tdev, thost = _temp_args(temp)
+        N.check(N.lib().sunb_episode_logits(fs.data_ptr(), fq.data_ptr(), out.data_ptr(), E, way, shot, Q, D, code,
+                                            N.ptr(tdev), thost, N.current_stream()), "sunb_episode_logits")
+        ctx.save_for_backward(fs, fq)
+        ctx.temp, ctx.code = temp, code
+        return out
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        fs, fq = ctx.saved_tensors
+        E, way, shot, D = fs.shape
+        Q = fq.shape[1]
+        dl = dlogits.contiguous().float()
+        dfs, dfq = torch.empty_like(fs), torch.empty_like(fq)
+        temp = ctx.temp
+        want_dt = isinstance(temp, torch.Tensor) and temp.requires_grad
+        dt = torch.zeros((), dtype=torch.float32, device=fs.device) if want_dt else None
+        tdev, thost = _temp_args(temp)
+        N.check(N.lib().sunb_episode_logits_backward(fs.data_ptr(), fq.data_ptr(), dl.data_ptr(), dfs.data_ptr(),
+                                                     dfq.data_ptr(), N.ptr(dt), E, way, shot, Q, D, ctx.code, N.ptr(tdev),
+                                                     thost, N.current_stream()), "sunb_episode_logits_backward")
+        return dfs, dfq, dt, None
+
+
 def episode_logits(feat_shot: torch.Tensor, feat_query: torch.Tensor, temp, metric: str = "cos") -> torch.Tensor:
     """feat_shot [E,way,shot,D], feat_query [E,Q,D] (fp32 CUDA) -> logits [E,Q,way].
-    Prototype mean + normalise + scaled dot product in one kernel (meta_baseline.py:36-46)."""
+    Prototype mean + normalise + scaled dot product in one kernel (meta_baseline.py:36-46); differentiable
+    (native backward) w.r.t. both feature tensors and a learnable `temp`."""
     N.require_cuda(feat_shot, feat_query)
-    E, way, shot, D = feat_shot.shape
-    Q = feat_query.shape[1]
-    fs, fq = feat_shot.contiguous().float(), feat_query.contiguous().float()
-    out = torch.empty(E, Q, way, dtype=torch.float32, device=fs.device)
     code = {"dot": 0, "cos": 1, "sqr": 2}[metric]
-    if isinstance(temp, torch.Tensor):
-        tdev, thost = temp.detach().float().reshape(1).contiguous(), 0.0
-        if not tdev.is_cuda:
-            tdev, thost = None, float(temp)
-    else:
-        tdev, thost = None, float(temp)
-    N.check(N.lib().sunb_episode_logits(fs.data_ptr(), fq.data_ptr(), out.data_ptr(), E, way, shot, Q, D, code,
-                                        N.ptr(tdev), thost, N.current_stream()), "sunb_episode_logits")
-    return out
+    return _EpisodeLogitsFn.apply(feat_shot, feat_query, temp, code)
 
 
 def ce_and_acc(logits: torch.Tensor, label: torch.Tensor) -> torch.Tensor:

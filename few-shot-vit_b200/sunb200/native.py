@@ -30,6 +30,21 @@ class GemmDesc(C.Structure):
         ("out", vp), ("ldc", C.c_int32),
         ("out_f32", fp), ("ldc_f32", C.c_int32),
         ("out_map", C.c_int32), ("oH", C.c_int32), ("oW", C.c_int32),
+        ("out2", vp), ("ldc2", C.c_int32),
+        ("dact_aux", vp), ("ld_aux", C.c_int32), ("dact", C.c_int32),
+    ]
+
+
+class WgradDesc(C.Structure):
+    _fields_ = [
+        ("P", C.c_int32), ("Ma", C.c_int32), ("Nb", C.c_int32), ("Ca", C.c_int32), ("Cb", C.c_int32),
+        ("groups", C.c_int32), ("a_goff", C.c_int32), ("b_goff", C.c_int32),
+        ("taps", C.c_int32),
+        ("mode", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("bw", C.c_int32), ("bh", C.c_int32),
+        ("dY", vp), ("ldy", C.c_int32),
+        ("X", vp), ("ldx", C.c_int32),
+        ("out", fp), ("ldo", C.c_int32),
+        ("ksplit", C.c_int32),
     ]
 
 
@@ -77,9 +92,32 @@ SIGNATURES = {
     "sunb_soft_ce_forward": (C.c_int, [fp, C.c_int, fp, C.c_int, C.c_int, C.c_int, C.c_int, fp, fp, vp]),
     "sunb_soft_ce_backward": (C.c_int, [fp, C.c_int, fp, C.c_int, C.c_int, C.c_int, C.c_int, fp, C.c_float, fp,
                                         C.c_int, vp]),
+    # train-mode building blocks
+    "sunb_wgrad": (C.c_int, [C.POINTER(WgradDesc), vp]),
+    "sunb_stem_in": (C.c_int, [fp, fp, fp, fp, fp, vp, vp, C.c_int, C.c_int, vp]),
+    "sunb_stem_wgrad": (C.c_int, [fp, vp, vp, fp, fp, C.c_int, vp]),
+    "sunb_colstats": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_long, C.c_int, fp, fp, vp]),
+    "sunb_bn_finalize": (C.c_int, [fp, fp, C.c_float, fp, fp, fp, fp, vp, C.c_float, C.c_float, C.c_int, fp, fp, fp, fp, vp]),
+    "sunb_bn_apply": (C.c_int, [vp, C.c_int, fp, fp, C.c_int, fp, C.c_int, vp, C.c_int, C.c_long, C.c_int, vp]),
+    "sunb_bn_bwd_finalize": (C.c_int, [fp, fp, C.c_float, fp, fp, fp, C.c_int, fp, fp, fp, fp, fp, vp]),
+    "sunb_bn_bwd_apply": (C.c_int, [vp, C.c_int, vp, C.c_int, fp, fp, fp, fp, vp, C.c_int, vp, C.c_int, C.c_long, C.c_int, vp]),
+    "sunb_stem_tail_forward": (C.c_int, [vp, vp, fp, fp, fp, fp, fp, vp, C.c_int, vp]),
+    "sunb_stem_tail_backward": (C.c_int, [vp, vp, fp, fp, fp, fp, vp, vp, C.c_int, vp]),
+    "sunb_final_norm_pool": (C.c_int, [vp, fp, fp, fp, vp, fp, vp, C.c_int, C.c_int, C.c_int, vp]),
+    "sunb_pool_backward": (C.c_int, [fp, fp, vp, C.c_int, C.c_int, C.c_int, vp]),
+    "sunb_scale_rows": (C.c_int, [vp, fp, C.c_int, vp, C.c_long, C.c_int, vp]),
+    "sunb_s2d_reorder": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "sunb_batch_sum": (C.c_int, [vp, C.c_int, C.c_long, fp, vp]),
+    "sunb_permute_cast": (C.c_int, [fp, C.c_long, C.c_long, C.c_long, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
+    "sunb_grouped_pairs": (C.c_int, [fp, vp, C.c_int, vp]),
+    "sunb_grouped_wgrad_extract": (C.c_int, [fp, fp, vp]),
+    "sunb_attention_backward": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "sunb_episode_logits_backward": (C.c_int, [fp, fp, fp, fp, fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                               C.c_int, fp, C.c_float, vp]),
 }
 
 _lib = None
+ABI_VERSION = 2
 
 
 def lib() -> C.CDLL:
@@ -94,7 +132,7 @@ def lib() -> C.CDLL:
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(l, name)
             fn.restype, fn.argtypes = res, args
-        if l.sunb_abi_version() != 1:
+        if l.sunb_abi_version() != ABI_VERSION:
             raise RuntimeError("libsunb200.so ABI version mismatch; rebuild")
         _lib = l
     return _lib

@@ -1,0 +1,390 @@
+"""Train-mode encoder: forward with batch-statistics BatchNorm + DropPath and the hand-written backward.
+
+Schedule of the SUN-M meta-tuning step's device work (reference: meta_tuning_sun_m/train_meta.py:168-174 driving
+autograd through test_phase/models/visformer.py).  Every device operation is a libsunb200 entry point
+(include/sunb200.h): sunb_gemm (forward convs, dgrads with the activation derivative fused into the epilogue),
+sunb_wgrad (tcgen05 weight gradients), sunb_attention(+_backward), and the BatchNorm / stem-tail / helper kernels.
+torch is used to allocate buffers and for views/permutes of small gradient tensors.
+
+Semantics kept from the reference: BN statistics over the whole concatenated batch, biased variance
+for normalisation / unbiased for the running stats with momentum 0.1, DropPath as a per-sample scale mask/keep drawn
+with torch.rand in forward order (attention branch first, then MLP), identity DropPath for rate 0.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional
+
+import torch
+
+from . import native as N
+
+ACT_NONE, ACT_LRELU, ACT_GELU = 0, 1, 2
+HEADS = 6
+DEPTH = (4, 2, 3)
+BN_EPS, BN_MOMENTUM = 1e-5, 0.1
+
+
+def _st():
+    return N.current_stream()
+
+
+def gemm(A, Wt, M, Nn, K, *, lda=None, ldw=None, out=None, ldc=None, taps=1, groups=1, a_goff=0, c_goff=0, conv=None,
+         bias=None, act=ACT_NONE, resid=None, row_scale=None, rows_per_img=1, out2=None, dact_aux=None, dact=ACT_NONE,
+         out_f32=None):
+    d = N.GemmDesc()
+    d.M, d.N, d.K, d.taps, d.groups, d.a_goff, d.c_goff = M, Nn, K, taps, groups, a_goff, c_goff
+    if conv is not None:
+        d.a_mode, d.H, d.W, d.bw, d.bh = 1, conv[0], conv[1], conv[2], conv[3]
+    d.A, d.lda = A.data_ptr(), lda if lda is not None else A.shape[-1]
+    d.Wt, d.ldw = Wt.data_ptr(), ldw if ldw is not None else Wt.shape[-1]
+    d.bias, d.bias_mod, d.bias_ld = N.ptr(bias), 1, 0
+    d.act = act
+    if resid is not None:
+        d.resid, d.ldr = resid.data_ptr(), resid.shape[-1]
+    if row_scale is not None:
+        d.row_scale, d.rows_per_img = row_scale.data_ptr(), rows_per_img
+    else:
+        d.rows_per_img = 1
+    if out is not None:
+        d.out, d.ldc = out.data_ptr(), ldc if ldc is not None else out.shape[-1]
+    if out_f32 is not None:
+        d.out_f32, d.ldc_f32 = out_f32.data_ptr(), out_f32.shape[-1]
+    if out2 is not None:
+        d.out2, d.ldc2 = out2.data_ptr(), out2.shape[-1]
+    if dact_aux is not None:
+        d.dact_aux, d.ld_aux, d.dact = dact_aux.data_ptr(), dact_aux.shape[-1], dact
+    N.check(N.lib().sunb_gemm(C.byref(d), 0, _st()), "sunb_gemm")
+    return out
+
+
+def wgrad(dY, X, out, P, Ma, Nb, *, Ca=None, Cb=None, ldo=None, taps=1, groups=1, a_goff=0, b_goff=0, conv=None):
+    d = N.WgradDesc()
+    d.P, d.Ma, d.Nb = P, Ma, Nb
+    d.Ca, d.Cb = Ca if Ca is not None else dY.shape[-1], Cb if Cb is not None else X.shape[-1]
+    d.groups, d.a_goff, d.b_goff, d.taps = groups, a_goff, b_goff, taps
+    if conv is not None:
+        d.mode, d.H, d.W, d.bw, d.bh = 1, conv[0], conv[1], conv[2], conv[3]
+    d.dY, d.ldy, d.X, d.ldx = dY.data_ptr(), dY.shape[-1], X.data_ptr(), X.shape[-1]
+    d.out, d.ldo, d.ksplit = out.data_ptr(), ldo if ldo is not None else Nb, 0
+    N.check(N.lib().sunb_wgrad(C.byref(d), _st()), "sunb_wgrad")
+
+
+class BNRec:
+    """Per-layer BatchNorm record: statistics of this step and the tensors the backward needs."""
+    __slots__ = ("name", "C", "count", "buf", "x")
+
+    def __init__(self, name, Cc, count, buf, x):
+        self.name, self.C, self.count, self.buf, self.x = name, Cc, count, buf, x
+
+    # buf rows: 0 sum, 1 sq, 2 scale, 3 shift, 4 mean, 5 rstd, 6 sdz, 7 sdzx, 8 a, 9 c1, 10 c2
+    def row(self, i):
+        return self.buf[i]
+
+
+class TrainEngine:
+    def __init__(self):
+        self.lib = N.lib()
+
+    # ------------------------------------------------------------------ small wrappers
+    def empty(self, *shape, dtype=torch.bfloat16):
+        return torch.empty(*shape, dtype=dtype, device=self.dev)
+
+    def bn_forward(self, x, name, Cc, M, P, Bf, update_running=True) -> BNRec:
+        """colstats + finalize for BatchNorm `name` over x [M, C] (bf16).  Running stats updated in place."""
+        buf = torch.zeros(11, Cc, dtype=torch.float32, device=self.dev)
+        rec = BNRec(name, Cc, float(M), buf, x)
+        N.check(self.lib.sunb_colstats(x.data_ptr(), x.shape[-1], None, 0, M, Cc, buf[0].data_ptr(), buf[1].data_ptr(),
+                                       _st()), "sunb_colstats")
+        rm, rv, nbt = Bf[name + ".running_mean"], Bf[name + ".running_var"], Bf[name + ".num_batches_tracked"]
+        N.check(self.lib.sunb_bn_finalize(buf[0].data_ptr(), buf[1].data_ptr(), float(M), P[name + ".weight"].data_ptr(),
+                                          P[name + ".bias"].data_ptr(), rm.data_ptr() if update_running else None,
+                                          rv.data_ptr() if update_running else None,
+                                          nbt.data_ptr() if update_running else None, BN_MOMENTUM, BN_EPS, Cc,
+                                          buf[2].data_ptr(), buf[3].data_ptr(), buf[4].data_ptr(), buf[5].data_ptr(), _st()),
+                "sunb_bn_finalize")
+        return rec
+
+    def bn_apply(self, x, rec: BNRec, M, act=ACT_NONE, tab=None, tab_mod=1):
+        out = self.empty(M, rec.C)
+        N.check(self.lib.sunb_bn_apply(x.data_ptr(), x.shape[-1], rec.row(2).data_ptr(), rec.row(3).data_ptr(), act,
+                                       N.ptr(tab), tab_mod, out.data_ptr(), rec.C, M, rec.C, _st()), "sunb_bn_apply")
+        return out
+
+    def bn_backward(self, dz, rec: BNRec, M, P, G, res=None):
+        """dz = gradient w.r.t. the BN output [M, C] -> gradient w.r.t. its input (+ res); accumulates dgamma / dbeta."""
+        b = rec.buf
+        N.check(self.lib.sunb_colstats(dz.data_ptr(), dz.shape[-1], rec.x.data_ptr(), rec.x.shape[-1], M, rec.C,
+                                       b[6].data_ptr(), b[7].data_ptr(), _st()), "sunb_colstats(bwd)")
+        N.check(self.lib.sunb_bn_bwd_finalize(b[6].data_ptr(), b[7].data_ptr(), rec.count, b[4].data_ptr(), b[5].data_ptr(),
+                                              P[rec.name + ".weight"].data_ptr(), rec.C, b[8].data_ptr(), b[9].data_ptr(),
+                                              b[10].data_ptr(), G[rec.name + ".weight"].data_ptr(),
+                                              G[rec.name + ".bias"].data_ptr(), _st()), "sunb_bn_bwd_finalize")
+        out = self.empty(M, rec.C)
+        N.check(self.lib.sunb_bn_bwd_apply(dz.data_ptr(), dz.shape[-1], rec.x.data_ptr(), rec.x.shape[-1], b[8].data_ptr(),
+                                           b[9].data_ptr(), b[10].data_ptr(), b[4].data_ptr(), N.ptr(res),
+                                           res.shape[-1] if res is not None else 0, out.data_ptr(), rec.C, M, rec.C, _st()),
+                "sunb_bn_bwd_apply")
+        return out
+
+    def pcast(self, src, dims, strides, off=0, ldd=None):
+        """bf16 dst[a][b][c] = src.flat[off + a*sa + b*sb + c*sc]."""
+        A, B, Cd = dims
+        ldd = ldd or Cd
+        dst = self.empty(A, B, ldd)
+        N.check(self.lib.sunb_permute_cast(src.data_ptr(), off, strides[0], strides[1], strides[2], A, B, Cd, ldd,
+                                           dst.data_ptr(), _st()), "sunb_permute_cast")
+        return dst
+
+    def scale_rows(self, g, rs, rows_per_img, M, Cc):
+        if rs is None:
+            return g
+        out = self.empty(M, Cc)
+        N.check(self.lib.sunb_scale_rows(g.data_ptr(), rs.data_ptr(), rows_per_img, out.data_ptr(), M, Cc, _st()),
+                "sunb_scale_rows")
+        return out
+
+    # ------------------------------------------------------------------ weight preparation (fp32 masters -> bf16 operands)
+    def prep_weights(self, P) -> Dict[str, torch.Tensor]:
+        W = {}
+        for name, cin, cout in (("stem.conv2", 64, 128), ("stem.conv3", 128, 128)):
+            w = P[name + ".weight"]
+            W[name + ".f"] = self.pcast(w, (9, cout, cin), (1, cin * 9, 9))                 # [tap][n][c]
+            W[name + ".d"] = self.pcast(w, (9, cin, cout), (-1, 9, cin * 9), off=8)          # [tap][c][n], taps mirrored
+        for i in range(DEPTH[0]):
+            b = f"stage1.{i}.mlp."
+            W[b + "conv1.f"] = self.pcast(P[b + "conv1.weight"], (1, 256, 128), (0, 128, 1))
+            W[b + "conv1.d"] = self.pcast(P[b + "conv1.weight"], (1, 128, 256), (0, 1, 128))
+            W[b + "conv3.f"] = self.pcast(P[b + "conv3.weight"], (1, 128, 256), (0, 256, 1))
+            W[b + "conv3.d"] = self.pcast(P[b + "conv3.weight"], (1, 256, 128), (0, 1, 256))
+            for key, flip in ((".f", 0), (".d", 1)):
+                dst = self.empty(4 * 9 * 64, 64)
+                N.check(self.lib.sunb_grouped_pairs(P[b + "conv2.weight"].data_ptr(), dst.data_ptr(), flip, _st()),
+                        "sunb_grouped_pairs")
+                W[b + "conv2" + key] = dst
+        for stage, cin, dim, depth in (("2", 128, 256, DEPTH[1]), ("3", 256, 512, DEPTH[2])):
+            w = P[f"patch_embed{stage}.proj.weight"]
+            W[f"pe{stage}.f"] = self.pcast(w, (dim, 4, cin), (cin * 4, 1, 4)).view(dim, 4 * cin)       # [n][(tap,c)]
+            W[f"pe{stage}.d"] = self.pcast(w, (4, cin, dim), (1, 4, cin * 4)).view(4 * cin, dim)       # [(tap,c)][n]
+            d = round(dim // HEADS)
+            inner = HEADS * d
+            ldi = (inner + 7) // 8 * 8
+            ld3 = (3 * inner + 7) // 8 * 8
+            for i in range(depth):
+                b = f"stage{stage}.{i}."
+                W[b + "qkv.f"] = self.pcast(P[b + "attn.qkv.weight"], (1, 3 * inner, dim), (0, dim, 1))
+                W[b + "qkv.d"] = self.pcast(P[b + "attn.qkv.weight"], (1, dim, 3 * inner), (0, 1, dim), ldd=ld3)
+                W[b + "proj.f"] = self.pcast(P[b + "attn.proj.weight"], (1, dim, inner), (0, inner, 1), ldd=ldi)
+                W[b + "proj.d"] = self.pcast(P[b + "attn.proj.weight"], (1, inner, dim), (0, 1, inner))
+                W[b + "conv1.f"] = self.pcast(P[b + "mlp.conv1.weight"], (1, 4 * dim, dim), (0, dim, 1))
+                W[b + "conv1.d"] = self.pcast(P[b + "mlp.conv1.weight"], (1, dim, 4 * dim), (0, 1, dim))
+                W[b + "conv3.f"] = self.pcast(P[b + "mlp.conv3.weight"], (1, dim, 4 * dim), (0, 4 * dim, 1))
+                W[b + "conv3.d"] = self.pcast(P[b + "mlp.conv3.weight"], (1, 4 * dim, dim), (0, 1, 4 * dim))
+        return {k: v.view(-1, v.shape[-1]) for k, v in W.items()}
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, P, Bf, x, rs: Dict[str, List[Optional[torch.Tensor]]], update_running=True):
+        """P: encoder parameters (fp32 CUDA, reference names without the 'encoder.' prefix); Bf: BN buffers;
+        x fp32 [B,3,80,80]; rs[block] = per-branch DropPath scales (fp32 [B]) or None.
+        Returns (pooled fp32 [B,512], dense fp32 NHWC [B,5,5,512], ctx)."""
+        self.dev = x.device
+        B = x.shape[0]
+        lib = self.lib
+        W = self.prep_weights(P)
+        ctx = {"B": B, "W": W, "x": x, "rs": rs, "blocks": []}
+        z64 = torch.zeros(64, device=self.dev)
+        z128 = torch.zeros(128, device=self.dev)
+
+        # ---- stem (visformer.py:220-239)
+        M0 = B * 1600
+        a1r, idr = self.empty(M0, 64), self.empty(M0, 128)
+        N.check(lib.sunb_stem_in(x.data_ptr(), P["stem.conv1.weight"].data_ptr(), z64.data_ptr(),
+                                 P["stem.downsample.0.weight"].data_ptr(), z128.data_ptr(), a1r.data_ptr(), idr.data_ptr(),
+                                 B, 0, _st()), "sunb_stem_in")
+        bn1 = self.bn_forward(a1r, "stem.bn1", 64, M0, P, Bf, update_running)
+        a1 = self.bn_apply(a1r, bn1, M0, ACT_LRELU)
+        a2r = gemm(a1, W["stem.conv2.f"], M0, 128, 64, out=self.empty(M0, 128), taps=9, conv=(40, 40, 8, 8))
+        bn2 = self.bn_forward(a2r, "stem.bn2", 128, M0, P, Bf, update_running)
+        a2 = self.bn_apply(a2r, bn2, M0, ACT_LRELU)
+        c3r = gemm(a2, W["stem.conv3.f"], M0, 128, 128, out=self.empty(M0, 128), taps=9, conv=(40, 40, 8, 8))
+        bn3 = self.bn_forward(c3r, "stem.bn3", 128, M0, P, Bf, update_running)
+        bnd = self.bn_forward(idr, "stem.downsample.1", 128, M0, P, Bf, update_running)
+        pos1 = P["pos_embed1"][0].permute(1, 2, 0).reshape(400, 128).contiguous()
+        M1 = B * 400
+        cur = self.empty(M1, 128)
+        N.check(lib.sunb_stem_tail_forward(c3r.data_ptr(), idr.data_ptr(), bn3.row(2).data_ptr(), bn3.row(3).data_ptr(),
+                                           bnd.row(2).data_ptr(), bnd.row(3).data_ptr(), pos1.data_ptr(), cur.data_ptr(), B,
+                                           _st()), "sunb_stem_tail_forward")
+        ctx["stem"] = dict(a1r=a1r, idr=idr, a1=a1, a2r=a2r, a2=a2, c3r=c3r, bn1=bn1, bn2=bn2, bn3=bn3, bnd=bnd)
+
+        # ---- stage 1 (visformer.py:152-163, 259-263)
+        for i in range(DEPTH[0]):
+            name = f"stage1.{i}"
+            r = (rs.get(name) or [None])[0]
+            bn = self.bn_forward(cur, name + ".norm2.bn", 128, M1, P, Bf, update_running)
+            xn = self.bn_apply(cur, bn, M1)
+            h1, h1p = self.empty(M1, 256), self.empty(M1, 256)
+            gemm(xn, W[name + ".mlp.conv1.f"], M1, 256, 128, out=h1, act=ACT_GELU, out2=h1p)
+            h2, h2p = self.empty(M1, 256), self.empty(M1, 256)
+            gemm(h1, W[name + ".mlp.conv2.f"], M1, 64, 64, out=h2, taps=9, groups=4, a_goff=64, c_goff=64,
+                 conv=(20, 20, 4, 4), act=ACT_GELU, out2=h2p)
+            nxt = gemm(h2, W[name + ".mlp.conv3.f"], M1, 128, 256, out=self.empty(M1, 128), resid=cur, row_scale=r,
+                       rows_per_img=400)
+            ctx["blocks"].append(dict(kind="conv", name=name, x=cur, bn=bn, xn=xn, h1=h1, h1p=h1p, h2=h2, h2p=h2p, rs=r))
+            cur = nxt
+
+        # ---- stages 2 and 3
+        for stage, cin, dim, side, depth in (("2", 128, 256, 10, DEPTH[1]), ("3", 256, 512, 5, DEPTH[2])):
+            S = side * side
+            M = B * S
+            xs = self.empty(M, 4 * cin)
+            N.check(lib.sunb_s2d_reorder(cur.data_ptr(), xs.data_ptr(), B, 2 * side, 2 * side, cin, 0, _st()), "sunb_s2d_reorder")
+            y = gemm(xs, W[f"pe{stage}.f"], M, dim, 4 * cin, out=self.empty(M, dim), bias=P[f"patch_embed{stage}.proj.bias"])
+            bnp = self.bn_forward(y, f"patch_embed{stage}.norm.bn", dim, M, P, Bf, update_running)
+            pos = P[f"pos_embed{stage}"][0].permute(1, 2, 0).reshape(S, dim).contiguous()
+            cur = self.bn_apply(y, bnp, M, ACT_NONE, tab=pos, tab_mod=S)
+            ctx[f"pe{stage}"] = dict(xs=xs, y=y, bn=bnp)
+            d = round(dim // HEADS)
+            inner = HEADS * d
+            ldi, ld3 = (inner + 7) // 8 * 8, (3 * inner + 7) // 8 * 8
+            for i in range(depth):
+                name = f"stage{stage}.{i}"
+                rr = rs.get(name) or [None, None]
+                bnA = self.bn_forward(cur, name + ".norm1.bn", dim, M, P, Bf, update_running)
+                xn1 = self.bn_apply(cur, bnA, M)
+                qkv = gemm(xn1, W[name + ".qkv.f"], M, 3 * inner, dim, out=self.empty(M, ld3))
+                ao = self.empty(M, ldi)
+                N.check(lib.sunb_attention(qkv.data_ptr(), ao.data_ptr(), B, S, d, HEADS, ld3, ldi, _st()), "sunb_attention")
+                mid = gemm(ao, W[name + ".proj.f"], M, dim, inner, out=self.empty(M, dim), resid=cur, row_scale=rr[0],
+                           rows_per_img=S)
+                bnM = self.bn_forward(mid, name + ".norm2.bn", dim, M, P, Bf, update_running)
+                xn2 = self.bn_apply(mid, bnM, M)
+                hid, hidp = self.empty(M, 4 * dim), self.empty(M, 4 * dim)
+                gemm(xn2, W[name + ".conv1.f"], M, 4 * dim, dim, out=hid, act=ACT_GELU, out2=hidp)
+                nxt = gemm(hid, W[name + ".conv3.f"], M, dim, 4 * dim, out=self.empty(M, dim), resid=mid, row_scale=rr[1],
+                           rows_per_img=S)
+                ctx["blocks"].append(dict(kind="attn", name=name, x=cur, bnA=bnA, xn1=xn1, qkv=qkv, ao=ao, mid=mid, bnM=bnM,
+                                          xn2=xn2, hid=hid, hidp=hidp, rs=rr, S=S, dim=dim, d=d, inner=inner, ldi=ldi,
+                                          ld3=ld3, M=M, stage=stage))
+                cur = nxt
+
+        # ---- final BN + pool (visformer.py:455-462)
+        Mf = B * 25
+        bnf = self.bn_forward(cur, "norm.bn", 512, Mf, P, Bf, update_running)
+        pooled = self.empty(B, 512, dtype=torch.float32)
+        dense = self.empty(B, 5, 5, 512, dtype=torch.float32)
+        N.check(lib.sunb_final_norm_pool(cur.data_ptr(), bnf.row(2).data_ptr(), bnf.row(3).data_ptr(), dense.data_ptr(), None,
+                                         pooled.data_ptr(), None, B, 25, 512, _st()), "sunb_final_norm_pool")
+        ctx["final"] = dict(x=cur, bn=bnf)
+        return pooled, dense, ctx
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, P, ctx, dpooled, ddense=None) -> Dict[str, torch.Tensor]:
+        lib = self.lib
+        B, W = ctx["B"], ctx["W"]
+        G = {k: torch.zeros_like(v, dtype=torch.float32) for k, v in P.items()}
+        Mf = B * 25
+        dy = self.empty(Mf, 512)
+        N.check(lib.sunb_pool_backward(N.ptr(dpooled), N.ptr(ddense), dy.data_ptr(), B, 25, 512, _st()), "sunb_pool_backward")
+        g = self.bn_backward(dy, ctx["final"]["bn"], Mf, P, G)
+
+        blocks = ctx["blocks"]
+        idx = len(blocks) - 1
+        for stage, cin, dim, side, depth in (("3", 256, 512, 5, DEPTH[2]), ("2", 128, 256, 10, DEPTH[1])):
+            for _ in range(depth):
+                g = self._attn_block_backward(blocks[idx], g, P, G, W)
+                idx -= 1
+            # PatchEmbed + pos_embed (visformer.py:438-441, 447-450)
+            S, M = side * side, B * side * side
+            pe = ctx[f"pe{stage}"]
+            gpos = torch.zeros(S * dim, dtype=torch.float32, device=self.dev)
+            N.check(lib.sunb_batch_sum(g.data_ptr(), B, S * dim, gpos.data_ptr(), _st()), "sunb_batch_sum")
+            G[f"pos_embed{stage}"] += gpos.view(side, side, dim).permute(2, 0, 1).unsqueeze(0)
+            dyp = self.bn_backward(g, pe["bn"], M, P, G)
+            sb = torch.zeros(2, dim, dtype=torch.float32, device=self.dev)
+            N.check(lib.sunb_colstats(dyp.data_ptr(), dim, None, 0, M, dim, sb[0].data_ptr(), sb[1].data_ptr(), _st()), "colstats")
+            G[f"patch_embed{stage}.proj.bias"] += sb[0]
+            gw = torch.zeros(dim, 4 * cin, dtype=torch.float32, device=self.dev)
+            wgrad(dyp, pe["xs"], gw, M, dim, 4 * cin)
+            G[f"patch_embed{stage}.proj.weight"] += gw.view(dim, 2, 2, cin).permute(0, 3, 1, 2)
+            dxs = gemm(dyp, W[f"pe{stage}.d"], M, 4 * cin, dim, out=self.empty(M, 4 * cin))
+            g = self.empty(M * 4, cin)
+            N.check(lib.sunb_s2d_reorder(dxs.data_ptr(), g.data_ptr(), B, 2 * side, 2 * side, cin, 1, _st()), "sunb_s2d_reorder")
+        for _ in range(DEPTH[0]):
+            g = self._conv_block_backward(blocks[idx], g, P, G, W, B)
+            idx -= 1
+        self._stem_backward(ctx, g, P, G, W, B)
+        return G
+
+    def _attn_block_backward(self, b, g, P, G, W, ):
+        lib = self.lib
+        name, M, dim, S, d, inner, ldi, ld3 = b["name"], b["M"], b["dim"], b["S"], b["d"], b["inner"], b["ldi"], b["ld3"]
+        Bn = M // S
+        r_att, r_mlp = b["rs"]
+        # ---- MLP branch: out = mid + rs * conv3(gelu(conv1(BN2(mid))))
+        gs = self.scale_rows(g, r_mlp, S, M, dim)
+        dhp = gemm(g, W[name + ".conv3.d"], M, 4 * dim, dim, out=self.empty(M, 4 * dim), row_scale=r_mlp, rows_per_img=S,
+                   dact_aux=b["hidp"], dact=ACT_GELU)
+        wgrad(gs, b["hid"], G[name + ".mlp.conv3.weight"], M, dim, 4 * dim)
+        dxn2 = gemm(dhp, W[name + ".conv1.d"], M, dim, 4 * dim, out=self.empty(M, dim))
+        wgrad(dhp, b["xn2"], G[name + ".mlp.conv1.weight"], M, 4 * dim, dim)
+        g1 = self.bn_backward(dxn2, b["bnM"], M, P, G, res=g)
+        # ---- attention branch: mid = x + rs * proj(attn(qkv(BN1(x))))
+        gs1 = self.scale_rows(g1, r_att, S, M, dim)
+        dao = gemm(g1, W[name + ".proj.d"], M, inner, dim, out=self.empty(M, ldi), row_scale=r_att, rows_per_img=S)
+        wgrad(gs1, b["ao"], G[name + ".attn.proj.weight"], M, dim, inner, Cb=inner)
+        dqkv = self.empty(M, ld3)
+        N.check(lib.sunb_attention_backward(b["qkv"].data_ptr(), dao.data_ptr(), dqkv.data_ptr(), Bn, S, d, HEADS, ld3, ldi,
+                                            _st()), "sunb_attention_backward")
+        dxn1 = gemm(dqkv, W[name + ".qkv.d"], M, dim, 3 * inner, out=self.empty(M, dim))
+        wgrad(dqkv, b["xn1"], G[name + ".attn.qkv.weight"], M, 3 * inner, dim, Ca=3 * inner)
+        return self.bn_backward(dxn1, b["bnA"], M, P, G, res=g1)
+
+    def _conv_block_backward(self, b, g, P, G, W, B):
+        lib = self.lib
+        name, r = b["name"], b["rs"]
+        M = B * 400
+        gs = self.scale_rows(g, r, 400, M, 128)
+        dh2p = gemm(g, W[name + ".mlp.conv3.d"], M, 256, 128, out=self.empty(M, 256), row_scale=r, rows_per_img=400,
+                    dact_aux=b["h2p"], dact=ACT_GELU)
+        wgrad(gs, b["h2"], G[name + ".mlp.conv3.weight"], M, 128, 256)
+        dh1p = gemm(dh2p, W[name + ".mlp.conv2.d"], M, 64, 64, out=self.empty(M, 256), taps=9, groups=4, a_goff=64,
+                    c_goff=64, conv=(20, 20, 4, 4), dact_aux=b["h1p"], dact=ACT_GELU)
+        scratch = torch.zeros(2 * 9 * 128, 128, dtype=torch.float32, device=self.dev)
+        wgrad(dh2p, b["h1"], scratch, M, 128, 128, Ca=256, Cb=256, taps=9, groups=2, a_goff=128, b_goff=128,
+              conv=(20, 20, 4, 4))
+        N.check(lib.sunb_grouped_wgrad_extract(scratch.data_ptr(), G[name + ".mlp.conv2.weight"].data_ptr(), _st()),
+                "sunb_grouped_wgrad_extract")
+        dxn = gemm(dh1p, W[name + ".mlp.conv1.d"], M, 128, 256, out=self.empty(M, 128))
+        wgrad(dh1p, b["xn"], G[name + ".mlp.conv1.weight"], M, 256, 128)
+        return self.bn_backward(dxn, b["bn"], M, P, G, res=g)
+
+    def _stem_backward(self, ctx, g, P, G, W, B):
+        lib = self.lib
+        s = ctx["stem"]
+        M0 = B * 1600
+        gpos = torch.zeros(400 * 128, dtype=torch.float32, device=self.dev)
+        N.check(lib.sunb_batch_sum(g.data_ptr(), B, 400 * 128, gpos.data_ptr(), _st()), "sunb_batch_sum")
+        G["pos_embed1"] += gpos.view(20, 20, 128).permute(2, 0, 1).unsqueeze(0)
+        bn3, bnd, bn2, bn1 = s["bn3"], s["bnd"], s["bn2"], s["bn1"]
+        dz = self.empty(M0, 128)
+        N.check(lib.sunb_stem_tail_backward(s["c3r"].data_ptr(), s["idr"].data_ptr(), bn3.row(2).data_ptr(),
+                                            bn3.row(3).data_ptr(), bnd.row(2).data_ptr(), bnd.row(3).data_ptr(), g.data_ptr(),
+                                            dz.data_ptr(), B, _st()), "sunb_stem_tail_backward")
+        dc3r = self.bn_backward(dz, bn3, M0, P, G)
+        didr = self.bn_backward(dz, bnd, M0, P, G)
+        gw3 = torch.zeros(9 * 128, 128, dtype=torch.float32, device=self.dev)
+        wgrad(dc3r, s["a2"], gw3, M0, 128, 128, taps=9, conv=(40, 40, 8, 8))
+        G["stem.conv3.weight"] += gw3.view(9, 128, 128).permute(1, 2, 0).reshape(128, 128, 3, 3)
+        da2 = gemm(dc3r, W["stem.conv3.d"], M0, 128, 128, out=self.empty(M0, 128), taps=9, conv=(40, 40, 8, 8),
+                   dact_aux=s["a2"], dact=ACT_LRELU)
+        da2r = self.bn_backward(da2, bn2, M0, P, G)
+        gw2 = torch.zeros(9 * 128, 64, dtype=torch.float32, device=self.dev)
+        wgrad(da2r, s["a1"], gw2, M0, 128, 64, taps=9, conv=(40, 40, 8, 8))
+        G["stem.conv2.weight"] += gw2.view(9, 128, 64).permute(1, 2, 0).reshape(128, 64, 3, 3)
+        da1 = gemm(da2r, W["stem.conv2.d"], M0, 64, 128, out=self.empty(M0, 64), taps=9, conv=(40, 40, 8, 8),
+                   dact_aux=s["a1"], dact=ACT_LRELU)
+        da1r = self.bn_backward(da1, bn1, M0, P, G)
+        N.check(lib.sunb_stem_wgrad(ctx["x"].data_ptr(), da1r.data_ptr(), didr.data_ptr(),
+                                    G["stem.conv1.weight"].data_ptr(), G["stem.downsample.0.weight"].data_ptr(), B, _st()),
+                "sunb_stem_wgrad")

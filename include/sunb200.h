@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SUNB_ABI_VERSION 1
+#define SUNB_ABI_VERSION 2
 
 int sunb_abi_version(void);
 const char* sunb_last_error(void);
@@ -60,6 +60,11 @@ typedef struct SunbGemmDesc {
     float* out_f32;         /* nullable */
     int32_t ldc_f32;
     int32_t out_map, oH, oW; /* 0 identity; 1 = 2x2 space-to-depth of an oH x oW raster (feeds PatchEmbed) */
+    void* out2;             /* bf16 copy of the value before `act` (saved for the backward pass), nullable */
+    int32_t ldc2;
+    const void* dact_aux;   /* backward: result *= act'(dact_aux[m, col]) with activation kind `dact`, nullable */
+    int32_t ld_aux;
+    int32_t dact;
 } SunbGemmDesc;
 
 /* impl: 0 = tcgen05 kernel (product path), 1 = SIMT cross-check kernel (tests only) */
@@ -143,6 +148,76 @@ int sunb_soft_ce_forward(const float* x, int ldx, const float* target, int ldt, 
                          float* loss, void* stream);
 int sunb_soft_ce_backward(const float* x, int ldx, const float* target, int ldt, int R, int Rt, int C, const float* gout,
                           float gscale, float* dx, int lddx, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Train-mode building blocks (meta-tuning step, reference: meta_tuning_sun_m/train_meta.py:168-174 driving
+ * autograd through the modules above with BatchNorm in batch-statistics mode and DropPath).
+ * The step schedule lives in few-shot-vit_b200/sunb200/train.py (torch.autograd.Function); every device
+ * operation it issues is one of the entry points below or sunb_gemm / sunb_attention.
+ * ------------------------------------------------------------------------------------------------- */
+
+/* Weight gradient on tcgen05 (MN-major operands, split-K, fp32 atomic accumulation into `out`):
+ *   out[g][tap][m, n] += sum_p dY[p, g*a_goff + m] * X_tap[p, g*b_goff + n]
+ * mode 0: plain rows.  mode 1: X shifted per 3x3 tap over NHWC [B,H,W,ldx] (same box geometry as sunb_gemm). */
+typedef struct SunbWgradDesc {
+    int32_t P, Ma, Nb, Ca, Cb;
+    int32_t groups, a_goff, b_goff;
+    int32_t taps;
+    int32_t mode, H, W, bw, bh;
+    const void* dY; int32_t ldy;     /* bf16 */
+    const void* X; int32_t ldx;      /* bf16 */
+    float* out; int32_t ldo;         /* fp32 [groups][taps][Ma][ldo] */
+    int32_t ksplit;                  /* 0 = choose */
+} SunbWgradDesc;
+int sunb_wgrad(const SunbWgradDesc* desc, void* stream);
+
+/* stem conv1 (3->64, s2) + downsample (3->128, s2) from the fp32 NCHW image (visformer.py:209-210,216);
+ * w1 fp32 [64][27], wd fp32 [128][27], biases fp32; lrelu != 0 applies LeakyReLU(0.1) to the conv1 branch. */
+int sunb_stem_in(const float* x, const float* w1, const float* b1, const float* wd, const float* bd, void* a1, void* idn,
+                 int B, int lrelu, void* stream);
+int sunb_stem_wgrad(const float* x, const void* da1, const void* didn, float* dw1, float* dwd, int B, void* stream);
+
+/* BatchNorm2d, training mode (visformer.py:118-124): column statistics, finalize (+ running stats, momentum),
+ * apply (+ activation, + positional table), and the backward pair. */
+int sunb_colstats(const void* x, int ldx, const void* u, int ldu, long M, int C, float* sum, float* sq, void* stream);
+int sunb_bn_finalize(const float* sum, const float* sq, float count, const float* gamma, const float* beta, float* rmean,
+                     float* rvar, int64_t* nbt, float momentum, float eps, int C, float* scale, float* shift, float* mean,
+                     float* rstd, void* stream);
+int sunb_bn_apply(const void* x, int ldx, const float* scale, const float* shift, int act, const float* tab, int tab_mod,
+                  void* out, int ldo, long M, int C, void* stream);
+int sunb_bn_bwd_finalize(const float* sdz, const float* sdzx, float count, const float* mean, const float* rstd,
+                         const float* gamma, int C, float* a, float* c1, float* c2, float* dgamma, float* dbeta,
+                         void* stream);
+int sunb_bn_bwd_apply(const void* dz, int lddz, const void* x, int ldx, const float* a, const float* c1, const float* c2,
+                      const float* mean, const void* res, int ldr, void* out, int ldo, long M, int C, void* stream);
+
+/* stem tail (visformer.py:232-237 + pos_embed1 :431): BN3(c3) + BNd(id) -> LeakyReLU -> 2x2 max-pool -> + pos */
+int sunb_stem_tail_forward(const void* c3, const void* idn, const float* s3, const float* t3, const float* sd,
+                           const float* td, const float* pos, void* out, int B, void* stream);
+int sunb_stem_tail_backward(const void* c3, const void* idn, const float* s3, const float* t3, const float* sd,
+                            const float* td, const void* g, void* dz, int B, void* stream);
+
+/* final BN (as scale/shift) + global average pool (visformer.py:455-462) and its pooling backward */
+int sunb_final_norm_pool(const void* x, const float* scale, const float* shift, float* dense, void* dense_bf16,
+                         float* pooled, void* pooled_bf16, int B, int T, int C, void* stream);
+int sunb_pool_backward(const float* dpooled, const float* ddense, void* dy, int B, int T, int C, void* stream);
+
+/* helpers: DropPath row scaling (visformer.py:89-97), space-to-depth reorder, positional-embedding gradient,
+ * weight preparation (fp32 master -> bf16 operand layouts), grouped-conv pair packing / gradient extraction */
+int sunb_scale_rows(const void* in, const float* rs, int rows_per_img, void* out, long M, int C, void* stream);
+int sunb_s2d_reorder(const void* in, void* out, int B, int H, int W, int C, int dir, void* stream);
+int sunb_batch_sum(const void* g, int B, long n, float* out, void* stream);
+int sunb_permute_cast(const float* src, long off, long sa, long sb, long sc, int A, int B, int Cd, int ldd, void* dst,
+                      void* stream);
+int sunb_grouped_pairs(const float* w, void* dst, int transpose_flip, void* stream);
+int sunb_grouped_wgrad_extract(const float* scratch, float* dw, void* stream);
+
+/* backward of the attention core and of the episode head */
+int sunb_attention_backward(const void* qkv, const void* dout, void* dqkv, int B, int S, int d, int heads, int ld_qkv,
+                            int ld_out, void* stream);
+int sunb_episode_logits_backward(const float* feat_shot, const float* feat_query, const float* dlogits, float* dshot,
+                                 float* dquery, float* dtemp, int E, int way, int shot, int Q, int D, int metric,
+                                 const float* temp_dev, float temp_host, void* stream);
 
 #ifdef __cplusplus
 }

@@ -150,7 +150,9 @@ def test_token_label_model(golden_dir):
     assert flat.shape == (100, 65)
 
 
-def test_train_mode_fails_loudly():
+def test_frozen_bn_training_fails_loudly():
+    import utils
     m = models.make("meta-baseline", encoder="visformer_micro_80", encoder_args={}).cuda().train()
+    utils.freeze_bn(m)
     with pytest.raises(NotImplementedError):
         m.encoder(torch.zeros(2, 3, 80, 80, device="cuda"))

@@ -1,0 +1,254 @@
+"""-m gpu: train-mode building blocks and the full meta-tuning step against torch autograd (fp32, same rounded inputs)
+and the golden files produced by the real reference (tests/golden/train_step_*.npz).
+
+Stated tolerances (bf16 operands, fp32 accumulate; BASELINE.md section 5 measures the reference itself under bf16
+autocast at 4.8 % median / 13 % worst per-tensor gradient rel-L2 error):
+  kernels vs fp32 torch on identical bf16 inputs : rel-L2 <= 1e-2
+  full step vs fp32 reference                    : loss |delta| <= 0.05 * max(1, loss); per-tensor gradient rel-L2
+                                                   <= 0.25 and cosine >= 0.97; running statistics rel <= 5e-2
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from gpu_helpers import rel_err, max_err  # noqa: E402
+from sunb200 import native as N, train as T, engine  # noqa: E402
+import sun_oracle as O  # noqa: E402
+
+DEV = "cuda"
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+@pytest.mark.parametrize("P,Ma,Nb", [(1024, 128, 128), (1000, 256, 64), (777, 756, 256), (2000, 256, 252), (640, 65, 512)])
+def test_wgrad_plain(P, Ma, Nb):
+    lda, ldb = (Ma + 7) // 8 * 8, (Nb + 7) // 8 * 8
+    dY = torch.full((P, lda), float("nan"), device=DEV, dtype=torch.bfloat16)
+    X = torch.full((P, ldb), float("nan"), device=DEV, dtype=torch.bfloat16)
+    dY[:, :Ma] = rnd(P, Ma, seed=1).bfloat16()
+    X[:, :Nb] = rnd(P, Nb, seed=2).bfloat16()
+    out = torch.zeros(Ma, Nb, device=DEV)
+    T.wgrad(dY, X, out, P, Ma, Nb, Ca=Ma, Cb=Nb)
+    torch.cuda.synchronize()
+    ref = dY[:, :Ma].float().t() @ X[:, :Nb].float()
+    assert rel_err(out, ref) < 2e-3
+    T.wgrad(dY, X, out, P, Ma, Nb, Ca=Ma, Cb=Nb)          # accumulates
+    torch.cuda.synchronize()
+    assert rel_err(out, 2 * ref) < 2e-3
+
+
+@pytest.mark.parametrize("B,H,Cin,Cout,box", [(3, 40, 64, 128, 8), (2, 40, 128, 128, 8), (5, 20, 128, 128, 4)])
+def test_wgrad_conv(B, H, Cin, Cout, box):
+    x = rnd(B, H, H, Cin, seed=3).bfloat16()
+    dy = rnd(B, H, H, Cout, seed=4).bfloat16()
+    out = torch.zeros(9 * Cout, Cin, device=DEV)
+    T.wgrad(dy.view(-1, Cout), x.view(-1, Cin), out, B * H * H, Cout, Cin, taps=9, conv=(H, H, box, box))
+    torch.cuda.synchronize()
+    ref = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (Cout, Cin, 3, 3), dy.float().permute(0, 3, 1, 2),
+                                      padding=1)
+    got = out.view(9, Cout, Cin).permute(1, 2, 0).reshape(Cout, Cin, 3, 3)
+    assert rel_err(got, ref) < 2e-3
+
+
+def test_wgrad_grouped_and_dgrad():
+    B, H = 3, 20
+    x = rnd(B, H, H, 256, seed=5).bfloat16()
+    dy = rnd(B, H, H, 256, seed=6).bfloat16()
+    w = rnd(256, 32, 3, 3, seed=7, scale=0.06)
+    scratch = torch.zeros(2 * 9 * 128, 128, device=DEV)
+    T.wgrad(dy.view(-1, 256), x.view(-1, 256), scratch, B * H * H, 128, 128, Ca=256, Cb=256, taps=9, groups=2, a_goff=128,
+            b_goff=128, conv=(H, H, 4, 4))
+    dw = torch.zeros(256, 32, 3, 3, device=DEV)
+    N.check(N.lib().sunb_grouped_wgrad_extract(scratch.data_ptr(), dw.data_ptr(), N.current_stream()), "extract")
+    xf = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    wf = w.bfloat16().float().requires_grad_(True)
+    y = F.conv2d(xf, wf, padding=1, groups=8)
+    y.backward(dy.float().permute(0, 3, 1, 2))
+    assert rel_err(dw, wf.grad) < 2e-3
+    # dgrad through the pair-packed, mirrored weights
+    dst = torch.empty(4 * 9 * 64, 64, device=DEV, dtype=torch.bfloat16)
+    N.check(N.lib().sunb_grouped_pairs(w.data_ptr(), dst.data_ptr(), 1, N.current_stream()), "pairs")
+    dx = T.gemm(dy.view(-1, 256), dst, B * H * H, 64, 64, out=torch.empty(B * H * H, 256, device=DEV, dtype=torch.bfloat16),
+                taps=9, groups=4, a_goff=64, c_goff=64, conv=(H, H, 4, 4))
+    torch.cuda.synchronize()
+    assert rel_err(dx, xf.grad.permute(0, 2, 3, 1).reshape(-1, 256)) < 1e-2
+
+
+def test_bn_forward_backward_kernels():
+    M, Cc = 5000, 256
+    x = rnd(M, Cc, seed=8).bfloat16() * 2 + 0.5
+    dz = rnd(M, Cc, seed=9).bfloat16()
+    res = rnd(M, Cc, seed=10).bfloat16()
+    gamma, beta = rnd(Cc, seed=11) * 0.2 + 1, rnd(Cc, seed=12) * 0.1
+    P = {"bn.weight": gamma, "bn.bias": beta}
+    Bf = {"bn.running_mean": torch.zeros(Cc, device=DEV), "bn.running_var": torch.ones(Cc, device=DEV),
+          "bn.num_batches_tracked": torch.zeros((), dtype=torch.long, device=DEV)}
+    eng = T.TrainEngine()
+    eng.dev = torch.device(DEV)
+    rec = eng.bn_forward(x, "bn", Cc, M, P, Bf)
+    y = eng.bn_apply(x, rec, M, T.ACT_NONE)
+    G = {"bn.weight": torch.zeros(Cc, device=DEV), "bn.bias": torch.zeros(Cc, device=DEV)}
+    dx = eng.bn_backward(dz, rec, M, P, G, res=res)
+    torch.cuda.synchronize()
+    xr = x.float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm, rv = torch.zeros(Cc, device=DEV), torch.ones(Cc, device=DEV)
+    yr = F.batch_norm(xr, rm, rv, gr, br, training=True, momentum=0.1, eps=1e-5)
+    yr.backward(dz.float())
+    assert rel_err(y, yr) < 5e-3
+    assert rel_err(dx, xr.grad + res.float()) < 1e-2
+    assert rel_err(G["bn.weight"], gr.grad) < 2e-3 and rel_err(G["bn.bias"], br.grad) < 2e-3
+    assert max_err(Bf["bn.running_mean"], rm) < 1e-4 and max_err(Bf["bn.running_var"], rv) < 1e-3
+    assert int(Bf["bn.num_batches_tracked"]) == 1
+
+
+@pytest.mark.parametrize("S,d", [(100, 42), (25, 85)])
+def test_attention_backward(S, d):
+    B, heads = 3, 6
+    inner = heads * d
+    ld3, ldi = (3 * inner + 7) // 8 * 8, (inner + 7) // 8 * 8
+    qkv = torch.zeros(B * S, ld3, device=DEV, dtype=torch.bfloat16)
+    qkv[:, : 3 * inner] = rnd(B * S, 3 * inner, seed=13).bfloat16()
+    dout = torch.zeros(B * S, ldi, device=DEV, dtype=torch.bfloat16)
+    dout[:, :inner] = rnd(B * S, inner, seed=14).bfloat16()
+    dqkv = torch.zeros(B * S, ld3, device=DEV, dtype=torch.bfloat16)
+    N.check(N.lib().sunb_attention_backward(qkv.data_ptr(), dout.data_ptr(), dqkv.data_ptr(), B, S, d, heads, ld3, ldi,
+                                            N.current_stream()), "attention_backward")
+    torch.cuda.synchronize()
+    t = qkv[:, : 3 * inner].float().requires_grad_(True)
+    u = t.reshape(B, S, 3, heads, d).permute(2, 0, 3, 1, 4)
+    p = torch.softmax(u[0] @ u[1].transpose(-1, -2) * d ** -0.5, dim=-1)
+    o = (p @ u[2]).permute(0, 2, 1, 3).reshape(B * S, inner)
+    o.backward(dout[:, :inner].float())
+    assert rel_err(dqkv[:, : 3 * inner], t.grad) < 1e-2
+
+
+@pytest.mark.parametrize("metric", ["cos", "sqr", "dot"])
+def test_episode_logits_backward(metric):
+    E, way, shot, Q, D = 2, 5, 3, 20, 512
+    fs = rnd(E, way, shot, D, seed=15).requires_grad_(True)
+    fq = rnd(E, Q, D, seed=16).requires_grad_(True)
+    temp = torch.tensor(10.0, device=DEV, requires_grad=True)
+    dl = rnd(E, Q, way, seed=17)
+    out = engine.episode_logits(fs, fq, temp, metric)
+    out.backward(dl)
+    fs2, fq2 = fs.detach().cpu().requires_grad_(True), fq.detach().cpu().requires_grad_(True)
+    t2 = torch.tensor(10.0, requires_grad=True)
+    ref = O.compute_logits(fq2, fs2.mean(2), metric, t2)
+    ref.backward(dl.cpu())
+    assert rel_err(fs.grad.cpu(), fs2.grad) < 1e-4 and rel_err(fq.grad.cpu(), fq2.grad) < 1e-4
+    assert abs(temp.grad.item() - t2.grad.item()) < 1e-3 * max(1.0, abs(t2.grad.item()))
+
+
+def test_stem_tail_forward_backward():
+    B = 3
+    c3, idn = rnd(B * 1600, 128, seed=18).bfloat16(), rnd(B * 1600, 128, seed=19).bfloat16()
+    s3, t3, sd, td = rnd(128, seed=20) * 0.2 + 1, rnd(128, seed=21) * 0.1, rnd(128, seed=22) * 0.2 + 1, rnd(128, seed=23) * 0.1
+    pos = rnd(400, 128, seed=24) * 0.02
+    g = rnd(B * 400, 128, seed=25).bfloat16()
+    out = torch.empty(B * 400, 128, device=DEV, dtype=torch.bfloat16)
+    dz = torch.empty(B * 1600, 128, device=DEV, dtype=torch.bfloat16)
+    lib, st = N.lib(), N.current_stream()
+    N.check(lib.sunb_stem_tail_forward(c3.data_ptr(), idn.data_ptr(), s3.data_ptr(), t3.data_ptr(), sd.data_ptr(),
+                                       td.data_ptr(), pos.data_ptr(), out.data_ptr(), B, st), "tail fwd")
+    N.check(lib.sunb_stem_tail_backward(c3.data_ptr(), idn.data_ptr(), s3.data_ptr(), t3.data_ptr(), sd.data_ptr(),
+                                        td.data_ptr(), g.data_ptr(), dz.data_ptr(), B, st), "tail bwd")
+    torch.cuda.synchronize()
+    z = (c3.float() * s3 + t3 + idn.float() * sd + td).view(B, 40, 40, 128).permute(0, 3, 1, 2).requires_grad_(True)
+    y = F.max_pool2d(F.leaky_relu(z, 0.1), 2).permute(0, 2, 3, 1).reshape(B * 400, 128) + pos.repeat(B, 1)
+    y.backward(g.float())
+    assert rel_err(out, y) < 5e-3
+    assert rel_err(dz, z.grad.permute(0, 2, 3, 1).reshape(-1, 128)) < 5e-3
+
+
+def _draw_dp_masks(seed, rate, batch):
+    rates = O.drop_path_rates(rate)
+    torch.manual_seed(seed)
+    names = [f"stage1.{i}" for i in range(4)] + [f"stage2.{i}" for i in range(2)] + [f"stage3.{i}" for i in range(3)]
+    masks = {}
+    for bi, name in enumerate(names):
+        if rates[bi] <= 0:
+            continue
+        n = 1 if name.startswith("stage1") else 2
+        masks[name] = [torch.floor((1 - rates[bi]) + torch.rand(batch, 1, 1, 1)) for _ in range(n)]
+    return masks, rates, names
+
+
+@pytest.mark.parametrize("tag,rate", [("dp0", 0.0), ("dp05", 0.5)])
+def test_meta_tuning_step_vs_reference(golden_dir, tag, rate):
+    import models
+    import utils
+    import utils.few_shot as fs
+    g = np.load(os.path.join(golden_dir, f"train_step_{tag}.npz"))
+    sd = O.calibrate_bn(O.init_meta_baseline_state_dict(12345))
+    model = models.make("meta-baseline", encoder="visformer_micro_80", encoder_args={"drop_path_rate": rate})
+    model.load_state_dict(sd)
+    model = model.cuda().train()
+    way, shot, query, ep = 3, 1, 2, 2
+    data = O.make_episode_images(500, ep * way, shot + query)
+    xs, xq = fs.split_shot_query(data.cuda(), way, shot, query, ep_per_batch=ep)
+    label = fs.make_nk_label(way, query, ep).cuda()
+    scales = None
+    if rate > 0:        # replay the reference's DropPath draws (CPU RNG stream under seed 77)
+        masks, rates, names = _draw_dp_masks(77, rate, data.shape[0])
+        scales = {n: [(m.view(-1) / (1 - rates[names.index(n)])).cuda() for m in ms] for n, ms in masks.items()}
+        model.encoder._drop_path_scales = lambda batch, device: scales
+    logits = model(xs, xq).view(-1, way)
+    loss = F.cross_entropy(logits, label)
+    model.zero_grad()
+    loss.backward()
+    torch.cuda.synchronize()
+    print(f"[{tag}] loss {loss.item():.5f} vs reference {float(g['loss']):.5f}; "
+          f"max |dlogit| {max_err(logits.detach().cpu(), torch.as_tensor(g['logits'])):.4f}")
+    assert abs(loss.item() - float(g["loss"])) <= 0.05 * max(1.0, abs(float(g["loss"])))
+    assert max_err(logits.detach().cpu(), torch.as_tensor(g["logits"])) < 0.35
+    zero_grad = {"encoder.patch_embed2.proj.bias", "encoder.patch_embed2.norm.bn.bias",
+                 "encoder.patch_embed3.proj.bias", "encoder.patch_embed3.norm.bn.bias"}
+    report, bad = [], []
+    for name, p in model.named_parameters():
+        assert p.grad is not None, name
+        gr = p.grad.detach().cpu().float()
+        ref_norm = float(g["gnorm." + name])
+        if name in zero_grad:
+            if gr.abs().max().item() > 2e-2 * max(1.0, ref_norm):
+                bad.append((name, "nonzero", gr.abs().max().item()))
+            continue
+        if "grad." + name in g.files:
+            ref = torch.as_tensor(g["grad." + name])
+            rel = ((gr - ref).norm() / (ref.norm() + 1e-12)).item()
+            cos = F.cosine_similarity(gr.flatten(), ref.flatten(), dim=0).item()
+        else:
+            ref = torch.as_tensor(g["gsamp." + name])
+            samp = gr.flatten()[:: max(1, gr.numel() // 2048)]
+            rel = ((samp - ref).norm() / (ref.norm() + 1e-12)).item()
+            cos = F.cosine_similarity(samp, ref, dim=0).item()
+        report.append((rel, cos, name))
+        if not (rel <= 0.25 and cos >= 0.97):
+            bad.append((name, rel, cos))
+    report.sort(reverse=True)
+    rels = sorted(r for r, _, _ in report)
+    print(f"[{tag}] gradient rel-L2: median {rels[len(rels) // 2]:.4f}, worst {report[0][0]:.4f} ({report[0][2]})")
+    for r, c, n in report[:8]:
+        print(f"    {n:50s} rel {r:.4f} cos {c:.5f}")
+    assert not bad, bad[:10]
+    for k in g.files:
+        if k.startswith("bn."):
+            name = k[3:]
+            got = model.state_dict()[name].cpu()
+            ref = torch.as_tensor(g[k])
+            assert ((got - ref).norm() / (ref.norm() + 1e-12)).item() < 5e-2, name
+    # one SGD step exactly as the reference builds it, on the natively computed gradients
+    opt, _ = utils.make_optimizer(model.parameters(), "sgd", lr=1e-3, weight_decay=5e-4)
+    opt.step()
+    assert abs(model.temp.item() - float(g["after_sgd.temp"])) < 1e-3
+    got = model.encoder.stage3[2].attn.proj.weight.detach().flatten()[::128].cpu()
+    assert rel_err(got, torch.as_tensor(g["after_sgd.encoder.stage3.2.attn.proj.weight.samp"])) < 1e-3

@@ -95,7 +95,7 @@ def test_c_abi_exports_every_declared_symbol():
     lib = ctypes.CDLL(N.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
-    assert N.lib().sunb_abi_version() == 1
+    assert N.lib().sunb_abi_version() == N.ABI_VERSION
     # struct layouts mirror the header (sizes are what the C compiler produces for these field lists)
     assert ctypes.sizeof(N.ConvMlpW) == 32 and ctypes.sizeof(N.AttnBlockW) == 48
     assert ctypes.sizeof(N.EncoderWeights) == 9 * 8 + 4 * 32 + 16 + 2 * 48 + 16 + 3 * 48 + 16
