@@ -178,6 +178,72 @@ def time_dominant_kernel(model_state, device, peaks_tf):
             "ms_per_launch": ms, "flops_per_launch": flops}
 
 
+TRAIN_WAY, TRAIN_SHOT, TRAIN_QUERY, TRAIN_EPISODES = 10, 1, 5, 8      # meta_tuning_sun_m/configs/train_meta_mini_visformer_1shot.yaml
+TRAIN_IMAGES = TRAIN_EPISODES * TRAIN_WAY * (TRAIN_SHOT + TRAIN_QUERY)  # 480 per step (whole job)
+
+
+def measure_train_step(args, device, world, rank, sd):
+    """SUN-M meta-tuning step (BASELINE.json configs[2]): fwd + bwd + gradient all-reduce + SGD through the public API.
+    The 8-episode batch is sharded over ranks as nn.DataParallel would (strong scaling); max-over-ranks device time."""
+    import torch
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    import models
+    import utils
+    import utils.few_shot as fs
+    from sunb200.dist import GradAllReducer, broadcast_module_state, shard_range
+    if TRAIN_EPISODES % world:
+        return None
+    torch.manual_seed(1234 + rank)
+    model = models.make("meta-baseline", encoder="visformer_micro_80", encoder_args={"drop_path_rate": 0.5})
+    model.load_state_dict(sd)
+    model = model.to(device).train()
+    broadcast_module_state(model)
+    opt, _ = utils.make_optimizer(model.parameters(), "sgd", lr=1e-3, weight_decay=5e-4)
+    reducer = GradAllReducer(model.parameters())
+    lo, hi = shard_range(TRAIN_EPISODES, rank, world)
+    ep = hi - lo
+    g = torch.Generator(device=device).manual_seed(77 + rank)
+    protos = torch.randn(ep, TRAIN_WAY, 1, 3, 80, 80, generator=g, device=device)
+    data = (protos + 0.5 * torch.randn(ep, TRAIN_WAY, TRAIN_SHOT + TRAIN_QUERY, 3, 80, 80, generator=g, device=device))
+    data = data.reshape(-1, 3, 80, 80)
+    label = fs.make_nk_label(TRAIN_WAY, TRAIN_QUERY, ep).to(device)
+
+    def step():
+        xs, xq = fs.split_shot_query(data, TRAIN_WAY, TRAIN_SHOT, TRAIN_QUERY, ep_per_batch=ep)
+        logits = model(xs, xq).view(-1, TRAIN_WAY)
+        loss = F.cross_entropy(logits, label)
+        reducer.attach()
+        reducer.flat.zero_()
+        loss.backward()
+        reducer.all_reduce_mean()
+        opt.step()
+        return loss
+
+    for _ in range(3):
+        loss = step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    flops = 3.0 * TRAIN_IMAGES * FLOP_PER_IMAGE
+    return {"metric": "SUN-M meta-tuning step (fwd+bwd+allreduce+SGD)", "ms_per_step": ms.item(), "unit": "ms",
+            "images_per_step": TRAIN_IMAGES, "episodes_per_gpu": ep, "scaling": "strong", "higher_is_better": False,
+            "achieved_tflops_per_gpu": flops / world / (ms.item() * 1e-3) / 1e12, "loss_last": float(loss.item()),
+            "config": "8 episodes x 10-way x (1 shot + 5 query), drop_path_rate 0.5, SGD(1e-3, 0.9, wd 5e-4), "
+                      "BN batch statistics per replica"}
+
+
 def run_product(args):
     import torch
     import torch.distributed as dist
@@ -196,6 +262,11 @@ def run_product(args):
     burst_tf, sustained_tf, hbm_gbs, peak_src = load_peaks()
 
     sd = O.calibrate_bn(O.init_meta_baseline_state_dict(12345))        # random-init, BN-calibrated (W1)
+    if os.environ.get("SUNB_BENCH_PROFILE") == "train":                # short run for ncu: the meta-tuning step only
+        t = measure_train_step(args, device, world, rank, sd)
+        if rank == 0:
+            print(json.dumps({"profile_mode": "train", "train_step": t}))
+        return
     model = models.make("meta-baseline", encoder="visformer_micro_80", encoder_args={})
     model.load_state_dict(sd)
     model = model.to(device).eval()
@@ -260,6 +331,10 @@ def run_product(args):
         # sanity: accuracy of the last step's logits on the class-structured episodes (not part of the timing)
         acc = (outs[0].reshape(-1, WAY).argmax(1) == label).float().mean().item()
 
+    train = None
+    if not profile_mode and os.environ.get("SUNB_BENCH_TRAIN", "1") == "1":
+        train = measure_train_step(args, device, world, rank, sd)
+
     episodes = world * EPISODES_PER_GPU * args.steps
     value = episodes / (ms_total * 1e-3)
     e2e_value = episodes / (ms_e2e * 1e-3)
@@ -289,6 +364,7 @@ def run_product(args):
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                              "sample": f"{cpu_n} episodes (100 images each) of the same workload in {cpu_dt:.1f} s, oracle port, torch fp32"},
             "sanity_acc": acc,
+            "train_step": train,
         }
         print(json.dumps(line))
     if world > 1:
