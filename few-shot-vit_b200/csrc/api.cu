@@ -30,6 +30,9 @@ int sunb_launch_episode_logits_bwd(const float* feat_shot, const float* feat_que
                                    const float* temp_dev, float temp_host, cudaStream_t stream);
 int sunb_launch_wgrad_tc(WgradParams p, cudaStream_t stream);
 
+int sunb_launch_layernorm_rows(const float* x, const float* gamma, const float* beta, float* y, long M, int C, float eps,
+                               cudaStream_t stream);
+
 static thread_local char g_err[512] = "";
 
 void sunb_set_error(const char* fmt, ...) {
@@ -336,6 +339,11 @@ int sunb_episode_logits_backward(const float* feat_shot, const float* feat_query
     SUNB_REQUIRE(feat_shot && feat_query && dlogits && dshot && dquery, "episode_logits_backward: null argument");
     return sunb_launch_episode_logits_bwd(feat_shot, feat_query, dlogits, dshot, dquery, dtemp, E, way, shot, Q, D, metric,
                                           temp_dev, temp_host, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int sunb_layernorm_rows(const float* x, const float* gamma, const float* beta, float* y, long M, int C, float eps,
+                        void* stream) {
+    return sunb_launch_layernorm_rows(x, gamma, beta, y, M, C, eps, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -279,3 +279,33 @@ int sunb_launch_episode_logits_bwd(const float* feat_shot, const float* feat_que
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Channel LayerNorm over NHWC rows (reference: LayerNorm wrapper, test_phase/models/visformer.py:109-115 --
+// not instantiated by visformer_micro_80; provided for API completeness).  One warp per row, fp32, two-pass variance.
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, float* __restrict__ y, long M,
+                                                             int C, float eps) {
+    const long row = blockIdx.x * 8L + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const float* xr = x + row * C;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += xr[c];
+    const float mean = warp_sum(s) / (float)C;
+    float v = 0.f;
+    for (int c = lane; c < C; c += 32) { const float d = xr[c] - mean; v = fmaf(d, d, v); }
+    const float rstd = rsqrtf(warp_sum(v) / (float)C + eps);
+    for (int c = lane; c < C; c += 32) y[row * C + c] = (xr[c] - mean) * rstd * gamma[c] + beta[c];
+}
+}  // namespace
+
+int sunb_launch_layernorm_rows(const float* x, const float* gamma, const float* beta, float* y, long M, int C, float eps,
+                               cudaStream_t stream) {
+    SUNB_REQUIRE(x && gamma && beta && y && M > 0 && C > 0, "layernorm_rows: bad arguments");
+    layernorm_rows_kernel<<<(int)((M + 7) / 8), 256, 0, stream>>>(x, gamma, beta, y, M, C, eps);
+    SUNB_CHECK_CUDA(cudaGetLastError());
+    return SUNB_OK;
+}

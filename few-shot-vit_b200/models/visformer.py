@@ -29,6 +29,26 @@ def _conv(cin, cout, k, stride=1, padding=0, groups=1, bias=False):
     return nn.Conv2d(cin, cout, k, stride=stride, padding=padding, groups=groups, bias=bias)
 
 
+class LayerNorm(nn.Module):
+    """Channel LayerNorm on NCHW tensors (reference wrapper visformer.py:109-115; unused by 'visformer_micro_80').
+    Inference-only native kernel (sunb_layernorm_rows) over the NHWC view."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.ln = nn.LayerNorm(dim)
+
+    def forward(self, x):
+        from sunb200 import native as N
+        N.require_cuda(x)
+        rows = x.permute(0, 2, 3, 1).contiguous().float()
+        out = torch.empty_like(rows)
+        M, Cc = rows.numel() // rows.shape[-1], rows.shape[-1]
+        N.check(N.lib().sunb_layernorm_rows(rows.data_ptr(), self.ln.weight.detach().float().data_ptr(),
+                                            self.ln.bias.detach().float().data_ptr(), out.data_ptr(), M, Cc,
+                                            float(self.ln.eps), N.current_stream()), "sunb_layernorm_rows")
+        return out.permute(0, 3, 1, 2)
+
+
 class BatchNorm(_Holder):
     def __init__(self, dim):
         super().__init__()

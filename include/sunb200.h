@@ -212,6 +212,11 @@ int sunb_permute_cast(const float* src, long off, long sa, long sb, long sc, int
 int sunb_grouped_pairs(const float* w, void* dst, int transpose_flip, void* stream);
 int sunb_grouped_wgrad_extract(const float* scratch, float* dw, void* stream);
 
+/* channel LayerNorm over NHWC rows, fp32 (LayerNorm wrapper, test_phase/models/visformer.py:109-115; not instantiated by
+ * 'visformer_micro_80', provided for API completeness) */
+int sunb_layernorm_rows(const float* x, const float* gamma, const float* beta, float* y, long M, int C, float eps,
+                        void* stream);
+
 /* backward of the attention core and of the episode head */
 int sunb_attention_backward(const void* qkv, const void* dout, void* dqkv, int B, int S, int d, int heads, int ld_qkv,
                             int ld_out, void* stream);

@@ -176,3 +176,14 @@ def test_soft_ce_forward_backward(golden_dir):
     x2 = torch.cat([s_logits, s_logits * 0.5]).to(DEV)
     l2 = engine.soft_target_cross_entropy(x2, soft.to(DEV))
     assert abs(l2.item() - O.soft_target_cross_entropy(x2.cpu(), soft).item()) < 1e-4
+
+
+def test_layernorm_wrapper():
+    from models.visformer import LayerNorm
+    ln = LayerNorm(96).cuda()
+    with torch.no_grad():
+        ln.ln.weight.copy_(rnd(96, seed=30) * 0.2 + 1)
+        ln.ln.bias.copy_(rnd(96, seed=31) * 0.1)
+    x = rnd(3, 96, 7, 5, seed=32) * 3 + 1
+    ref = F.layer_norm(x.permute(0, 2, 3, 1), (96,), ln.ln.weight, ln.ln.bias, ln.ln.eps).permute(0, 3, 1, 2)
+    assert max_err(ln(x), ref) < 1e-5
