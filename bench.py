@@ -344,7 +344,12 @@ def run_product(args):
     if rank == 0:
         roof = time_dominant_kernel(sd, device, burst_tf)
         roof["peak_source"] = f"{peak_src} burst bf16 (MEASURED_PEAKS.json)"
-        cpu_v, cpu_n, cpu_dt = cpu_oracle_eps_per_s(min_seconds=10.0, max_episodes=20)
+        if world == 1:      # the CPU baseline is reported at N=1 only (torchrun pins OMP_NUM_THREADS=1 per rank)
+            cpu_v, cpu_n, cpu_dt = cpu_oracle_eps_per_s(min_seconds=10.0, max_episodes=20)
+            cpu_base = {"value": cpu_v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                        "sample": f"{cpu_n} episodes (100 images each) of the same workload in {cpu_dt:.1f} s, oracle port, torch fp32"}
+        else:
+            cpu_base = None
         path_tf = value / world * FLOP_PER_EPISODE / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -361,8 +366,7 @@ def run_product(args):
             "roofline": roof,
             "path_roofline": {"achieved": path_tf, "peak": sustained_tf, "unit": "TFLOP/s", "frac": path_tf / sustained_tf,
                               "note": "whole eval step per GPU: 203.06 GFLOP/episode algorithmic vs sustained bf16 peak"},
-            "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                             "sample": f"{cpu_n} episodes (100 images each) of the same workload in {cpu_dt:.1f} s, oracle port, torch fp32"},
+            "cpu_baseline": cpu_base,
             "sanity_acc": acc,
             "train_step": train,
         }

@@ -127,55 +127,103 @@ __device__ __forceinline__ int map_out_row(const GemmParams& p, int m) {
 }
 
 // Epilogue for NC consecutive columns [col, col+NC) of raster row m of group g.  v = fp32 accumulators.
+// Every per-element loop is branch-free inside (the activation switch is hoisted) so the unrolled bodies interleave.
 template <int NC>
 __device__ __forceinline__ void epilogue_row(const GemmParams& p, int g, int m, int col, float* v) {
     if (m >= p.M) return;
     const int ncol = min(NC, p.N - col);
     if (ncol <= 0) return;
     const int gcol = g * p.c_goff + col;
-    const float rs = p.row_scale ? p.row_scale[m / p.rows_per_img] : 1.f;
-    const float* bias = p.bias ? p.bias + (size_t)(m % p.bias_mod) * p.bias_ld + gcol : nullptr;
-    const bf16* res = p.resid ? p.resid + (size_t)m * p.ldr + gcol : nullptr;
-    const bool full = (ncol == NC);
-    if (res) {
-        if (full && (NC % 8 == 0) && ((((size_t)res) & 15) == 0)) {
+    const bool full = (ncol == NC) && (NC % 8 == 0);
+    if (p.row_scale) {
+        const float rs = p.row_scale[m / p.rows_per_img];
+#pragma unroll
+        for (int i = 0; i < NC; ++i) v[i] *= rs;
+    }
+    if (p.resid) {
+        const bf16* res = p.resid + (size_t)m * p.ldr + gcol;
+        if (full && ((((size_t)res) & 15) == 0)) {
 #pragma unroll
             for (int i = 0; i < NC; i += 8) {
-                uint4 u = *reinterpret_cast<const uint4*>(res + i);
+                const uint4 u = *reinterpret_cast<const uint4*>(res + i);
                 const bf16* h = reinterpret_cast<const bf16*>(&u);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[i + j] = v[i + j] * rs + __bfloat162float(h[j]);
+                for (int j = 0; j < 8; ++j) v[i + j] += __bfloat162float(h[j]);
             }
         } else {
 #pragma unroll
             for (int i = 0; i < NC; ++i)
-                if (i < ncol) v[i] = v[i] * rs + __bfloat162float(res[i]);
+                if (i < ncol) v[i] += __bfloat162float(res[i]);
         }
-    } else if (p.row_scale) {
+    }
+    if (p.bias) {
+        const float* bias = p.bias + (size_t)(m % p.bias_mod) * p.bias_ld + gcol;
+        if (full && ((((size_t)bias) & 15) == 0)) {
 #pragma unroll
-        for (int i = 0; i < NC; ++i) v[i] *= rs;
+            for (int i = 0; i < NC; i += 4) {
+                const float4 b = *reinterpret_cast<const float4*>(bias + i);
+                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NC; ++i)
+                if (i < ncol) v[i] += bias[i];
+        }
     }
     const int orow = map_out_row(p, m);
     if (p.out2) {                                   // training forward: keep the pre-activation for the backward pass
         bf16* o2 = p.out2 + (size_t)orow * p.ldc2 + gcol;
+        if (full && ((((size_t)o2) & 15) == 0)) {
 #pragma unroll
-        for (int i = 0; i < NC; ++i)
-            if (i < ncol) o2[i] = __float2bfloat16(v[i] + (bias ? bias[i] : 0.f));
+            for (int i = 0; i < NC; i += 8) {
+                uint4 u;
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[i + 2 * j], v[i + 2 * j + 1]);
+                *reinterpret_cast<uint4*>(o2 + i) = u;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NC; ++i)
+                if (i < ncol) o2[i] = __float2bfloat16(v[i]);
+        }
     }
+    if (p.act == ACT_GELU) {
 #pragma unroll
-    for (int i = 0; i < NC; ++i) {
-        float b = (bias && i < ncol) ? bias[i] : 0.f;
-        v[i] = act_apply(v[i] + b, p.act);
+        for (int i = 0; i < NC; ++i) v[i] = 0.5f * v[i] * (1.f + erf_fast(v[i] * 0.70710678118654752f));
+    } else if (p.act == ACT_LRELU) {
+#pragma unroll
+        for (int i = 0; i < NC; ++i) v[i] = v[i] > 0.f ? v[i] : 0.1f * v[i];
     }
     if (p.dact_aux) {                               // backward: chain through the activation of the producing layer
         const bf16* ax = p.dact_aux + (size_t)m * p.ld_aux + gcol;
+        float a[NC];
+        if (full && ((((size_t)ax) & 15) == 0)) {
 #pragma unroll
-        for (int i = 0; i < NC; ++i)
-            if (i < ncol) v[i] *= act_grad(__bfloat162float(ax[i]), p.dact);
+            for (int i = 0; i < NC; i += 8) {
+                const uint4 u = *reinterpret_cast<const uint4*>(ax + i);
+                const bf16* h = reinterpret_cast<const bf16*>(&u);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[i + j] = __bfloat162float(h[j]);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NC; ++i) a[i] = (i < ncol) ? __bfloat162float(ax[i]) : 0.f;
+        }
+        if (p.dact == ACT_GELU) {
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                const float cdf = 0.5f * (1.f + erf_fast(a[i] * 0.70710678118654752f));
+                v[i] *= cdf + a[i] * 0.3989422804014327f * __expf(-0.5f * a[i] * a[i]);
+            }
+        } else if (p.dact == ACT_LRELU) {
+#pragma unroll
+            for (int i = 0; i < NC; ++i) v[i] *= a[i] > 0.f ? 1.f : 0.1f;
+        }
     }
     if (p.out) {
         bf16* o = p.out + (size_t)orow * p.ldc + gcol;
-        if (full && (NC % 8 == 0) && ((((size_t)o) & 15) == 0)) {
+        if (full && ((((size_t)o) & 15) == 0)) {
 #pragma unroll
             for (int i = 0; i < NC; i += 8) {
                 uint4 u;
