@@ -103,17 +103,18 @@ __device__ __forceinline__ float act_grad(float x, int act) {
     return 1.f;
 }
 
-// raster row of tile-row r (conv mode tiles are made of (bw x bh) sub-boxes)
+// raster row of tile-row r.  A conv-mode tile is one (bw x bh) spatial block of 128/(bw*bh) consecutive images, so the
+// whole A tile is a single 4-D TMA box (channels, bw, bh, images).  Images past the batch map to M (dropped).
 __device__ __forceinline__ int conv_tile_row_to_pixel(const GemmParams& p, int tile, int r) {
     const int box = p.bw * p.bh;
-    const int nsub = 128 / box;
+    const int nimg = 128 / box;
     const int tiles_x = p.W / p.bw, spi = tiles_x * (p.H / p.bh);
-    const int st = tile * nsub + r / box;
+    const int blk = tile % spi, img = (tile / spi) * nimg + r / box;
     const int rr = r % box;
-    const int img = st / spi, rem = st % spi;
-    const int y = (rem / tiles_x) * p.bh + rr / p.bw;
-    const int x = (rem % tiles_x) * p.bw + rr % p.bw;
-    return (img * p.H + y) * p.W + x;
+    const int y = (blk / tiles_x) * p.bh + rr / p.bw;
+    const int x = (blk % tiles_x) * p.bw + rr % p.bw;
+    const int m = (img * p.H + y) * p.W + x;
+    return m < p.M ? m : p.M;
 }
 
 __device__ __forceinline__ int map_out_row(const GemmParams& p, int m) {

@@ -10,6 +10,7 @@
 #include "common.cuh"
 
 #include <mutex>
+#include <stdlib.h>
 
 namespace {
 
@@ -119,7 +120,8 @@ struct SmemLayout {
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);   // ~192 KB ring, one persistent CTA per SM
-    static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;
+    static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;       // 192 KB for every BN
+    static constexpr int MAX_RING = 12;                           // barrier slots (weight-stationary mode has up to 10 A stages)
     static constexpr int BAR_BYTES = 256;
     static constexpr int TOTAL = TILE_BYTES + BAR_BYTES + 1024;   // + slack for 1024-byte alignment
 };
@@ -127,29 +129,40 @@ struct SmemLayout {
 // Persistent kernel: CTA b processes tiles b, b + gridDim.x, ...  (tile id = (m_tile * groups + g) * n_tiles + n_tile).
 // The smem ring runs continuously across tiles; two TMEM accumulators let the epilogue of tile i overlap the
 // MMAs of tile i + 1.
-template <int BN>
+// BSTAT (weight-stationary): a CTA keeps one (n-tile, group) for its whole life, loads that tile's complete weight
+// operand (all taps x K blocks) into shared memory once, and streams only activation tiles through the ring.
+template <int BN, bool BSTAT>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                  const __grid_constant__ CUtensorMap tmB,
                                                                  const GemmParams p, const int n_tiles,
-                                                                 const int total_tiles) {
+                                                                 const int total_tiles, const int a_stages) {
     using L = SmemLayout<BN>;
-    constexpr int STAGES = L::STAGES;
+    constexpr int MAXR = L::MAX_RING;
+    const int STAGES = BSTAT ? a_stages : L::STAGES;
     constexpr uint32_t TMEM_COLS = 2 * BN;           // two accumulators; 128 / 256 / 512 columns
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-    const uint32_t bars = smem_base + L::TILE_BYTES;    // full[STAGES], empty[STAGES], acc_full[2], acc_empty[2]
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + L::TILE_BYTES + 8 * (2 * STAGES + 4));
+    const uint32_t bars = smem_base + L::TILE_BYTES;    // full[MAXR], empty[MAXR], acc_full[2], acc_empty[2], b_full
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + L::TILE_BYTES + 8 * (2 * MAXR + 5));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kpt = (p.K + BK - 1) / BK;
     const int nk = p.taps * kpt;
 
     auto full_bar = [&](int s) { return bars + 8u * s; };
-    auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
-    auto acc_full = [&](int a) { return bars + 8u * (2 * STAGES + a); };
-    auto acc_empty = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
+    auto empty_bar = [&](int s) { return bars + 8u * (MAXR + s); };
+    auto acc_full = [&](int a) { return bars + 8u * (2 * MAXR + a); };
+    auto acc_empty = [&](int a) { return bars + 8u * (2 * MAXR + 2 + a); };
+    const uint32_t b_full = bars + 8u * (2 * MAXR + 4);
+    // smem map: generic mode = ring of (A|B) stages; stationary mode = [nk B blocks][ring of A stages]
+    const uint32_t ring_base = BSTAT ? smem_base + nk * L::B_BYTES : smem_base;
+    constexpr uint32_t RING_STRIDE = BSTAT ? L::A_BYTES : L::STAGE_BYTES;
+    // tile schedule
+    const int slots = n_tiles * p.groups;
+    const int tile0 = BSTAT ? (blockIdx.x / slots) * slots + (blockIdx.x % slots) : blockIdx.x;
+    const int tstep = gridDim.x;                         // stationary mode: gridDim.x is a multiple of slots
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -160,6 +173,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             mbar_init(acc_full(a), 1);
             mbar_init(acc_empty(a), NUM_EPI_WARPS);
         }
+        mbar_init(b_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {   // whole warp allocates TMEM, base address lands in shared memory
@@ -176,12 +190,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-            const int box = p.bw * p.bh;
-            const int nsub = p.a_mode ? BM / box : 1;
+            const int nimg = p.a_mode ? BM / (p.bw * p.bh) : 1;
             const int tiles_x = p.a_mode ? p.W / p.bw : 1;
             const int spi = p.a_mode ? tiles_x * (p.H / p.bh) : 1;
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            if (BSTAT && tile0 < total_tiles) {          // the whole weight operand of this CTA's (n-tile, group), once
+                const int n0 = (tile0 % n_tiles) * BN;
+                const int g = (tile0 / n_tiles) % p.groups;
+                mbar_expect_tx(b_full, nk * L::B_BYTES);
+                for (int kb = 0; kb < nk; ++kb)
+                    tma_load_2d(smem_base + kb * L::B_BYTES, &tmB, b_full, (kb % kpt) * BK,
+                                (g * p.taps + kb / kpt) * p.N + n0);
+            }
+            for (int tile = tile0; tile < total_tiles; tile += tstep) {
                 const int n0 = (tile % n_tiles) * BN;
                 const int g = (tile / n_tiles) % p.groups;
                 const int m_tile = tile / (n_tiles * p.groups);
@@ -189,23 +210,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(empty_bar(s), ph ^ 1);
-                    const uint32_t a_dst = smem_base + s * L::STAGE_BYTES;
+                    const uint32_t a_dst = ring_base + s * RING_STRIDE;
                     const uint32_t b_dst = a_dst + L::A_BYTES;
-                    mbar_expect_tx(full_bar(s), L::STAGE_BYTES);
+                    mbar_expect_tx(full_bar(s), BSTAT ? L::A_BYTES : L::STAGE_BYTES);
                     const int tap = kb / kpt, kc = kb % kpt;
                     if (p.a_mode == 0) {
                         tma_load_2d(a_dst, &tmA, full_bar(s), g * p.a_goff + kc * BK, m_tile * BM);
                     } else {
+                        // one box: (64 channels, bw, bh, nimg images) of spatial block `blk`, shifted by the tap
                         const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-                        for (int j = 0; j < nsub; ++j) {
-                            const int st = m_tile * nsub + j;
-                            const int img = st / spi, rem = st % spi;
-                            const int y0 = (rem / tiles_x) * p.bh, x0 = (rem % tiles_x) * p.bw;
-                            tma_load_4d(a_dst + j * box * 128, &tmA, full_bar(s), g * p.a_goff + kc * BK, x0 + dx,
-                                        y0 + dy, img);
-                        }
+                        const int blk = m_tile % spi, img0 = (m_tile / spi) * nimg;
+                        tma_load_4d(a_dst, &tmA, full_bar(s), g * p.a_goff + kc * BK, (blk % tiles_x) * p.bw + dx,
+                                    (blk / tiles_x) * p.bh + dy, img0);
                     }
-                    tma_load_2d(b_dst, &tmB, full_bar(s), kc * BK, (g * p.taps + tap) * p.N + n0);
+                    if (!BSTAT) tma_load_2d(b_dst, &tmB, full_bar(s), kc * BK, (g * p.taps + tap) * p.N + n0);
                 }
             }
         }
@@ -213,7 +231,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(BM, BN);
             uint32_t it = 0, lt = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+            if (BSTAT && tile0 < total_tiles) mbar_wait(b_full, 0);
+            for (int tile = tile0; tile < total_tiles; tile += tstep, ++lt) {
                 const uint32_t acc = lt & 1, aph = (lt >> 1) & 1;
                 mbar_wait(acc_empty(acc), aph ^ 1);       // epilogue has drained this accumulator
                 tc_fence_after();
@@ -223,9 +242,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(full_bar(s), ph);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_base + s * L::STAGE_BYTES;
+                    const uint32_t a_addr = ring_base + s * RING_STRIDE;
                     const uint64_t a_desc = make_sw128_desc(a_addr);
-                    const uint64_t b_desc = make_sw128_desc(a_addr + L::A_BYTES);
+                    const uint64_t b_desc = make_sw128_desc(BSTAT ? smem_base + kb * L::B_BYTES : a_addr + L::A_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)   // advance 32 bytes (2 x 16-byte units) per UMMA_K = 16
                         umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) ? 1u : 0u);
@@ -240,7 +259,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         const int half = (warp - 2) >> 2;
         const int r = q * 32 + lane;
         uint32_t lt = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        for (int tile = tile0; tile < total_tiles; tile += tstep, ++lt) {
             const int n0 = (tile % n_tiles) * BN;
             const int g = (tile / n_tiles) % p.groups;
             const int m_tile = tile / (n_tiles * p.groups);
@@ -323,15 +342,35 @@ int launch_bn(const GemmParams& p, const CUtensorMap& tmA, const CUtensorMap& tm
     using L = SmemLayout<BN>;
     static bool configured = false;
     if (!configured) {
-        SUNB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        SUNB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        SUNB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         configured = true;
     }
     const int n_tiles = (p.N + BN - 1) / BN;
-    const int m_tiles = (p.M + BM - 1) / BM;
+    int m_tiles = (p.M + BM - 1) / BM;
+    if (p.a_mode) {       // spatial blocks x groups of 128/(bw*bh) images
+        const int nimg = BM / (p.bw * p.bh), B = p.M / (p.H * p.W);
+        m_tiles = (p.W / p.bw) * (p.H / p.bh) * ((B + nimg - 1) / nimg);
+    }
     const long total = (long)n_tiles * m_tiles * p.groups;
     SUNB_REQUIRE(total < (1L << 31), "gemm_tc: too many tiles");
-    const int grid = (int)(total < num_sms() ? total : num_sms());     // persistent: one CTA per SM
-    gemm_tc_kernel<BN><<<grid, NUM_THREADS, L::TOTAL, stream>>>(tmA, tmB, p, n_tiles, (int)total);
+    const int sms = num_sms();
+    // weight-stationary schedule when the (n-tile, group) weight operand fits beside >= 3 activation stages and every
+    // CTA gets enough m-tiles to amortise loading it
+    const int nk = p.taps * ((p.K + BK - 1) / BK);
+    const long b_bytes = (long)nk * L::B_BYTES;
+    const int slots = n_tiles * p.groups;
+    static int allow_bstat = -1;
+    if (allow_bstat < 0) { const char* e = getenv("SUNB_GEMM_BSTAT"); allow_bstat = (e && e[0] == '0') ? 0 : 1; }
+    if (allow_bstat && b_bytes <= L::TILE_BYTES - 3 * L::A_BYTES && slots <= sms && m_tiles >= 4 * (sms / slots)) {
+        int a_stages = (int)((L::TILE_BYTES - b_bytes) / L::A_BYTES);
+        if (a_stages > 10) a_stages = 10;
+        const int grid = (sms / slots) * slots;
+        gemm_tc_kernel<BN, true><<<grid, NUM_THREADS, L::TOTAL, stream>>>(tmA, tmB, p, n_tiles, (int)total, a_stages);
+    } else {
+        const int grid = (int)(total < sms ? total : sms);     // persistent: one CTA per SM
+        gemm_tc_kernel<BN, false><<<grid, NUM_THREADS, L::TOTAL, stream>>>(tmA, tmB, p, n_tiles, (int)total, L::STAGES);
+    }
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
 }
@@ -370,7 +409,7 @@ int sunb_launch_gemm_tc(const GemmParams& p, cudaStream_t stream) {
         const int C = p.groups > 1 ? p.a_goff * (p.groups - 1) + p.K : p.K;
         cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)B};
         cuuint64_t strides[3] = {(cuuint64_t)p.lda * 2, (cuuint64_t)p.lda * 2 * p.W, (cuuint64_t)p.lda * 2 * p.W * p.H};
-        cuuint32_t box[4] = {BK, (cuuint32_t)p.bw, (cuuint32_t)p.bh, 1};
+        cuuint32_t box[4] = {BK, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)(BM / (p.bw * p.bh))};
         SUNB_TRY(encode_map(&tmA, p.A, 4, dims, strides, box));
     }
     {

@@ -131,11 +131,12 @@ __global__ void __launch_bounds__(NUM_THREADS) wgrad_tc_kernel(const __grid_cons
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tile = blockIdx.x % n_tiles, m_tile = blockIdx.x / n_tiles;
     const int tap = blockIdx.y % p.taps, g = blockIdx.y / p.taps;
-    // K blocks of this split
+    // K blocks of this split.  conv mode: a K block = one (bw x bh) spatial block of 64/(bw*bh) consecutive images
     const int box = p.mode ? p.bw * p.bh : BKP;
-    const int nsub = BKP / box;
-    const int total_sub = p.mode ? (p.P / (p.H * p.W)) * ((p.W / p.bw) * (p.H / p.bh)) : 0;
-    const int kblocks = p.mode ? (total_sub + nsub - 1) / nsub : (p.P + BKP - 1) / BKP;
+    const int nimg = BKP / box;
+    const int tiles_x = p.mode ? p.W / p.bw : 1;
+    const int spi = p.mode ? tiles_x * (p.H / p.bh) : 1;
+    const int kblocks = p.mode ? spi * ((p.P / (p.H * p.W) + nimg - 1) / nimg) : (p.P + BKP - 1) / BKP;
     const int per = (kblocks + p.ksplit - 1) / p.ksplit;
     const int kb0 = blockIdx.z * per;
     const int kb1 = min(kb0 + per, kblocks);
@@ -162,8 +163,6 @@ __global__ void __launch_bounds__(NUM_THREADS) wgrad_tc_kernel(const __grid_cons
     if (nk > 0) {
         if (warp == 0) {
             if (lane == 0) {
-                const int tiles_x = p.mode ? p.W / p.bw : 1;
-                const int spi = p.mode ? tiles_x * (p.H / p.bh) : 1;
                 const int dy = p.mode ? tap / 3 - 1 : 0, dx = p.mode ? tap % 3 - 1 : 0;
                 const int ca = g * p.a_goff + m_tile * BM;
                 const int cb = g * p.b_goff + n_tile * BN;
@@ -181,18 +180,14 @@ __global__ void __launch_bounds__(NUM_THREADS) wgrad_tc_kernel(const __grid_cons
 #pragma unroll
                         for (int a = 0; a < BN / 64; ++a) tma_load_2d(b_dst + a * ATOM_BYTES, &tmX, full_bar(s), cb + a * 64, kb * BKP);
                     } else {
-                        for (int j = 0; j < nsub; ++j) {
-                            const int st = kb * nsub + j;
-                            const int img = st / spi, rem = st % spi;
-                            const int y0 = (rem / tiles_x) * p.bh, x0 = (rem % tiles_x) * p.bw;
+                        const int blk = kb % spi, img0 = (kb / spi) * nimg;
+                        const int y0 = (blk / tiles_x) * p.bh, x0 = (blk % tiles_x) * p.bw;
 #pragma unroll
-                            for (int a = 0; a < 2; ++a)
-                                tma_load_4d(a_dst + a * ATOM_BYTES + j * box * 128, &tmY, full_bar(s), ca + a * 64, x0, y0, img);
+                        for (int a = 0; a < 2; ++a)
+                            tma_load_4d(a_dst + a * ATOM_BYTES, &tmY, full_bar(s), ca + a * 64, x0, y0, img0);
 #pragma unroll
-                            for (int a = 0; a < BN / 64; ++a)
-                                tma_load_4d(b_dst + a * ATOM_BYTES + j * box * 128, &tmX, full_bar(s), cb + a * 64, x0 + dx,
-                                            y0 + dy, img);
-                        }
+                        for (int a = 0; a < BN / 64; ++a)
+                            tma_load_4d(b_dst + a * ATOM_BYTES, &tmX, full_bar(s), cb + a * 64, x0 + dx, y0 + dy, img0);
                     }
                 }
             }
@@ -278,7 +273,7 @@ int make_map(CUtensorMap* map, const bf16* base, int C, int ld, const WgradParam
         const int B = p.P / (p.H * p.W);
         cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)B};
         cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * p.W, (cuuint64_t)ld * 2 * p.W * p.H};
-        cuuint32_t box[4] = {64, (cuuint32_t)p.bw, (cuuint32_t)p.bh, 1};
+        cuuint32_t box[4] = {64, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)(BKP / (p.bw * p.bh))};
         r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(base), dims, strides, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -322,7 +317,7 @@ int sunb_launch_wgrad_tc(WgradParams p, cudaStream_t stream) {
     const int BN = p.Nb <= 64 ? 64 : (p.Nb <= 128 ? 128 : 256);
     const int n_tiles = (p.Nb + BN - 1) / BN, m_tiles = (p.Ma + BM - 1) / BM;
     const int box = conv ? p.bw * p.bh : BKP;
-    const int kblocks = conv ? ((p.P / (p.H * p.W)) * ((p.W / p.bw) * (p.H / p.bh)) + BKP / box - 1) / (BKP / box)
+    const int kblocks = conv ? (p.W / p.bw) * (p.H / p.bh) * ((p.P / (p.H * p.W) + BKP / box - 1) / (BKP / box))
                              : (p.P + BKP - 1) / BKP;
     if (p.ksplit <= 0) {       // ~2 waves of CTAs, at least 4 K blocks per CTA
         const int tiles = n_tiles * m_tiles * p.taps * p.groups;
