@@ -74,32 +74,49 @@ struct GemmParams {
     int dact;
 };
 
-// erf via Abramowitz & Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the bf16 output resolution): one ex2, one rcp
-// and seven FMAs instead of libdevice erff's ~30 instructions with a branch -- the GELU epilogues are issue-bound.
+// MUFU approximations (rel. error ~2^-22), one instruction each
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// erf via Abramowitz & Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the bf16 output resolution).
 __device__ __forceinline__ float erf_fast(float x) {
     const float ax = fabsf(x);
-    const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.f));
+    const float t = rcp_approx(fmaf(0.3275911f, ax, 1.f));
     float y = fmaf(1.061405429f, t, -1.453152027f);
     y = fmaf(y, t, 1.421413741f);
     y = fmaf(y, t, -0.284496736f);
     y = fmaf(y, t, 0.254829592f);
-    y = 1.f - y * t * __expf(-ax * ax);
+    y = 1.f - y * t * ex2_approx(-1.4426950408889634f * ax * ax);
     return copysignf(y, x);
 }
 
+// Exact-erf GELU  v * Phi(v)  with Phi(v) = 0.5 * (1 + erf(v / sqrt 2)), same A&S polynomial with the 1/sqrt2 and 0.5
+// factors folded into the constants: h = 0.5 * poly(t) * exp(-v^2 / 2), Phi = v >= 0 ? 1 - h : h.
+// 16 instructions per element (2 MUFU); the GELU epilogues are issue-bound, so the count matters.
+__device__ __forceinline__ float gelu_phi(float v) {
+    const float t = rcp_approx(fmaf(0.2316418882f, fabsf(v), 1.f));          // 0.3275911 / sqrt(2)
+    float y = fmaf(0.5307027145f, t, -0.7265760135f);                         // 0.5 * A&S coefficients
+    y = fmaf(y, t, 0.7107068705f);
+    y = fmaf(y, t, -0.142248368f);
+    y = fmaf(y, t, 0.127414796f);
+    const float h = y * t * ex2_approx(-0.7213475204444817f * v * v);          // exp(-v^2/2)
+    return v >= 0.f ? 1.f - h : h;
+}
+__device__ __forceinline__ float gelu_fast(float v) { return v * gelu_phi(v); }
+
 __device__ __forceinline__ float act_apply(float v, int act) {
     if (act == ACT_LRELU) return v > 0.f ? v : 0.1f * v;
-    if (act == ACT_GELU) return 0.5f * v * (1.f + erf_fast(v * 0.70710678118654752f));
+    if (act == ACT_GELU) return gelu_fast(v);
     return v;
 }
 
 // derivative of the activation evaluated at the saved tensor (GELU: pre-activation; LeakyReLU: either side of it)
+__device__ __forceinline__ float gelu_grad(float x) {       // Phi(x) + x * phi(x)
+    return gelu_phi(x) + x * 0.3989422804014327f * ex2_approx(-0.7213475204444817f * x * x);
+}
 __device__ __forceinline__ float act_grad(float x, int act) {
     if (act == ACT_LRELU) return x > 0.f ? 1.f : 0.1f;
-    if (act == ACT_GELU) {
-        const float cdf = 0.5f * (1.f + erf_fast(x * 0.70710678118654752f));
-        return cdf + x * 0.3989422804014327f * __expf(-0.5f * x * x);
-    }
+    if (act == ACT_GELU) return gelu_grad(x);
     return 1.f;
 }
 
@@ -191,7 +208,7 @@ __device__ __forceinline__ void epilogue_row(const GemmParams& p, int g, int m, 
     }
     if (p.act == ACT_GELU) {
 #pragma unroll
-        for (int i = 0; i < NC; ++i) v[i] = 0.5f * v[i] * (1.f + erf_fast(v[i] * 0.70710678118654752f));
+        for (int i = 0; i < NC; ++i) v[i] = gelu_fast(v[i]);
     } else if (p.act == ACT_LRELU) {
 #pragma unroll
         for (int i = 0; i < NC; ++i) v[i] = v[i] > 0.f ? v[i] : 0.1f * v[i];
@@ -213,10 +230,7 @@ __device__ __forceinline__ void epilogue_row(const GemmParams& p, int g, int m, 
         }
         if (p.dact == ACT_GELU) {
 #pragma unroll
-            for (int i = 0; i < NC; ++i) {
-                const float cdf = 0.5f * (1.f + erf_fast(a[i] * 0.70710678118654752f));
-                v[i] *= cdf + a[i] * 0.3989422804014327f * __expf(-0.5f * a[i] * a[i]);
-            }
+            for (int i = 0; i < NC; ++i) v[i] *= gelu_grad(a[i]);
         } else if (p.dact == ACT_LRELU) {
 #pragma unroll
             for (int i = 0; i < NC; ++i) v[i] *= a[i] > 0.f ? 1.f : 0.1f;

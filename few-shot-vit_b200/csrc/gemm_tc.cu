@@ -42,12 +42,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // Bounded wait: a broken pipeline traps (launch error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
+    // try_wait suspends in hardware; the watchdog (a broken pipeline traps instead of hanging the GPU) is only
+    // consulted every 4096 failed polls so the spin loop stays two instructions long
     const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
+    for (;;) {
+#pragma unroll 1
+        for (int i = 0; i < 4096; ++i)
+            if (mbar_try_wait(bar, parity)) return;
         if (clock64() - t0 > 4000000000LL) {   // ~2 s at 2 GHz
-            printf("sunb gemm_tc: mbarrier timeout block (%d,%d,%d) thread %d\n", blockIdx.x, blockIdx.y,
-                   blockIdx.z, threadIdx.x);
+            printf("sunb gemm_tc: mbarrier timeout block (%d,%d,%d) thread %d\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
             __trap();
         }
     }
@@ -361,7 +364,7 @@ int launch_bn(const GemmParams& p, const CUtensorMap& tmA, const CUtensorMap& tm
     const long b_bytes = (long)nk * L::B_BYTES;
     const int slots = n_tiles * p.groups;
     static int allow_bstat = -1;
-    if (allow_bstat < 0) { const char* e = getenv("SUNB_GEMM_BSTAT"); allow_bstat = (e && e[0] == '0') ? 0 : 1; }
+    if (allow_bstat < 0) { const char* e = getenv("SUNB_GEMM_BSTAT"); allow_bstat = (e && e[0] == '1') ? 1 : 0;   // opt-in: measured neutral on B200 once conv tiles became single TMA boxes }
     if (allow_bstat && b_bytes <= L::TILE_BYTES - 3 * L::A_BYTES && slots <= sms && m_tiles >= 4 * (sms / slots)) {
         int a_stages = (int)((L::TILE_BYTES - b_bytes) / L::A_BYTES);
         if (a_stages > 10) a_stages = 10;

@@ -35,12 +35,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
+    // try_wait suspends in hardware; the watchdog (a broken pipeline traps instead of hanging the GPU) is only
+    // consulted every 4096 failed polls so the spin loop stays two instructions long
     const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) {
-            printf("sunb wgrad_tc: mbarrier timeout block (%d,%d,%d) thread %d\n", blockIdx.x, blockIdx.y, blockIdx.z,
-                   threadIdx.x);
+    for (;;) {
+#pragma unroll 1
+        for (int i = 0; i < 4096; ++i)
+            if (mbar_try_wait(bar, parity)) return;
+        if (clock64() - t0 > 4000000000LL) {   // ~2 s at 2 GHz
+            printf("sunb wgrad_tc: mbarrier timeout block (%d,%d,%d) thread %d\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
             __trap();
         }
     }
