@@ -364,7 +364,8 @@ int launch_bn(const GemmParams& p, const CUtensorMap& tmA, const CUtensorMap& tm
     const long b_bytes = (long)nk * L::B_BYTES;
     const int slots = n_tiles * p.groups;
     static int allow_bstat = -1;
-    if (allow_bstat < 0) { const char* e = getenv("SUNB_GEMM_BSTAT"); allow_bstat = (e && e[0] == '1') ? 1 : 0;   // opt-in: measured neutral on B200 once conv tiles became single TMA boxes }
+    // weight-stationary schedule is opt-in (SUNB_GEMM_BSTAT=1): measured neutral on B200 once conv tiles became single TMA boxes
+    if (allow_bstat < 0) { const char* e = getenv("SUNB_GEMM_BSTAT"); allow_bstat = (e && e[0] == '1') ? 1 : 0; }
     if (allow_bstat && b_bytes <= L::TILE_BYTES - 3 * L::A_BYTES && slots <= sms && m_tiles >= 4 * (sms / slots)) {
         int a_stages = (int)((L::TILE_BYTES - b_bytes) / L::A_BYTES);
         if (a_stages > 10) a_stages = 10;

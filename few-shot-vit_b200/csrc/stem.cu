@@ -6,6 +6,9 @@
 //   pool_pos : 2x2 max-pool of the [B,40,40,128] map + pos_embed1 -> [B,20,20,128]
 #include "common.cuh"
 
+#include <stdlib.h>
+#include <string.h>
+
 namespace {
 
 constexpr int IMG = 80, OUT = 40, C1 = 64, CD = 128;
@@ -90,9 +93,15 @@ __global__ void pool_pos_kernel(const bf16* __restrict__ in, const float* __rest
 
 }  // namespace
 
+int sunb_launch_stem_in_tc(const float* x, const float* w1, const float* b1, const float* wd, const float* bd, bf16* a1,
+                           bf16* idn, int B, int lrelu, cudaStream_t stream);
+
 int sunb_launch_stem_in(const float* x, const float* w1, const float* b1, const float* wd, const float* bd, bf16* a1,
                         bf16* idn, int B, int lrelu, cudaStream_t stream) {
     SUNB_REQUIRE(B > 0, "stem_in: B must be positive");
+    static int use_simt = -1;       // SUNB_STEM=simt selects the CUDA-core cross-check kernel (tests / debugging)
+    if (use_simt < 0) { const char* e = getenv("SUNB_STEM"); use_simt = (e && strcmp(e, "simt") == 0) ? 1 : 0; }
+    if (!use_simt) return sunb_launch_stem_in_tc(x, w1, b1, wd, bd, a1, idn, B, lrelu, stream);
     stem_in_kernel<<<B * OUT, 128, 0, stream>>>(x, w1, b1, wd, bd, a1, idn, B, lrelu);
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;

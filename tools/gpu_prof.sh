@@ -1,5 +1,5 @@
 #!/bin/bash
-# GPU tests + bench + per-launch device times (generic vs weight-stationary schedule)
+# GPU tests + bench + per-launch device times
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -5 gpurun_out/pytest_gpu.log
 timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"; tail -5 gpurun_out/bench.err
@@ -10,5 +10,4 @@ try:
 except Exception as e: print('parse fail', e)
 PY
 SUNB_BENCH_PROFILE=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 > gpurun_out/prof_run.log 2>&1; echo "ncu list exit $?"
-SUNB_GEMM_BSTAT=1 SUNB_BENCH_PROFILE=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_bstat.csv python bench.py --steps 1 --warmup 1 > gpurun_out/prof_run2.log 2>&1; echo "ncu list bstat exit $?"
 SUNB_BENCH_PROFILE=train timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_train.csv python bench.py --steps 1 --warmup 1 > gpurun_out/prof_train_run.log 2>&1; echo "ncu train list exit $?"
