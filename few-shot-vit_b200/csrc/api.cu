@@ -33,6 +33,9 @@ int sunb_launch_wgrad_tc(WgradParams p, cudaStream_t stream);
 int sunb_launch_layernorm_rows(const float* x, const float* gamma, const float* beta, float* y, long M, int C, float eps,
                                cudaStream_t stream);
 
+extern "C" int sunb_gconv3x3(const void* x, int ldx, const void* wg, void* y, int ldy, void* y2, int ldy2, const void* aux,
+                             int ldaux, int B, int act, int dact, void* stream);
+
 static thread_local char g_err[512] = "";
 
 void sunb_set_error(const char* fmt, ...) {
@@ -198,11 +201,7 @@ int sunb_encoder_forward(const SunbEncoderWeights* w, const float* x, int B, voi
         GemmParams p = base_gemm(B * 400, 256, 128, ws.s1, 128, bw.w1, 128, ws.h1, 256);
         p.bias = bw.b1; p.act = ACT_GELU;
         SUNB_TRY(sunb_launch_gemm(p, st));
-        p = base_gemm(B * 400, 64, 64, ws.h1, 256, bw.w2, 64, ws.h2, 256);
-        p.taps = 9; p.groups = 4; p.a_goff = 64; p.c_goff = 64;
-        p.a_mode = 1; p.H = 20; p.W = 20; p.bw = 4; p.bh = 4;
-        p.act = ACT_GELU;
-        SUNB_TRY(sunb_launch_gemm(p, st));
+        SUNB_TRY(sunb_gconv3x3(ws.h1, 256, bw.w2, ws.h2, 256, nullptr, 0, nullptr, 0, B, ACT_GELU, ACT_NONE, stream));
         p = base_gemm(B * 400, 128, 256, ws.h2, 256, bw.w3, 256, last ? ws.s1d : ws.s1, 128);
         p.resid = ws.s1; p.ldr = 128;
         if (last) { p.out_map = MAP_S2D; p.oH = 20; p.oW = 20; }

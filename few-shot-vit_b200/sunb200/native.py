@@ -111,6 +111,8 @@ SIGNATURES = {
     "sunb_permute_cast": (C.c_int, [fp, C.c_long, C.c_long, C.c_long, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
     "sunb_grouped_pairs": (C.c_int, [fp, vp, C.c_int, vp]),
     "sunb_grouped_wgrad_extract": (C.c_int, [fp, fp, vp]),
+    "sunb_gconv3x3": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "sunb_gconv_pack": (C.c_int, [fp, vp, C.c_int, vp]),
     "sunb_layernorm_rows": (C.c_int, [fp, fp, fp, fp, C.c_long, C.c_int, C.c_float, vp]),
     "sunb_attention_backward": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "sunb_episode_logits_backward": (C.c_int, [fp, fp, fp, fp, fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

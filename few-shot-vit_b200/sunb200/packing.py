@@ -45,6 +45,13 @@ def _grouped_pairs(w: torch.Tensor, groups: int = 8) -> torch.Tensor:
     return out.contiguous()
 
 
+def _grouped_taps(w: torch.Tensor, groups: int = 8) -> torch.Tensor:
+    """Grouped 3x3 weight [256, 32, 3, 3] -> [8 groups][9 taps][32 n][32 k] (operand of sunb_gconv3x3)."""
+    n_out, cpg = w.shape[0], w.shape[1]
+    opg = n_out // groups
+    return w.reshape(groups, opg, cpg, 9).permute(0, 3, 1, 2).contiguous()
+
+
 def _pad_cols(w: torch.Tensor, mult: int = 8) -> torch.Tensor:
     k = w.shape[1]
     kp = (k + mult - 1) // mult * mult
@@ -81,7 +88,7 @@ def pack_encoder(sd: Dict[str, torch.Tensor], prefix: str = "", wdtype: torch.dt
         w1 = w2d(b + "mlp.conv1.weight")
         P[f"s1.{i}.w1"] = (w1 * s[None, :]).to(wdtype).contiguous()
         P[f"s1.{i}.b1"] = (w1 @ t).contiguous()
-        P[f"s1.{i}.w2"] = _grouped_pairs(g[b + "mlp.conv2.weight"].float()).to(wdtype)
+        P[f"s1.{i}.w2"] = _grouped_taps(g[b + "mlp.conv2.weight"].float()).to(wdtype)
         P[f"s1.{i}.w3"] = w2d(b + "mlp.conv3.weight").to(wdtype).contiguous()
 
     for stage, depth, hw in (("2", DEPTH[1], 100), ("3", DEPTH[2], 25)):
@@ -169,8 +176,8 @@ def emulate_forward(P: Dict[str, torch.Tensor], x: torch.Tensor, taps: Dict[str,
     for i in range(4):
         h1 = _gelu(s1 @ f[f"s1.{i}.w1"].t() + f[f"s1.{i}.b1"])
         h2 = torch.empty_like(h1)
-        for p in range(4):
-            h2[..., p * 64:(p + 1) * 64] = _gelu(_conv3x3_nhwc(h1[..., p * 64:(p + 1) * 64], f[f"s1.{i}.w2"][p]))
+        for gi in range(8):
+            h2[..., gi * 32:(gi + 1) * 32] = _gelu(_conv3x3_nhwc(h1[..., gi * 32:(gi + 1) * 32], f[f"s1.{i}.w2"][gi]))
         s1 = s1 + h2 @ f[f"s1.{i}.w3"].t()
         tap(f"stage1.{i}", s1)
     t = _s2d(s1) @ f["pe2_w"].t()

@@ -158,9 +158,9 @@ class TrainEngine:
             W[b + "conv3.f"] = self.pcast(P[b + "conv3.weight"], (1, 128, 256), (0, 256, 1))
             W[b + "conv3.d"] = self.pcast(P[b + "conv3.weight"], (1, 256, 128), (0, 1, 256))
             for key, flip in ((".f", 0), (".d", 1)):
-                dst = self.empty(4 * 9 * 64, 64)
-                N.check(self.lib.sunb_grouped_pairs(P[b + "conv2.weight"].data_ptr(), dst.data_ptr(), flip, _st()),
-                        "sunb_grouped_pairs")
+                dst = self.empty(8 * 9 * 32, 32)
+                N.check(self.lib.sunb_gconv_pack(P[b + "conv2.weight"].data_ptr(), dst.data_ptr(), flip, _st()),
+                        "sunb_gconv_pack")
                 W[b + "conv2" + key] = dst
         for stage, cin, dim, depth in (("2", 128, 256, DEPTH[1]), ("3", 256, 512, DEPTH[2])):
             w = P[f"patch_embed{stage}.proj.weight"]
@@ -226,8 +226,8 @@ class TrainEngine:
             h1, h1p = self.empty(M1, 256), self.empty(M1, 256)
             gemm(xn, W[name + ".mlp.conv1.f"], M1, 256, 128, out=h1, act=ACT_GELU, out2=h1p)
             h2, h2p = self.empty(M1, 256), self.empty(M1, 256)
-            gemm(h1, W[name + ".mlp.conv2.f"], M1, 64, 64, out=h2, taps=9, groups=4, a_goff=64, c_goff=64,
-                 conv=(20, 20, 4, 4), act=ACT_GELU, out2=h2p)
+            N.check(lib.sunb_gconv3x3(h1.data_ptr(), 256, W[name + ".mlp.conv2.f"].data_ptr(), h2.data_ptr(), 256,
+                                      h2p.data_ptr(), 256, None, 0, B, ACT_GELU, ACT_NONE, _st()), "sunb_gconv3x3")
             nxt = gemm(h2, W[name + ".mlp.conv3.f"], M1, 128, 256, out=self.empty(M1, 128), resid=cur, row_scale=r,
                        rows_per_img=400)
             ctx["blocks"].append(dict(kind="conv", name=name, x=cur, bn=bn, xn=xn, h1=h1, h1p=h1p, h2=h2, h2p=h2p, rs=r))
@@ -348,8 +348,9 @@ class TrainEngine:
         dh2p = gemm(g, W[name + ".mlp.conv3.d"], M, 256, 128, out=self.empty(M, 256), row_scale=r, rows_per_img=400,
                     dact_aux=b["h2p"], dact=ACT_GELU)
         wgrad(gs, b["h2"], G[name + ".mlp.conv3.weight"], M, 128, 256)
-        dh1p = gemm(dh2p, W[name + ".mlp.conv2.d"], M, 64, 64, out=self.empty(M, 256), taps=9, groups=4, a_goff=64,
-                    c_goff=64, conv=(20, 20, 4, 4), dact_aux=b["h1p"], dact=ACT_GELU)
+        dh1p = self.empty(M, 256)
+        N.check(lib.sunb_gconv3x3(dh2p.data_ptr(), 256, W[name + ".mlp.conv2.d"].data_ptr(), dh1p.data_ptr(), 256, None, 0,
+                                  b["h1p"].data_ptr(), 256, B, ACT_NONE, ACT_GELU, _st()), "sunb_gconv3x3(dgrad)")
         scratch = torch.zeros(2 * 9 * 128, 128, dtype=torch.float32, device=self.dev)
         wgrad(dh2p, b["h1"], scratch, M, 128, 128, Ca=256, Cb=256, taps=9, groups=2, a_goff=128, b_goff=128,
               conv=(20, 20, 4, 4))

@@ -77,7 +77,7 @@ int sunb_gemm(const SunbGemmDesc* desc, int impl, void* stream);
  * ------------------------------------------------------------------------------------------------- */
 typedef struct SunbConvMlpW {        /* stage-1 Block: norm2 folded into conv1 */
     const void* w1; const float* b1; /* bf16 [256][128], fp32 [256] */
-    const void* w2;                  /* bf16 grouped 3x3 as 4 channel pairs: [4][9][64][64] block-diagonal */
+    const void* w2;                  /* bf16 grouped 3x3 weights [8 groups][9 taps][32 n][32 k] */
     const void* w3;                  /* bf16 [128][256] */
 } SunbConvMlpW;
 
@@ -216,6 +216,13 @@ int sunb_grouped_wgrad_extract(const float* scratch, float* dw, void* stream);
  * 'visformer_micro_80', provided for API completeness) */
 int sunb_layernorm_rows(const float* x, const float* gamma, const float* beta, float* y, long M, int C, float eps,
                         void* stream);
+
+/* Grouped 3x3 convolution (8 groups x 32 channels, pad 1) on 20x20 maps: Mlp.conv2 (visformer.py:146-148,157-159), forward
+ * (act = 2: GELU, y2 = pre-activation copy) and data gradient (transposed/mirrored weights from sunb_gconv_pack(.., 1),
+ * aux/dact = chain-rule factor act'(aux)).  x, y, y2, aux: bf16 [B*400, ld]; wg: bf16 [8][9][32][32]. */
+int sunb_gconv3x3(const void* x, int ldx, const void* wg, void* y, int ldy, void* y2, int ldy2, const void* aux, int ldaux,
+                  int B, int act, int dact, void* stream);
+int sunb_gconv_pack(const float* w, void* dst, int transpose_flip, void* stream);
 
 /* backward of the attention core and of the episode head */
 int sunb_attention_backward(const void* qkv, const void* dout, void* dqkv, int B, int S, int d, int heads, int ld_qkv,

@@ -187,3 +187,38 @@ def test_layernorm_wrapper():
     x = rnd(3, 96, 7, 5, seed=32) * 3 + 1
     ref = F.layer_norm(x.permute(0, 2, 3, 1), (96,), ln.ln.weight, ln.ln.bias, ln.ln.eps).permute(0, 3, 1, 2)
     assert max_err(ln(x), ref) < 1e-5
+
+
+def test_gconv3x3_forward_and_dgrad():
+    """Warp-MMA grouped conv (sunb_gconv3x3) vs torch conv2d(groups=8) forward, GELU, pre-activation copy and dgrad."""
+    from sunb200 import packing
+    B = 3
+    x = rnd(B * 400, 256, seed=40).bfloat16()
+    w = rnd(256, 32, 3, 3, seed=41, scale=(9 * 32) ** -0.5)
+    wg = packing._grouped_taps(w).bfloat16().contiguous()
+    y = torch.empty(B * 400, 256, device=DEV, dtype=torch.bfloat16)
+    y2 = torch.empty_like(y)
+    lib, st = N.lib(), N.current_stream()
+    N.check(lib.sunb_gconv3x3(x.data_ptr(), 256, wg.data_ptr(), y.data_ptr(), 256, y2.data_ptr(), 256, None, 0, B, 2, 0, st), "gconv")
+    torch.cuda.synchronize()
+    xf = x.float().view(B, 20, 20, 256).permute(0, 3, 1, 2).requires_grad_(True)
+    pre = F.conv2d(xf, w.bfloat16().float(), padding=1, groups=8)
+    ref_pre = pre.permute(0, 2, 3, 1).reshape(-1, 256)
+    assert rel_err(y2, ref_pre) < BF16_OUT
+    assert rel_err(y, act_ref(ref_pre, 2)) < BF16_OUT
+    # dgrad: conv-transpose weights packed on the device, chain-rule factor gelu'(aux)
+    dy = rnd(B * 400, 256, seed=42).bfloat16()
+    aux = rnd(B * 400, 256, seed=43).bfloat16()
+    wd = torch.empty(8 * 9 * 32, 32, device=DEV, dtype=torch.bfloat16)
+    N.check(lib.sunb_gconv_pack(w.data_ptr(), wd.data_ptr(), 1, st), "pack")
+    wf = torch.empty(8 * 9 * 32, 32, device=DEV, dtype=torch.bfloat16)
+    N.check(lib.sunb_gconv_pack(w.data_ptr(), wf.data_ptr(), 0, st), "pack")
+    assert torch.equal(wf.view(8, 9, 32, 32), wg)
+    dx = torch.empty_like(y)
+    N.check(lib.sunb_gconv3x3(dy.data_ptr(), 256, wd.data_ptr(), dx.data_ptr(), 256, None, 0, aux.data_ptr(), 256, B, 0, 2, st), "gconv dgrad")
+    torch.cuda.synchronize()
+    pre.backward(dy.float().view(B, 20, 20, 256).permute(0, 3, 1, 2))
+    a = aux.float()
+    gprime = 0.5 * (1 + torch.erf(a * 0.70710678118654752)) + a * torch.exp(-0.5 * a * a) * 0.3989422804014327
+    ref_dx = xf.grad.permute(0, 2, 3, 1).reshape(-1, 256) * gprime
+    assert rel_err(dx, ref_dx) < 1e-2

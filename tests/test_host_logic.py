@@ -31,8 +31,9 @@ def test_packed_layouts():
     sd = O.init_encoder_state_dict(3)
     P = packing.pack_encoder(sd)
     assert P["stem_w2"].shape == (9, 128, 64) and P["stem_w2"].dtype == torch.bfloat16
-    assert P["s1.0.w2"].shape == (4, 9, 64, 64)
-    blk = P["s1.0.w2"].float()
+    assert P["s1.0.w2"].shape == (8, 9, 32, 32)
+    blk = packing._grouped_pairs(sd["stage1.0.mlp.conv2.weight"])
+    assert blk.shape == (4, 9, 64, 64)
     assert (blk[:, :, :32, 32:] == 0).all() and (blk[:, :, 32:, :32] == 0).all()      # block-diagonal pairs
     assert P["s2.0.wqkv"].shape == (756, 256) and P["s3.0.wqkv"].shape == (1530, 512)
     assert P["s2.0.wproj"].shape == (256, 256) and (P["s2.0.wproj"][:, 252:] == 0).all()
