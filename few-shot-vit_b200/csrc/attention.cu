@@ -27,11 +27,10 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 
 template <int S_PAD, int D_PAD, int PAIRS>
 struct AttnCfg {
-    static constexpr int QK_LD = D_PAD + 8;        // bf16 elements per Q/K row (conflict-free fragment loads)
-    static constexpr int VT_LD = S_PAD + 8;        // bf16 elements per V^T row
+    static constexpr int QK_LD = D_PAD + 8;        // bf16 elements per Q/K/V row (conflict-free fragment loads)
     static constexpr int WARPS_PER_PAIR = S_PAD / 16;
     static constexpr int THREADS = 32 * WARPS_PER_PAIR * PAIRS;
-    static constexpr int PAIR_ELEMS = 2 * S_PAD * QK_LD + D_PAD * VT_LD;
+    static constexpr int PAIR_ELEMS = 3 * S_PAD * QK_LD;
     static constexpr size_t SMEM = (size_t)PAIRS * PAIR_ELEMS * sizeof(bf16);
 };
 
@@ -40,30 +39,52 @@ __global__ void __launch_bounds__(AttnCfg<S_PAD, D_PAD, PAIRS>::THREADS)
 attention_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int n_pairs, int S, int d, int heads,
                      int ld_qkv, int ld_out, float scale_log2e) {
     using Cfg = AttnCfg<S_PAD, D_PAD, PAIRS>;
-    constexpr int QK_LD = Cfg::QK_LD, VT_LD = Cfg::VT_LD;
+    constexpr int QK_LD = Cfg::QK_LD;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     bf16* smem = reinterpret_cast<bf16*>(smem_raw);
     const int inner = heads * d;
 
-    // ---- stage Q, K (row-major) and V^T for the PAIRS problems of this CTA, zero padded
+    // ---- stage Q, K, V (all row-major [token][d]) for the PAIRS problems of this CTA.  Padding must read as zero:
+    //      clear the tiles, then fill the valid part -- with 4-byte cp.async when every row segment is 4-byte aligned
+    //      (d even: stage 2), else with scalar loads (d = 85: odd heads start on a 2-byte boundary).
+    {
+        uint4* z = reinterpret_cast<uint4*>(smem_raw);
+        for (int i = threadIdx.x; i < (int)(Cfg::SMEM / 16); i += Cfg::THREADS) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    const bool vec2 = ((d & 1) == 0) && ((ld_qkv & 1) == 0);
     for (int pl = 0; pl < PAIRS; ++pl) {
         const int pair = blockIdx.x * PAIRS + pl;
+        if (pair >= n_pairs) break;
         bf16* sq = smem + pl * Cfg::PAIR_ELEMS;
         bf16* sk = sq + S_PAD * QK_LD;
         bf16* sv = sk + S_PAD * QK_LD;
-        const bool live = pair < n_pairs;
-        const int img = live ? pair / heads : 0, head = live ? pair % heads : 0;
+        const int img = pair / heads, head = pair % heads;
         const bf16* base = qkv + (size_t)img * S * ld_qkv + head * d;
-        for (int i = threadIdx.x; i < S_PAD * D_PAD; i += Cfg::THREADS) {
-            const int t = i / D_PAD, z = i % D_PAD;
-            const bool in = live && t < S && z < d;
-            const bf16* row = base + (size_t)t * ld_qkv + z;
-            const bf16 zero = __float2bfloat16(0.f);
-            sq[t * QK_LD + z] = in ? row[0] : zero;
-            sk[t * QK_LD + z] = in ? row[inner] : zero;
-            sv[z * VT_LD + t] = in ? row[2 * inner] : zero;
+        if (vec2) {
+            const int dh = d >> 1;
+            for (int i = threadIdx.x; i < S * dh; i += Cfg::THREADS) {
+                const int t = i / dh, z = (i % dh) * 2;
+                const bf16* row = base + (size_t)t * ld_qkv + z;
+                const uint32_t dq = (uint32_t)__cvta_generic_to_shared(sq + t * QK_LD + z);
+                const uint32_t dk = (uint32_t)__cvta_generic_to_shared(sk + t * QK_LD + z);
+                const uint32_t dv = (uint32_t)__cvta_generic_to_shared(sv + t * QK_LD + z);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dq), "l"(row) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dk), "l"(row + inner) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dv), "l"(row + 2 * inner) : "memory");
+            }
+        } else {
+            for (int i = threadIdx.x; i < S * d; i += Cfg::THREADS) {
+                const int t = i / d, z = i % d;
+                const bf16* row = base + (size_t)t * ld_qkv + z;
+                sq[t * QK_LD + z] = row[0];
+                sk[t * QK_LD + z] = row[inner];
+                sv[t * QK_LD + z] = row[2 * inner];
+            }
         }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -135,11 +156,17 @@ attention_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int n
         const uint32_t a1 = pack_bf16(sc[2 * kk][2], sc[2 * kk][3]);
         const uint32_t a2 = pack_bf16(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
         const uint32_t a3 = pack_bf16(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
+        // B fragments of V (row-major [key][d]) through ldmatrix.trans: lanes 0-7 / 8-15 address keys kk*16 + 0..7 / 8..15,
+        // lanes 16-31 the same keys of the next 8 head-dim columns -> (b0, b1) of two n-tiles per instruction
+        const bf16* vrow = sv + (kk * 16 + (lane & 15)) * QK_LD + ((lane >> 4) << 3);
 #pragma unroll
-        for (int j = 0; j < OT; ++j) {
-            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(sv + (j * 8 + g) * VT_LD + kk * 16 + t * 2);
-            const uint32_t b1 = *reinterpret_cast<const uint32_t*>(sv + (j * 8 + g) * VT_LD + kk * 16 + 8 + t * 2);
+        for (int j = 0; j < OT; j += 2) {
+            uint32_t b0, b1, b2, b3;
+            asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                         : "r"((uint32_t)__cvta_generic_to_shared(vrow + j * 8)));
             mma_bf16_16816(oc[j], a0, a1, a2, a3, b0, b1);
+            mma_bf16_16816(oc[j + 1], a0, a1, a2, a3, b2, b3);
         }
     }
     const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;

@@ -94,18 +94,36 @@ __global__ void __launch_bounds__(THREADS, 2) stem_in_tc_kernel(const float* __r
     uint32_t phase = 0;
 
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        // ---- gather the im2col tile: element (r, k) = x[img][ci][2*oy-1+ky][2*ox-1+kx], k = (ci*3+ky)*3+kx
-        for (int i = tid; i < 128 * 32; i += THREADS) {
-            const int k = i >> 7, r = i & 127;
+        // ---- gather the im2col tile: element (r, k) = x[img][ci][2*oy-1+ky][2*ox-1+kx], k = (ci*3+ky)*3+kx.
+        //      thread = (pixel row r, 16-wide k half): the pixel decode happens once, the 16 values leave as two 16-byte
+        //      swizzled chunks; lanes walk consecutive pixels so the stride-2 image reads stay within a few sectors.
+        {
+            const int r = tid & 127, kh = tid >> 7;
             const int m = tile * 128 + r;
-            float v = 0.f;
-            if (k < KREAL && m < total) {
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = 0.f;
+            if (m < total) {
                 const int img = m / NPIX, rem = m - img * NPIX, oy = rem / OUTP, ox = rem - oy * OUTP;
-                const int ci = k / 9, ky = (k - ci * 9) / 3, kx = k - ci * 9 - ky * 3;
-                const int iy = 2 * oy - 1 + ky, ix = 2 * ox - 1 + kx;
-                if (iy >= 0 && iy < IMG && ix >= 0 && ix < IMG) v = __ldg(x + ((size_t)(img * 3 + ci) * IMG + iy) * IMG + ix);
+                const float* xi = x + (size_t)img * 3 * IMG * IMG;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int k = kh * 16 + j;
+                    if (k < KREAL) {
+                        const int ci = k / 9, ky = (k % 9) / 3, kx = k % 3;
+                        const int iy = 2 * oy - 1 + ky, ix = 2 * ox - 1 + kx;
+                        if (iy >= 0 && iy < IMG && ix >= 0 && ix < IMG) v[j] = __ldg(xi + (ci * IMG + iy) * IMG + ix);
+                    }
+                }
             }
-            *reinterpret_cast<bf16*>(sA + sw128_off(r, k)) = __float2bfloat16(v);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint4 u;
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[c * 8 + 2 * j], v[c * 8 + 2 * j + 1]);
+                *reinterpret_cast<uint4*>(sA + sw128_off(r, kh * 16 + c * 8)) = u;
+            }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the tensor core
         __syncthreads();
