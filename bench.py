@@ -288,14 +288,25 @@ def run_product(args):
 
     stage = [torch.empty_like(dev_chunks[0]) for _ in range(2)]
     host_out = torch.empty(n_chunks, CHUNK, WAY * QUERY, WAY, dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream(device=device)
+    ready = [torch.cuda.Event() for _ in range(2)]
+    free = [torch.cuda.Event() for _ in range(2)]
 
     def step_e2e():
+        """Public API with HOST inputs: pinned H2D of every chunk (double-buffered on a copy stream so the transfer of
+        chunk c+1 overlaps the encoder on chunk c), model call, D2H of the logits -- all inside the timed region."""
+        main = torch.cuda.current_stream()
         for c in range(n_chunks):
             buf = stage[c % 2]
-            buf.copy_(host_chunks[c], non_blocking=True)                 # H2D inside the timed region
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(free[c % 2])
+                buf.copy_(host_chunks[c], non_blocking=True)             # H2D inside the timed region
+                ready[c % 2].record(copy_stream)
+            main.wait_event(ready[c % 2])
             xs, xq = fs.split_shot_query(buf, WAY, SHOT, QUERY, ep_per_batch=CHUNK)
             host_out[c].copy_(model(xs, xq), non_blocking=True)          # D2H of the step's result (logits)
-        torch.cuda.current_stream().synchronize()
+            free[c % 2].record(main)
+        main.synchronize()
 
     def barrier():
         if world > 1:
