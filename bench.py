@@ -222,13 +222,37 @@ def measure_train_step(args, device, world, rank, sd):
 
     for _ in range(3):
         loss = step()
+    # Whole-step CUDA graph (forward, backward, NCCL all-reduce, SGD): the step is ~500 short launches, which becomes
+    # launch-bound once the batch is sharded over 4-8 GPUs.  Falls back to eager launches if capture is refused.
+    run, mode = step, "eager"
+    if os.environ.get("SUNB_TRAIN_GRAPH", "1") == "1":
+        try:
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_loss = step()
+            graph.replay()
+            torch.cuda.synchronize()
+
+            def run():
+                graph.replay()
+                return static_loss
+            mode = "cuda_graph"
+        except Exception as exc:          # keep measuring: eager mode is still the real public-API path
+            torch.cuda.synchronize()
+            if rank == 0:
+                print(f"[bench] CUDA-graph capture of the train step failed ({type(exc).__name__}: {exc}); using eager launches",
+                      file=sys.stderr)
+            run, mode = step, "eager"
+    for _ in range(2):
+        loss = run()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e0.record()
     for _ in range(args.steps):
-        loss = step()
+        loss = run()
     e1.record()
     if world > 1:
         dist.barrier()
@@ -240,6 +264,7 @@ def measure_train_step(args, device, world, rank, sd):
     return {"metric": "SUN-M meta-tuning step (fwd+bwd+allreduce+SGD)", "ms_per_step": ms.item(), "unit": "ms",
             "images_per_step": TRAIN_IMAGES, "episodes_per_gpu": ep, "scaling": "strong", "higher_is_better": False,
             "achieved_tflops_per_gpu": flops / world / (ms.item() * 1e-3) / 1e12, "loss_last": float(loss.item()),
+            "launch_mode": mode,
             "config": "8 episodes x 10-way x (1 shot + 5 query), drop_path_rate 0.5, SGD(1e-3, 0.9, wd 5e-4), "
                       "BN batch statistics per replica"}
 

@@ -2,9 +2,8 @@
 // (reference: Mlp.conv2, test_phase/models/visformer.py:146-148,157-159), forward and data-gradient.
 //
 // Warp-level tensor-core kernel staged through shared memory (north_star: "grouped 3x3 conv ... warp-level kernels"):
-// persistent CTAs own one group and loop over images.  The group's 9 x 32 x 32 weights are loaded once per CTA; each
-// image's 32-channel slice is loaded ONCE into shared memory with a zero halo (22 x 22 pixels, cp.async 16-byte chunks,
-// double-buffered so the next image streams in while the current one is multiplied), and every filter tap
+// a CTA owns one (image, group).  The group's 32-channel slice of the image is loaded ONCE into shared memory with a
+// zero halo (22 x 22 pixels, cp.async 16-byte chunks), the group's 9 x 32 x 32 weights sit beside it, and every filter tap
 // is just a different ldmatrix row address into that halo tile -- the activation is read from L2 once instead of nine
 // times (the tcgen05 implicit-GEMM formulation re-fetched a shifted box per tap and wasted half of each 64-wide
 // block-diagonal MMA).  5 warps x 5 m16 tiles cover the 400 pixels; a warp keeps the B fragments of a k-step in registers
@@ -19,7 +18,7 @@ constexpr int W_LD = GC + 8;
 constexpr int A_ELEMS = HP * HP * A_LD;                    // 19360
 constexpr int W_ELEMS = 9 * GC * W_LD;                     // 11520
 constexpr int WARPS = 5, TILES_PER_WARP = 5, THREADS = WARPS * 32;
-constexpr size_t SMEM = (size_t)(2 * A_ELEMS + W_ELEMS) * sizeof(bf16);   // 100,480 B -> 2 CTAs per SM
+constexpr size_t SMEM = (size_t)(A_ELEMS + W_ELEMS) * sizeof(bf16);   // 61,760 B -> 3 CTAs per SM
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
@@ -37,40 +36,39 @@ __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1
 }
 
 // x, y, y2, aux: bf16 [B*400, ld] NHWC rows; wg: bf16 [8 groups][9 taps][32 n][32 k]
-__global__ void __launch_bounds__(THREADS, 2) gconv3x3_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ wg,
+__global__ void __launch_bounds__(THREADS, 3) gconv3x3_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ wg,
                                                               bf16* __restrict__ y, int ldy, bf16* __restrict__ y2, int ldy2,
-                                                              const bf16* __restrict__ aux, int ldaux, int B, int act,
-                                                              int dact) {
+                                                              const bf16* __restrict__ aux, int ldaux, int act, int dact) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    bf16* sW = reinterpret_cast<bf16*>(smem_raw);
-    bf16* sAbuf = sW + W_ELEMS;                    // two halo tiles
-    const int grp = blockIdx.y;
+    bf16* sA = reinterpret_cast<bf16*>(smem_raw);
+    bf16* sW = sA + A_ELEMS;
+    const int img = blockIdx.x, grp = blockIdx.y;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    // weights of this group (once) and the zero halo ring of both tiles (the interior is always overwritten)
+    // zero the halo ring (interior is overwritten by cp.async; disjoint addresses)
+    for (int i = tid; i < HP * HP; i += THREADS) {
+        const int hy = i / HP, hx = i % HP;
+        if (hy == 0 || hy == HP - 1 || hx == 0 || hx == HP - 1) {
+            uint4* p = reinterpret_cast<uint4*>(sA + i * A_LD);
+#pragma unroll
+            for (int j = 0; j < A_LD / 8; ++j) p[j] = make_uint4(0, 0, 0, 0);
+        }
+    }
+    // interior: 400 pixels x 4 chunks of 16 B
+    const bf16* xin = x + (size_t)img * NPIX * ldx + grp * GC;
+    for (int i = tid; i < NPIX * 4; i += THREADS) {
+        const int p = i >> 2, c = i & 3;
+        const int py = p / HW, px = p % HW;
+        cp_async16(sA + ((py + 1) * HP + px + 1) * A_LD + c * 8, xin + (size_t)p * ldx + c * 8);
+    }
     const bf16* wsrc = wg + (size_t)grp * 9 * GC * GC;
     for (int i = tid; i < 9 * GC * 4; i += THREADS) {
         const int row = i >> 2, c = i & 3;
         cp_async16(sW + row * W_LD + c * 8, wsrc + row * GC + c * 8);
     }
-    for (int i = tid; i < 2 * HP * HP; i += THREADS) {
-        const int px = i % (HP * HP), hy = px / HP, hx = px % HP;
-        if (hy == 0 || hy == HP - 1 || hx == 0 || hx == HP - 1) {
-            uint4* p = reinterpret_cast<uint4*>(sAbuf + (i / (HP * HP)) * A_ELEMS + px * A_LD);
-#pragma unroll
-            for (int j = 0; j < A_LD / 8; ++j) p[j] = make_uint4(0, 0, 0, 0);
-        }
-    }
-    auto prefetch = [&](int img, int buf) {          // interior: 400 pixels x 4 chunks of 16 B
-        const bf16* xin = x + (size_t)img * NPIX * ldx + grp * GC;
-        bf16* dst = sAbuf + buf * A_ELEMS;
-        for (int i = tid; i < NPIX * 4; i += THREADS) {
-            const int p = i >> 2, c = i & 3;
-            cp_async16(dst + ((p / HW + 1) * HP + p % HW + 1) * A_LD + c * 8, xin + (size_t)p * ldx + c * 8);
-        }
-    };
-    if ((int)blockIdx.x < B) prefetch(blockIdx.x, 0);
     asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
 
     // ldmatrix row assignment: lane -> (row within the m16 tile, 8-wide k half)
     const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8;
@@ -82,67 +80,56 @@ __global__ void __launch_bounds__(THREADS, 2) gconv3x3_kernel(const bf16* __rest
         a_off[mt] = ((p / HW) * HP + (p % HW)) * A_LD + lk;
     }
     const int g = lane >> 2, t = lane & 3;
-
-    int it = 0;
-    for (int img = blockIdx.x; img < B; img += gridDim.x, ++it) {
-        const int nxt = img + gridDim.x;
-        if (nxt < B) prefetch(nxt, (it + 1) & 1);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 1;" ::: "memory");      // everything but the newest group has landed
-        __syncthreads();
-        const bf16* sA = sAbuf + (it & 1) * A_ELEMS;
-
-        float acc[TILES_PER_WARP][4][4];
+    float acc[TILES_PER_WARP][4][4];
 #pragma unroll
-        for (int mt = 0; mt < TILES_PER_WARP; ++mt)
+    for (int mt = 0; mt < TILES_PER_WARP; ++mt)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[mt][j][0] = acc[mt][j][1] = acc[mt][j][2] = acc[mt][j][3] = 0.f;
+        for (int j = 0; j < 4; ++j) acc[mt][j][0] = acc[mt][j][1] = acc[mt][j][2] = acc[mt][j][3] = 0.f;
+
 #pragma unroll 1
-        for (int tap = 0; tap < 9; ++tap) {
-            const int tap_off = ((tap / 3) * HP + (tap % 3)) * A_LD;
-            const bf16* wt = sW + tap * GC * W_LD;
+    for (int tap = 0; tap < 9; ++tap) {
+        const int tap_off = ((tap / 3) * HP + (tap % 3)) * A_LD;
+        const bf16* wt = sW + tap * GC * W_LD;
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-                uint32_t b[4][2];
+        for (int ks = 0; ks < 2; ++ks) {
+            uint32_t b[4][2];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    b[j][0] = *reinterpret_cast<const uint32_t*>(wt + (j * 8 + g) * W_LD + ks * 16 + t * 2);
-                    b[j][1] = *reinterpret_cast<const uint32_t*>(wt + (j * 8 + g) * W_LD + ks * 16 + 8 + t * 2);
-                }
+            for (int j = 0; j < 4; ++j) {
+                b[j][0] = *reinterpret_cast<const uint32_t*>(wt + (j * 8 + g) * W_LD + ks * 16 + t * 2);
+                b[j][1] = *reinterpret_cast<const uint32_t*>(wt + (j * 8 + g) * W_LD + ks * 16 + 8 + t * 2);
+            }
 #pragma unroll
-                for (int mt = 0; mt < TILES_PER_WARP; ++mt) {
-                    uint32_t a0, a1, a2, a3;
-                    ldmatrix_x4(a0, a1, a2, a3, sA + a_off[mt] + tap_off + ks * 16);
+            for (int mt = 0; mt < TILES_PER_WARP; ++mt) {
+                uint32_t a0, a1, a2, a3;
+                ldmatrix_x4(a0, a1, a2, a3, sA + a_off[mt] + tap_off + ks * 16);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) mma16816(acc[mt][j], a0, a1, a2, a3, b[j][0], b[j][1]);
-                }
+                for (int j = 0; j < 4; ++j) mma16816(acc[mt][j], a0, a1, a2, a3, b[j][0], b[j][1]);
             }
         }
-        // epilogue: rows g / g+8 of each tile, channels j*8 + t*2 (+1)
-#pragma unroll
-        for (int mt = 0; mt < TILES_PER_WARP; ++mt) {
-#pragma unroll
-            for (int hr = 0; hr < 2; ++hr) {
-                const int p = (warp * TILES_PER_WARP + mt) * 16 + g + hr * 8;
-                const size_t row = (size_t)img * NPIX + p;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int ch = grp * GC + j * 8 + t * 2;
-                    float v0 = acc[mt][j][hr * 2], v1 = acc[mt][j][hr * 2 + 1];
-                    if (y2) *reinterpret_cast<__nv_bfloat162*>(y2 + row * ldy2 + ch) = __floats2bfloat162_rn(v0, v1);
-                    if (act == ACT_GELU) { v0 = gelu_fast(v0); v1 = gelu_fast(v1); }
-                    if (aux) {
-                        const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(aux + row * ldaux + ch);
-                        v0 *= act_grad(__bfloat162float(a.x), dact);
-                        v1 *= act_grad(__bfloat162float(a.y), dact);
-                    }
-                    *reinterpret_cast<__nv_bfloat162*>(y + row * ldy + ch) = __floats2bfloat162_rn(v0, v1);
-                }
-            }
-        }
-        __syncthreads();      // every warp is done with this tile before the next prefetch overwrites it
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+
+    // epilogue: rows g / g+8 of each tile, channels j*8 + t*2 (+1)
+#pragma unroll
+    for (int mt = 0; mt < TILES_PER_WARP; ++mt) {
+#pragma unroll
+        for (int hr = 0; hr < 2; ++hr) {
+            const int p = (warp * TILES_PER_WARP + mt) * 16 + g + hr * 8;
+            const size_t row = (size_t)img * NPIX + p;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int ch = grp * GC + j * 8 + t * 2;
+                float v0 = acc[mt][j][hr * 2], v1 = acc[mt][j][hr * 2 + 1];
+                if (y2) *reinterpret_cast<__nv_bfloat162*>(y2 + row * ldy2 + ch) = __floats2bfloat162_rn(v0, v1);
+                if (act == ACT_GELU) { v0 = gelu_fast(v0); v1 = gelu_fast(v1); }
+                if (aux) {
+                    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(aux + row * ldaux + ch);
+                    v0 *= act_grad(__bfloat162float(a.x), dact);
+                    v1 *= act_grad(__bfloat162float(a.y), dact);
+                }
+                *reinterpret_cast<__nv_bfloat162*>(y + row * ldy + ch) = __floats2bfloat162_rn(v0, v1);
+            }
+        }
+    }
 }
 
 // fp32 grouped weight [256][32][3][3] -> bf16 [8][9][32 n][32 k].  transpose_flip = 1 gives the conv-transpose operand
@@ -170,10 +157,9 @@ int sunb_gconv3x3(const void* x, int ldx, const void* wg, void* y, int ldy, void
         SUNB_CHECK_CUDA(cudaFuncSetAttribute(gconv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
         configured = true;
     }
-    const int per_group = B < 37 ? B : 37;          // 8 groups x 37 CTAs = 296 = 2 persistent CTAs per SM
-    gconv3x3_kernel<<<dim3(per_group, 8), THREADS, SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(
+    gconv3x3_kernel<<<dim3(B, 8), THREADS, SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<const bf16*>(wg), reinterpret_cast<bf16*>(y), ldy,
-        reinterpret_cast<bf16*>(y2), ldy2, reinterpret_cast<const bf16*>(aux), ldaux, B, act, dact);
+        reinterpret_cast<bf16*>(y2), ldy2, reinterpret_cast<const bf16*>(aux), ldaux, act, dact);
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
 }
