@@ -200,7 +200,14 @@ def measure_train_step(args, device, world, rank, sd):
     model = model.to(device).train()
     broadcast_module_state(model)
     opt, _ = utils.make_optimizer(model.parameters(), "sgd", lr=1e-3, weight_decay=5e-4)
-    reducer = GradAllReducer(model.parameters())
+    # encoder gradients are all-reduced inside the native backward (overlapped); the reducer below only handles what is
+    # left (the head's `temp`), so with overlap on it all-reduces a 1-element bucket
+    overlap = world > 1 and os.environ.get("SUNB_DDP_OVERLAP", "1") == "1"
+    if overlap:
+        model.encoder.enable_data_parallel()
+        reducer = GradAllReducer([model.temp])
+    else:
+        reducer = GradAllReducer(model.parameters())
     lo, hi = shard_range(TRAIN_EPISODES, rank, world)
     ep = hi - lo
     g = torch.Generator(device=device).manual_seed(77 + rank)
@@ -213,10 +220,9 @@ def measure_train_step(args, device, world, rank, sd):
         xs, xq = fs.split_shot_query(data, TRAIN_WAY, TRAIN_SHOT, TRAIN_QUERY, ep_per_batch=ep)
         logits = model(xs, xq).view(-1, TRAIN_WAY)
         loss = F.cross_entropy(logits, label)
-        reducer.attach()
-        reducer.flat.zero_()
+        opt.zero_grad(set_to_none=True)      # fresh .grad tensors every step (also what makes the step graph-capturable)
         loss.backward()
-        reducer.all_reduce_mean()
+        reducer.all_reduce_mean()            # world 1: no-op; overlap mode: only `temp` is left to reduce
         opt.step()
         return loss
 
@@ -240,6 +246,7 @@ def measure_train_step(args, device, world, rank, sd):
             mode = "cuda_graph"
         except Exception as exc:          # keep measuring: eager mode is still the real public-API path
             torch.cuda.synchronize()
+            torch.cuda.manual_seed(4321 + rank)      # a failed capture leaves the CUDA generator in capture mode
             if rank == 0:
                 print(f"[bench] CUDA-graph capture of the train step failed ({type(exc).__name__}: {exc}); using eager launches",
                       file=sys.stderr)
@@ -264,7 +271,8 @@ def measure_train_step(args, device, world, rank, sd):
     return {"metric": "SUN-M meta-tuning step (fwd+bwd+allreduce+SGD)", "ms_per_step": ms.item(), "unit": "ms",
             "images_per_step": TRAIN_IMAGES, "episodes_per_gpu": ep, "scaling": "strong", "higher_is_better": False,
             "achieved_tflops_per_gpu": flops / world / (ms.item() * 1e-3) / 1e12, "loss_last": float(loss.item()),
-            "launch_mode": mode,
+            "launch_mode": mode, "grad_allreduce": ("overlapped with backward (per-stage NCCL all-reduce on a side stream)"
+                                                   if overlap else ("single flat bucket after backward" if world > 1 else "none (1 GPU)")),
             "config": "8 episodes x 10-way x (1 shot + 5 query), drop_path_rate 0.5, SGD(1e-3, 0.9, wd 5e-4), "
                       "BN batch statistics per replica"}
 

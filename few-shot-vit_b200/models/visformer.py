@@ -147,6 +147,14 @@ class Visformer(nn.Module):
     def _bn_in_eval(self):
         return all(not m.training for m in self.modules() if isinstance(m, nn.BatchNorm2d))
 
+    def enable_data_parallel(self, group=None):
+        """Multi-GPU meta-tuning (one process per GPU): all-reduce(mean) the encoder gradients inside the native backward
+        pass, overlapped with the remaining backward kernels (replaces nn.DataParallel's reduce_add, train_meta.py:128-129).
+        BatchNorm statistics stay per replica, as under DataParallel."""
+        from sunb200.dist import GradComm
+        self._train_engine.grad_comm = GradComm(group)
+        return self
+
     def _drop_path_scales(self, batch, device):
         """DropPath draws in the reference's forward order (visformer.py:89-97, 261-262): per block with rate > 0 one
         draw for the attention branch (stages 2/3) and one for the MLP; scale = floor(keep + U[0,1)) / keep."""
@@ -205,7 +213,7 @@ class _EncoderTrainFn(torch.autograd.Function):
         dd = ddense.contiguous().float() if ddense is not None else None
         if dp is None and dd is None:
             return (None,) * (4 + len(ctx.names))
-        G = ctx.eng.backward(ctx.P, ctx.c, dp, dd)
+        G = ctx.eng.backward(ctx.P, ctx.c, dp, dd, comm=getattr(ctx.eng, "grad_comm", None))
         ctx.c = None
         return (None, None, None, None) + tuple(G[n] for n in ctx.names)
 

@@ -63,3 +63,27 @@ def broadcast_module_state(module: torch.nn.Module, src: int = 0, group=None):
         return
     for t in list(module.parameters()) + list(module.buffers()):
         dist.broadcast(t.data, src=src, group=group)
+
+
+class GradComm:
+    """Overlapped data-parallel gradient reduction for the native backward pass (sunb200/train.py): every ready slice of
+    the flat gradient buffer is all-reduced (sum) on a dedicated stream while the compute stream keeps running the
+    remaining backward kernels; `finish` joins the streams and turns the sums into means."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.stream = torch.cuda.Stream() if torch.cuda.is_available() else None
+
+    def all_reduce_async(self, flat_slice: torch.Tensor):
+        if self.world == 1:
+            return
+        self.stream.wait_stream(torch.cuda.current_stream())       # the slice's producers have been enqueued
+        with torch.cuda.stream(self.stream):
+            dist.all_reduce(flat_slice, op=dist.ReduceOp.SUM, group=self.group)
+
+    def finish(self, flat: torch.Tensor):
+        if self.world == 1:
+            return
+        torch.cuda.current_stream().wait_stream(self.stream)
+        flat.div_(self.world)

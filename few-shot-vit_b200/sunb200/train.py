@@ -279,10 +279,38 @@ class TrainEngine:
         return pooled, dense, ctx
 
     # ------------------------------------------------------------------ backward
-    def backward(self, P, ctx, dpooled, ddense=None) -> Dict[str, torch.Tensor]:
+    # parameter groups in the order their gradients become final during the backward pass
+    @staticmethod
+    def _grad_groups(names):
+        def pick(*prefixes):
+            return [n for n in names if n.startswith(prefixes)]
+        return [pick("stage3.", "norm."), pick("patch_embed3.", "pos_embed3"), pick("stage2."),
+                pick("patch_embed2.", "pos_embed2"), pick("stage1."), pick("stem.", "pos_embed1")]
+
+    def backward(self, P, ctx, dpooled, ddense=None, comm=None) -> Dict[str, torch.Tensor]:
+        """Gradients of every encoder parameter.  With `comm` (a GradComm, multi-GPU data parallel) the gradients live in
+        one flat buffer ordered by readiness and each group is all-reduced on a side stream as soon as its stage of
+        the backward pass has been enqueued, overlapping NCCL with the remaining dgrad / wgrad kernels."""
         lib = self.lib
         B, W = ctx["B"], ctx["W"]
-        G = {k: torch.zeros_like(v, dtype=torch.float32) for k, v in P.items()}
+        groups = self._grad_groups(list(P.keys()))
+        order = [n for grp in groups for n in grp]
+        assert len(order) == len(P), "parameter grouping must cover every encoder parameter"
+        flat = torch.zeros(sum(P[n].numel() for n in order), dtype=torch.float32, device=self.dev)
+        G, spans, off = {}, [], 0
+        for grp in groups:
+            lo = off
+            for n in grp:
+                G[n] = flat[off:off + P[n].numel()].view_as(P[n])
+                off += P[n].numel()
+            spans.append((lo, off))
+        done = iter(spans)
+
+        def group_ready():
+            lo, hi = next(done)
+            if comm is not None:
+                comm.all_reduce_async(flat[lo:hi])
+
         Mf = B * 25
         dy = self.empty(Mf, 512)
         N.check(lib.sunb_pool_backward(N.ptr(dpooled), N.ptr(ddense), dy.data_ptr(), B, 25, 512, _st()), "sunb_pool_backward")
@@ -294,6 +322,7 @@ class TrainEngine:
             for _ in range(depth):
                 g = self._attn_block_backward(blocks[idx], g, P, G, W)
                 idx -= 1
+            group_ready()                                   # stage blocks (+ final norm for stage 3)
             # PatchEmbed + pos_embed (visformer.py:438-441, 447-450)
             S, M = side * side, B * side * side
             pe = ctx[f"pe{stage}"]
@@ -310,10 +339,15 @@ class TrainEngine:
             dxs = gemm(dyp, W[f"pe{stage}.d"], M, 4 * cin, dim, out=self.empty(M, 4 * cin))
             g = self.empty(M * 4, cin)
             N.check(lib.sunb_s2d_reorder(dxs.data_ptr(), g.data_ptr(), B, 2 * side, 2 * side, cin, 1, _st()), "sunb_s2d_reorder")
+            group_ready()                                   # patch embed + its pos_embed
         for _ in range(DEPTH[0]):
             g = self._conv_block_backward(blocks[idx], g, P, G, W, B)
             idx -= 1
+        group_ready()
         self._stem_backward(ctx, g, P, G, W, B)
+        group_ready()
+        if comm is not None:
+            comm.finish(flat)
         return G
 
     def _attn_block_backward(self, b, g, P, G, W, ):
