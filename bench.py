@@ -234,8 +234,10 @@ def measure_train_step(args, device, world, rank, sd):
     if os.environ.get("SUNB_TRAIN_GRAPH", "1") == "1":
         try:
             torch.cuda.synchronize()
+            rng_state = torch.cuda.get_rng_state(device)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            # thread_local: the NCCL watchdog thread's event queries must not invalidate the capture
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 static_loss = step()
             graph.replay()
             torch.cuda.synchronize()
@@ -246,7 +248,11 @@ def measure_train_step(args, device, world, rank, sd):
             mode = "cuda_graph"
         except Exception as exc:          # keep measuring: eager mode is still the real public-API path
             torch.cuda.synchronize()
-            torch.cuda.manual_seed(4321 + rank)      # a failed capture leaves the CUDA generator in capture mode
+            try:                                     # a failed capture can leave the CUDA generator in capture mode
+                torch.cuda.set_rng_state(rng_state, device)
+                torch.cuda.manual_seed(4321 + rank)
+            except Exception:
+                pass
             if rank == 0:
                 print(f"[bench] CUDA-graph capture of the train step failed ({type(exc).__name__}: {exc}); using eager launches",
                       file=sys.stderr)
