@@ -216,6 +216,19 @@ def measure_train_step(args, device, world, rank, sd):
     data = data.reshape(-1, 3, 80, 80)
     label = fs.make_nk_label(TRAIN_WAY, TRAIN_QUERY, ep).to(device)
 
+    # DropPath scales (mask / keep per sample and branch) live in static tensors that are re-drawn before every step with
+    # the module's own sampler; the (graph-capturable) step only reads them, so no RNG call sits inside a capture.
+    enc = model.encoder
+    draw = enc._drop_path_scales
+    static_rs = draw(data.shape[0], device)
+    enc._drop_path_scales = lambda batch, dev: static_rs
+
+    def refresh_drop_path():
+        fresh = draw(data.shape[0], device)
+        for name, lst in static_rs.items():
+            for dst, src in zip(lst, fresh[name]):
+                dst.copy_(src)
+
     def step():
         xs, xq = fs.split_shot_query(data, TRAIN_WAY, TRAIN_SHOT, TRAIN_QUERY, ep_per_batch=ep)
         logits = model(xs, xq).view(-1, TRAIN_WAY)
@@ -226,15 +239,18 @@ def measure_train_step(args, device, world, rank, sd):
         opt.step()
         return loss
 
+    def eager_step():
+        refresh_drop_path()
+        return step()
+
     for _ in range(3):
-        loss = step()
+        loss = eager_step()
     # Whole-step CUDA graph (forward, backward, NCCL all-reduce, SGD): the step is ~500 short launches, which becomes
     # launch-bound once the batch is sharded over 4-8 GPUs.  Falls back to eager launches if capture is refused.
-    run, mode = step, "eager"
+    run, mode = eager_step, "eager"
     if os.environ.get("SUNB_TRAIN_GRAPH", "1") == "1":
         try:
             torch.cuda.synchronize()
-            rng_state = torch.cuda.get_rng_state(device)
             graph = torch.cuda.CUDAGraph()
             # thread_local: the NCCL watchdog thread's event queries must not invalidate the capture
             with torch.cuda.graph(graph, capture_error_mode="thread_local"):
@@ -243,20 +259,16 @@ def measure_train_step(args, device, world, rank, sd):
             torch.cuda.synchronize()
 
             def run():
+                refresh_drop_path()
                 graph.replay()
                 return static_loss
             mode = "cuda_graph"
         except Exception as exc:          # keep measuring: eager mode is still the real public-API path
             torch.cuda.synchronize()
-            try:                                     # a failed capture can leave the CUDA generator in capture mode
-                torch.cuda.set_rng_state(rng_state, device)
-                torch.cuda.manual_seed(4321 + rank)
-            except Exception:
-                pass
             if rank == 0:
                 print(f"[bench] CUDA-graph capture of the train step failed ({type(exc).__name__}: {exc}); using eager launches",
                       file=sys.stderr)
-            run, mode = step, "eager"
+            run, mode = eager_step, "eager"
     for _ in range(2):
         loss = run()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
