@@ -219,7 +219,12 @@ def measure_train_step(args, device, world, rank, sd):
     # DropPath scales (mask / keep per sample and branch) live in static tensors that are re-drawn before every step with
     # the module's own sampler; the (graph-capturable) step only reads them, so no RNG call sits inside a capture.
     enc = model.encoder
-    draw = enc._drop_path_scales
+    dp_gen = torch.Generator(device=device)          # private generator: never registered with a CUDA graph
+    dp_gen.manual_seed(99 + rank)
+    sampler = enc._drop_path_scales
+
+    def draw(batch, dev):
+        return sampler(batch, dev, generator=dp_gen)
     static_rs = draw(data.shape[0], device)
     enc._drop_path_scales = lambda batch, dev: static_rs
 

@@ -155,7 +155,7 @@ class Visformer(nn.Module):
         self._train_engine.grad_comm = GradComm(group)
         return self
 
-    def _drop_path_scales(self, batch, device):
+    def _drop_path_scales(self, batch, device, generator=None):
         """DropPath draws in the reference's forward order (visformer.py:89-97, 261-262): per block with rate > 0 one
         draw for the attention branch (stages 2/3) and one for the MLP; scale = floor(keep + U[0,1)) / keep."""
         rs = {}
@@ -165,8 +165,8 @@ class Visformer(nn.Module):
                     continue
                 keep = 1.0 - blk.drop_prob
                 n = 1 if stage == "stage1" else 2
-                rs[f"{stage}.{i}"] = [torch.floor(keep + torch.rand(batch, 1, 1, 1, device=device)).div_(keep).view(batch)
-                                      for _ in range(n)]
+                rs[f"{stage}.{i}"] = [torch.floor(keep + torch.rand(batch, 1, 1, 1, device=device, generator=generator))
+                                      .div_(keep).view(batch) for _ in range(n)]
         return rs
 
     def forward(self, x, taps=None, drop_path_scales=None):

@@ -34,7 +34,7 @@ def _worker(rank, world, port, out_dir):
     xs, xq = shard_episodes(xs, xq, rank, world)
     label = fs.make_nk_label(way, query, xs.shape[0]).cuda()
     grads = {}
-    for mode in ("flat", "overlap"):
+    for mode in ("flat", "flat_again", "overlap"):
         model = models.make("meta-baseline", encoder="visformer_micro_80", encoder_args={})
         model.load_state_dict(sd)
         model = model.cuda().train()
@@ -51,14 +51,18 @@ def _worker(rank, world, port, out_dir):
         torch.cuda.synchronize()
         grads[mode] = {n: p.grad.detach().clone() for n, p in model.named_parameters()}
     zero_grad = ("patch_embed2.proj.bias", "patch_embed2.norm.bn.bias", "patch_embed3.proj.bias", "patch_embed3.norm.bn.bias")
-    rels = []
-    for n in grads["flat"]:
-        if n.endswith(zero_grad):          # analytically zero under batch-stat BN: pure rounding noise, no relative error
-            continue
-        a, b = grads["flat"][n], grads["overlap"][n]
-        rels.append((((a - b).norm() / (a.norm() + 1e-12)).item(), n))
-    rels.sort(reverse=True)
-    torch.save({"worst": rels[0][0], "median": rels[len(rels) // 2][0], "top": rels[:5],
+    def compare(x, y):
+        rels = []
+        for n in grads[x]:
+            if n.endswith(zero_grad):      # analytically zero under batch-stat BN: pure rounding noise, no relative error
+                continue
+            a, b = grads[x][n], grads[y][n]
+            rels.append((((a - b).norm() / (a.norm() + 1e-12)).item(), n))
+        rels.sort(reverse=True)
+        return rels
+    noise, rels = compare("flat", "flat_again"), compare("flat", "overlap")
+    torch.save({"worst": rels[0][0], "median": rels[len(rels) // 2][0], "top": rels[:4],
+                "noise_worst": noise[0][0], "noise_median": noise[len(noise) // 2][0],
                 "probe": grads["overlap"]["encoder.stage3.2.attn.proj.weight"].cpu()},
                os.path.join(out_dir, f"rank{rank}.pt"))
     dist.barrier()
@@ -70,8 +74,10 @@ def test_overlapped_allreduce_matches_flat_allreduce(tmp_path):
     import torch.multiprocessing as mp
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     r0, r1 = torch.load(tmp_path / "rank0.pt"), torch.load(tmp_path / "rank1.pt")
-    # Two independent runs of the same step: fp32 atomic-add order (BN statistics, split-K wgrad) differs, which flips a few
-    # bf16 roundings downstream -- run-to-run noise, far below the bf16-vs-fp32 tolerance of the step itself.
-    print("top offenders:", r0["top"])
-    assert r0["median"] < 5e-3 and r0["worst"] < 0.1, r0["top"]
+    # Independent runs of the same step differ by the fp32 atomic-add order (BN statistics, split-K wgrad), which flips a few
+    # bf16 roundings downstream.  The overlapped schedule must sit inside that run-to-run noise (measured with two flat runs),
+    # far below the bf16-vs-fp32 tolerance of the step itself.
+    print(f"flat vs flat: median {r0['noise_median']:.2e} worst {r0['noise_worst']:.2e}; "
+          f"flat vs overlap: median {r0['median']:.2e} worst {r0['worst']:.2e}; top {r0['top']}")
+    assert r0["median"] <= 3 * r0["noise_median"] + 1e-3 and r0["worst"] <= 3 * r0["noise_worst"] + 1e-2, r0["top"]
     assert torch.equal(r0["probe"], r1["probe"])          # ranks hold identical averaged gradients
