@@ -87,6 +87,20 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* _
     }
 }
 
+// frozen BatchNorm (module in eval() inside a training step, utils.freeze_bn): running statistics instead of batch statistics
+__global__ void bn_frozen_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 const float* __restrict__ rmean, const float* __restrict__ rvar, float eps, int C,
+                                 float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                                 float* __restrict__ rstd_out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float rstd = rsqrtf(rvar[c] + eps);
+    scale[c] = gamma[c] * rstd;
+    shift[c] = beta[c] - rmean[c] * gamma[c] * rstd;
+    mean_out[c] = rmean[c];
+    rstd_out[c] = rstd;
+}
+
 // y = act(x*scale + shift) + tab[(m % tab_mod)][c]   (tab nullable); vector of 8 channels per thread
 __global__ void bn_apply_kernel(const bf16* __restrict__ x, int ldx, const float* __restrict__ scale,
                                 const float* __restrict__ shift, int act, const float* __restrict__ tab, int tab_mod,
@@ -202,15 +216,16 @@ __global__ void stem_tail_bwd_kernel(const bf16* __restrict__ c3, const bf16* __
 // BN backward coefficients.  dx = a*(dz - c1 - (x - mean)*c2);  dgamma = rstd*(sum(dz*x) - mean*sum(dz));  dbeta = sum(dz)
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ sdz, const float* __restrict__ sdzx, float count,
                                        const float* __restrict__ mean, const float* __restrict__ rstd,
-                                       const float* __restrict__ gamma, int C, float* __restrict__ a,
+                                       const float* __restrict__ gamma, int C, int frozen, float* __restrict__ a,
                                        float* __restrict__ c1, float* __restrict__ c2, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const float cen = sdzx[c] - mean[c] * sdz[c];        // sum dz*(x-mean)
     a[c] = gamma[c] * rstd[c];
-    c1[c] = sdz[c] / count;
-    c2[c] = rstd[c] * rstd[c] * cen / count;
+    // frozen statistics do not depend on the batch: dx = a*dz, no mean / projection terms
+    c1[c] = frozen ? 0.f : sdz[c] / count;
+    c2[c] = frozen ? 0.f : rstd[c] * rstd[c] * cen / count;
     dgamma[c] += rstd[c] * cen;
     dbeta[c] += sdz[c];
 }
@@ -344,17 +359,20 @@ __global__ void pool_bwd_kernel(const float* __restrict__ dpooled, const float* 
 }
 
 // stem K=27 weight gradients: dW1[64][27] += sum_p da1[p, c] * patch(x)[p, :],  dWd[128][27] likewise from didn.
-// block = (image, 8 output rows), 192 threads = channel lanes (0..63 conv1, 64..191 downsample)
-constexpr int SW_ROWS = 8;
+// block = one image half (20 output rows), 192 threads = channel lanes (0..63 conv1, 64..191 downsample); the input rows
+// are staged once in shared memory and every thread keeps its 27 partial sums in registers -> 27 atomics per thread
+// per half image (the atomics, not the FMAs, bound this kernel).
+constexpr int SW_ROWS = 20;
 __global__ void __launch_bounds__(192) stem_wgrad_kernel(const float* __restrict__ x, const bf16* __restrict__ da1,
                                                          const bf16* __restrict__ didn, float* __restrict__ dw1,
                                                          float* __restrict__ dwd, int B) {
-    __shared__ float in[3][2 * SW_ROWS + 1][82];
+    extern __shared__ float in_s[];                 // [3][2*SW_ROWS+1][82]
+    constexpr int RS = 2 * SW_ROWS + 1;
     const int img = blockIdx.x / (40 / SW_ROWS), oy0 = (blockIdx.x % (40 / SW_ROWS)) * SW_ROWS;
-    for (int i = threadIdx.x; i < 3 * (2 * SW_ROWS + 1) * 82; i += blockDim.x) {
-        const int c = i / ((2 * SW_ROWS + 1) * 82), r = (i / 82) % (2 * SW_ROWS + 1), xx = i % 82;
+    for (int i = threadIdx.x; i < 3 * RS * 82; i += blockDim.x) {
+        const int c = i / (RS * 82), r = (i / 82) % RS, xx = i % 82;
         const int iy = 2 * oy0 - 1 + r, ix = xx - 1;
-        in[c][r][xx] = (iy >= 0 && iy < 80 && ix >= 0 && ix < 80) ? x[((size_t)(img * 3 + c) * 80 + iy) * 80 + ix] : 0.f;
+        in_s[i] = (iy >= 0 && iy < 80 && ix >= 0 && ix < 80) ? x[((size_t)(img * 3 + c) * 80 + iy) * 80 + ix] : 0.f;
     }
     __syncthreads();
     const int t = threadIdx.x;
@@ -371,7 +389,8 @@ __global__ void __launch_bounds__(192) stem_wgrad_kernel(const float* __restrict
                 for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
                     for (int kx = 0; kx < 3; ++kx)
-                        acc[(ci * 3 + ky) * 3 + kx] = fmaf(gv, in[ci][2 * r + ky][2 * ox + kx], acc[(ci * 3 + ky) * 3 + kx]);
+                        acc[(ci * 3 + ky) * 3 + kx] =
+                            fmaf(gv, in_s[(ci * RS + 2 * r + ky) * 82 + 2 * ox + kx], acc[(ci * 3 + ky) * 3 + kx]);
         }
     }
     float* dst = t < 64 ? dw1 + t * 27 : dwd + (t - 64) * 27;
@@ -445,12 +464,20 @@ int sunb_stem_tail_backward(const void* c3, const void* idn, const float* s3, co
     return SUNB_OK;
 }
 
+int sunb_bn_frozen(const float* gamma, const float* beta, const float* rmean, const float* rvar, float eps, int C,
+                   float* scale, float* shift, float* mean, float* rstd, void* stream) {
+    SUNB_REQUIRE(gamma && beta && rmean && rvar && scale && shift && mean && rstd && C > 0, "bn_frozen: bad arguments");
+    bn_frozen_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(gamma, beta, rmean, rvar, eps, C, scale, shift, mean, rstd);
+    SUNB_CHECK_CUDA(cudaGetLastError());
+    return SUNB_OK;
+}
+
 int sunb_bn_bwd_finalize(const float* sdz, const float* sdzx, float count, const float* mean, const float* rstd,
-                         const float* gamma, int C, float* a, float* c1, float* c2, float* dgamma, float* dbeta,
+                         const float* gamma, int C, int frozen, float* a, float* c1, float* c2, float* dgamma, float* dbeta,
                          void* stream) {
     SUNB_REQUIRE(sdz && sdzx && mean && rstd && gamma && a && c1 && c2 && dgamma && dbeta, "bn_bwd_finalize: bad arguments");
-    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(sdz, sdzx, count, mean, rstd, gamma, C, a, c1, c2, dgamma,
-                                                                     dbeta);
+    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(sdz, sdzx, count, mean, rstd, gamma, C, frozen, a, c1, c2,
+                                                                     dgamma, dbeta);
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
 }
@@ -520,8 +547,9 @@ int sunb_pool_backward(const float* dpooled, const float* ddense, void* dy, int 
 
 int sunb_stem_wgrad(const float* x, const void* da1, const void* didn, float* dw1, float* dwd, int B, void* stream) {
     SUNB_REQUIRE(x && da1 && didn && dw1 && dwd && B > 0, "stem_wgrad: bad arguments");
-    stem_wgrad_kernel<<<B * (40 / SW_ROWS), 192, 0, ST(stream)>>>(x, reinterpret_cast<const bf16*>(da1),
-                                                                   reinterpret_cast<const bf16*>(didn), dw1, dwd, B);
+    const size_t smem = (size_t)3 * (2 * SW_ROWS + 1) * 82 * sizeof(float);      // 40 KB
+    stem_wgrad_kernel<<<B * (40 / SW_ROWS), 192, smem, ST(stream)>>>(x, reinterpret_cast<const bf16*>(da1),
+                                                                      reinterpret_cast<const bf16*>(didn), dw1, dwd, B);
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
 }

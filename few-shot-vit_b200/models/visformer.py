@@ -178,10 +178,9 @@ class Visformer(nn.Module):
             out = self._engine.forward(state, x, want_dense=self.output != "pooled", taps=taps)
             pooled, dense = out["pooled"], out["dense"]
         else:
-            if bn_eval or any(not m.training for m in self.modules() if isinstance(m, nn.BatchNorm2d)):
-                raise NotImplementedError(
-                    "sunb200: training with frozen BatchNorm (utils.freeze_bn) is not built; the shipped SUN-M configs "
-                    "do not set freeze_bn.  There is deliberately no PyTorch fallback.")
+            # BatchNorm layers put in eval() by utils.freeze_bn use their running statistics inside the training step
+            self._train_engine.frozen_bn = frozenset(n for n, m in self.named_modules()
+                                                     if isinstance(m, nn.BatchNorm2d) and not m.training)
             rs = drop_path_scales if drop_path_scales is not None else self._drop_path_scales(x.shape[0], x.device)
             names = [n for n, _ in self.named_parameters()]
             params = [p for _, p in self.named_parameters()]

@@ -99,7 +99,8 @@ SIGNATURES = {
     "sunb_colstats": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_long, C.c_int, fp, fp, vp]),
     "sunb_bn_finalize": (C.c_int, [fp, fp, C.c_float, fp, fp, fp, fp, vp, C.c_float, C.c_float, C.c_int, fp, fp, fp, fp, vp]),
     "sunb_bn_apply": (C.c_int, [vp, C.c_int, fp, fp, C.c_int, fp, C.c_int, vp, C.c_int, C.c_long, C.c_int, vp]),
-    "sunb_bn_bwd_finalize": (C.c_int, [fp, fp, C.c_float, fp, fp, fp, C.c_int, fp, fp, fp, fp, fp, vp]),
+    "sunb_bn_frozen": (C.c_int, [fp, fp, fp, fp, C.c_float, C.c_int, fp, fp, fp, fp, vp]),
+    "sunb_bn_bwd_finalize": (C.c_int, [fp, fp, C.c_float, fp, fp, fp, C.c_int, C.c_int, fp, fp, fp, fp, fp, vp]),
     "sunb_bn_bwd_apply": (C.c_int, [vp, C.c_int, vp, C.c_int, fp, fp, fp, fp, vp, C.c_int, vp, C.c_int, C.c_long, C.c_int, vp]),
     "sunb_stem_tail_forward": (C.c_int, [vp, vp, fp, fp, fp, fp, fp, vp, C.c_int, vp]),
     "sunb_stem_tail_backward": (C.c_int, [vp, vp, fp, fp, fp, fp, vp, vp, C.c_int, vp]),

@@ -72,10 +72,10 @@ def wgrad(dY, X, out, P, Ma, Nb, *, Ca=None, Cb=None, ldo=None, taps=1, groups=1
 
 class BNRec:
     """Per-layer BatchNorm record: statistics of this step and the tensors the backward needs."""
-    __slots__ = ("name", "C", "count", "buf", "x")
+    __slots__ = ("name", "C", "count", "buf", "x", "frozen")
 
-    def __init__(self, name, Cc, count, buf, x):
-        self.name, self.C, self.count, self.buf, self.x = name, Cc, count, buf, x
+    def __init__(self, name, Cc, count, buf, x, frozen=False):
+        self.name, self.C, self.count, self.buf, self.x, self.frozen = name, Cc, count, buf, x, frozen
 
     # buf rows: 0 sum, 1 sq, 2 scale, 3 shift, 4 mean, 5 rstd, 6 sdz, 7 sdzx, 8 a, 9 c1, 10 c2
     def row(self, i):
@@ -85,6 +85,7 @@ class BNRec:
 class TrainEngine:
     def __init__(self):
         self.lib = N.lib()
+        self.frozen_bn = frozenset()       # names of BatchNorm layers currently in eval() (utils.freeze_bn)
 
     # ------------------------------------------------------------------ small wrappers
     def empty(self, *shape, dtype=torch.bfloat16):
@@ -93,7 +94,13 @@ class TrainEngine:
     def bn_forward(self, x, name, Cc, M, P, Bf, update_running=True) -> BNRec:
         """colstats + finalize for BatchNorm `name` over x [M, C] (bf16).  Running stats updated in place."""
         buf = torch.zeros(11, Cc, dtype=torch.float32, device=self.dev)
-        rec = BNRec(name, Cc, float(M), buf, x)
+        rec = BNRec(name, Cc, float(M), buf, x, frozen=name in self.frozen_bn)
+        if rec.frozen:      # module switched to eval() by utils.freeze_bn: running statistics, no update
+            N.check(self.lib.sunb_bn_frozen(P[name + ".weight"].data_ptr(), P[name + ".bias"].data_ptr(),
+                                            Bf[name + ".running_mean"].data_ptr(), Bf[name + ".running_var"].data_ptr(), BN_EPS,
+                                            Cc, buf[2].data_ptr(), buf[3].data_ptr(), buf[4].data_ptr(), buf[5].data_ptr(),
+                                            _st()), "sunb_bn_frozen")
+            return rec
         N.check(self.lib.sunb_colstats(x.data_ptr(), x.shape[-1], None, 0, M, Cc, buf[0].data_ptr(), buf[1].data_ptr(),
                                        _st()), "sunb_colstats")
         rm, rv, nbt = Bf[name + ".running_mean"], Bf[name + ".running_var"], Bf[name + ".num_batches_tracked"]
@@ -117,7 +124,7 @@ class TrainEngine:
         N.check(self.lib.sunb_colstats(dz.data_ptr(), dz.shape[-1], rec.x.data_ptr(), rec.x.shape[-1], M, rec.C,
                                        b[6].data_ptr(), b[7].data_ptr(), _st()), "sunb_colstats(bwd)")
         N.check(self.lib.sunb_bn_bwd_finalize(b[6].data_ptr(), b[7].data_ptr(), rec.count, b[4].data_ptr(), b[5].data_ptr(),
-                                              P[rec.name + ".weight"].data_ptr(), rec.C, b[8].data_ptr(), b[9].data_ptr(),
+                                              P[rec.name + ".weight"].data_ptr(), rec.C, int(rec.frozen), b[8].data_ptr(), b[9].data_ptr(),
                                               b[10].data_ptr(), G[rec.name + ".weight"].data_ptr(),
                                               G[rec.name + ".bias"].data_ptr(), _st()), "sunb_bn_bwd_finalize")
         out = self.empty(M, rec.C)

@@ -185,8 +185,11 @@ int sunb_bn_finalize(const float* sum, const float* sq, float count, const float
                      float* rstd, void* stream);
 int sunb_bn_apply(const void* x, int ldx, const float* scale, const float* shift, int act, const float* tab, int tab_mod,
                   void* out, int ldo, long M, int C, void* stream);
+/* frozen BatchNorm inside a training step (utils.freeze_bn, test_phase/utils/__init__.py:150-153): running statistics */
+int sunb_bn_frozen(const float* gamma, const float* beta, const float* rmean, const float* rvar, float eps, int C,
+                   float* scale, float* shift, float* mean, float* rstd, void* stream);
 int sunb_bn_bwd_finalize(const float* sdz, const float* sdzx, float count, const float* mean, const float* rstd,
-                         const float* gamma, int C, float* a, float* c1, float* c2, float* dgamma, float* dbeta,
+                         const float* gamma, int C, int frozen, float* a, float* c1, float* c2, float* dgamma, float* dbeta,
                          void* stream);
 int sunb_bn_bwd_apply(const void* dz, int lddz, const void* x, int ldx, const float* a, const float* c1, const float* c2,
                       const float* mean, const void* res, int ldr, void* out, int ldo, long M, int C, void* stream);

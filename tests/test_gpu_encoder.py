@@ -150,9 +150,39 @@ def test_token_label_model(golden_dir):
     assert flat.shape == (100, 65)
 
 
-def test_frozen_bn_training_fails_loudly():
+def test_frozen_bn_training_step_matches_oracle():
+    """utils.freeze_bn during training (test_phase/utils/__init__.py:150-153): BatchNorm uses its running statistics but
+    stays differentiable.  Compared with the oracle's autograd in eval-BN mode (fp32)."""
     import utils
-    m = models.make("meta-baseline", encoder="visformer_micro_80", encoder_args={}).cuda().train()
+    import torch.nn.functional as F
+    sd = O.calibrate_bn(O.init_meta_baseline_state_dict(12345))
+    m = models.make("meta-baseline", encoder="visformer_micro_80", encoder_args={})
+    m.load_state_dict(sd)
+    m = m.cuda().train()
     utils.freeze_bn(m)
-    with pytest.raises(NotImplementedError):
-        m.encoder(torch.zeros(2, 3, 80, 80, device="cuda"))
+    way, shot, query, ep = 3, 1, 2, 2
+    data = O.make_episode_images(500, ep * way, shot + query)
+    xs, xq = O.split_shot_query(data, way, shot, query, ep)
+    label = O.make_nk_label(way, query, ep)
+    logits = m(xs.cuda(), xq.cuda()).view(-1, way)
+    loss = F.cross_entropy(logits, label.cuda())
+    loss.backward()
+    params = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in sd.items()}
+    ref_logits = O.meta_baseline_forward(params, xs, xq, training=False).view(-1, way)
+    ref_loss = O.cross_entropy(ref_logits, label)
+    ref_loss.backward()
+    assert max_err(logits.detach().cpu(), ref_logits.detach()) < 0.25
+    assert abs(loss.item() - ref_loss.item()) < 0.05 * max(1.0, ref_loss.item())
+    before = {k: v.clone() for k, v in sd.items() if "running" in k}
+    for k, v in m.state_dict().items():                      # frozen statistics are not updated
+        if "running" in k:
+            assert torch.equal(v.cpu(), before[k]), k
+    worst = 0.0
+    for name, p in m.named_parameters():
+        ref = params[name].grad
+        if ref.norm().item() < 1e-7:
+            continue
+        rel = ((p.grad.cpu() - ref).norm() / ref.norm()).item()
+        worst = max(worst, rel)
+        assert rel < 0.3, (name, rel)
+    print(f"frozen-BN step: worst per-tensor gradient rel-L2 {worst:.4f}")
