@@ -310,6 +310,9 @@ def measure_train_step(args, device, world, rank, sd):
 
 
 def run_product(args):
+    # stdout carries exactly one JSON line: keep NCCL's version banner off it unless the caller asked for NCCL logging
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     import torch
     import torch.distributed as dist
     import models
