@@ -410,6 +410,42 @@ def run_product(args):
         # sanity: accuracy of the last step's logits on the class-structured episodes (not part of the timing)
         acc = (outs[0].reshape(-1, WAY).argmax(1) == label).float().mean().item()
 
+    # single-episode latency: test_few_shot.py's default (ep_per_batch = 1), eager launches and one CUDA graph replay
+    latency = None
+    if rank == 0:
+        with torch.no_grad():
+            one = dev_chunks[0][:IMGS_PER_EPISODE]
+            xs1, xq1 = fs.split_shot_query(one, WAY, SHOT, QUERY, ep_per_batch=1)
+            for _ in range(3):
+                model(xs1, xq1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(20):
+                model(xs1, xq1)
+            e1.record()
+            torch.cuda.synchronize()
+            latency = {"episodes": 1, "eager_ms": e0.elapsed_time(e1) / 20}
+            try:
+                side = torch.cuda.Stream(device=device)
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    model(xs1, xq1)
+                    g1 = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g1, stream=side, capture_error_mode="thread_local"):
+                        static_out = model(xs1, xq1)
+                    g1.replay()
+                    torch.cuda.synchronize()
+                    e0.record()
+                    for _ in range(20):
+                        g1.replay()
+                    e1.record()
+                    torch.cuda.synchronize()
+                    latency["cuda_graph_ms"] = e0.elapsed_time(e1) / 20
+                torch.cuda.current_stream().wait_stream(side)
+            except Exception as exc:
+                latency["cuda_graph_error"] = f"{type(exc).__name__}: {str(exc).splitlines()[0]}"
+
     episodes = world * EPISODES_PER_GPU * args.steps
     value = episodes / (ms_total * 1e-3)
     e2e_value = episodes / (ms_e2e * 1e-3)
@@ -454,6 +490,7 @@ def run_product(args):
                               "note": "whole eval step per GPU: 203.06 GFLOP/episode algorithmic vs sustained bf16 peak"},
             "cpu_baseline": cpu_base,
             "sanity_acc": acc,
+            "single_episode_latency": latency,
             "train_step": train,
         }
         print(json.dumps(line))
