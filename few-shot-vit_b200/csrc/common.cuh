@@ -144,6 +144,37 @@ __device__ __forceinline__ int map_out_row(const GemmParams& p, int m) {
     return m;
 }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one full 32-byte sector per thread-instruction, so the row-strided
+// epilogue traffic is made of whole sectors instead of 16-byte halves.
+__device__ __forceinline__ void ld_global_256(const void* p, uint32_t (&r)[8]) {
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p));
+}
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t (&r)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+// 16 consecutive bf16 <-> 16 floats through one 256-bit access
+__device__ __forceinline__ void load16_bf16(const bf16* p, float* f) {
+    uint32_t r[8];
+    ld_global_256(p, r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&r[j]);
+        f[2 * j] = __bfloat162float(h.x);
+        f[2 * j + 1] = __bfloat162float(h.y);
+    }
+}
+__device__ __forceinline__ void store16_bf16(bf16* p, const float* f) {
+    uint32_t r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+        r[j] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    st_global_256(p, r);
+}
+
 // Epilogue for NC consecutive columns [col, col+NC) of raster row m of group g.  v = fp32 accumulators.
 // Every per-element loop is branch-free inside (the activation switch is hoisted) so the unrolled bodies interleave.
 template <int NC>
@@ -160,7 +191,15 @@ __device__ __forceinline__ void epilogue_row(const GemmParams& p, int g, int m, 
     }
     if (p.resid) {
         const bf16* res = p.resid + (size_t)m * p.ldr + gcol;
-        if (full && ((((size_t)res) & 15) == 0)) {
+        if (full && (NC % 16 == 0) && ((((size_t)res) & 31) == 0)) {
+#pragma unroll
+            for (int i = 0; i < NC; i += 16) {
+                float f[16];
+                load16_bf16(res + i, f);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[i + j] += f[j];
+            }
+        } else if (full && ((((size_t)res) & 15) == 0)) {
 #pragma unroll
             for (int i = 0; i < NC; i += 8) {
                 const uint4 u = *reinterpret_cast<const uint4*>(res + i);
@@ -191,7 +230,10 @@ __device__ __forceinline__ void epilogue_row(const GemmParams& p, int g, int m, 
     const int orow = map_out_row(p, m);
     if (p.out2) {                                   // training forward: keep the pre-activation for the backward pass
         bf16* o2 = p.out2 + (size_t)orow * p.ldc2 + gcol;
-        if (full && ((((size_t)o2) & 15) == 0)) {
+        if (full && (NC % 16 == 0) && ((((size_t)o2) & 31) == 0)) {
+#pragma unroll
+            for (int i = 0; i < NC; i += 16) store16_bf16(o2 + i, v + i);
+        } else if (full && ((((size_t)o2) & 15) == 0)) {
 #pragma unroll
             for (int i = 0; i < NC; i += 8) {
                 uint4 u;
@@ -216,7 +258,10 @@ __device__ __forceinline__ void epilogue_row(const GemmParams& p, int g, int m, 
     if (p.dact_aux) {                               // backward: chain through the activation of the producing layer
         const bf16* ax = p.dact_aux + (size_t)m * p.ld_aux + gcol;
         float a[NC];
-        if (full && ((((size_t)ax) & 15) == 0)) {
+        if (full && (NC % 16 == 0) && ((((size_t)ax) & 31) == 0)) {
+#pragma unroll
+            for (int i = 0; i < NC; i += 16) load16_bf16(ax + i, a + i);
+        } else if (full && ((((size_t)ax) & 15) == 0)) {
 #pragma unroll
             for (int i = 0; i < NC; i += 8) {
                 const uint4 u = *reinterpret_cast<const uint4*>(ax + i);
@@ -238,7 +283,10 @@ __device__ __forceinline__ void epilogue_row(const GemmParams& p, int g, int m, 
     }
     if (p.out) {
         bf16* o = p.out + (size_t)orow * p.ldc + gcol;
-        if (full && ((((size_t)o) & 15) == 0)) {
+        if (full && (NC % 16 == 0) && ((((size_t)o) & 31) == 0)) {
+#pragma unroll
+            for (int i = 0; i < NC; i += 16) store16_bf16(o + i, v + i);
+        } else if (full && ((((size_t)o) & 15) == 0)) {
 #pragma unroll
             for (int i = 0; i < NC; i += 8) {
                 uint4 u;

@@ -176,7 +176,7 @@ class TrainEngine:
             d = round(dim // HEADS)
             inner = HEADS * d
             ldi = (inner + 7) // 8 * 8
-            ld3 = (3 * inner + 7) // 8 * 8
+            ld3 = (3 * inner + 15) // 16 * 16
             for i in range(depth):
                 b = f"stage{stage}.{i}."
                 W[b + "qkv.f"] = self.pcast(P[b + "attn.qkv.weight"], (1, 3 * inner, dim), (0, dim, 1))
@@ -253,7 +253,7 @@ class TrainEngine:
             ctx[f"pe{stage}"] = dict(xs=xs, y=y, bn=bnp)
             d = round(dim // HEADS)
             inner = HEADS * d
-            ldi, ld3 = (inner + 7) // 8 * 8, (3 * inner + 7) // 8 * 8
+            ldi, ld3 = (inner + 15) // 16 * 16, (3 * inner + 15) // 16 * 16
             for i in range(depth):
                 name = f"stage{stage}.{i}"
                 rr = rs.get(name) or [None, None]
