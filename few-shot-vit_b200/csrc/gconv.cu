@@ -10,6 +10,12 @@
 // across its 5 tiles.  Epilogue: GELU (+ pre-activation copy for training) or the chain-rule factor gelu'(aux) for dgrad.
 #include "common.cuh"
 
+#include <stdlib.h>
+#include <string.h>
+
+int sunb_launch_gconv_tc(const bf16* x, int ldx, const bf16* wg, bf16* y, int ldy, bf16* y2, int ldy2, const bf16* aux,
+                         int ldaux, int B, int act, int dact, cudaStream_t stream);
+
 namespace {
 
 constexpr int HW = 20, HP = 22, NPIX = 400, GC = 32;      // map side, padded side, pixels, channels per group
@@ -152,6 +158,16 @@ int sunb_gconv3x3(const void* x, int ldx, const void* wg, void* y, int ldy, void
     SUNB_REQUIRE(x && wg && y && B > 0, "gconv3x3: bad arguments");
     SUNB_REQUIRE(ldx % 8 == 0 && ldy % 2 == 0 && (((size_t)x) & 15) == 0 && (((size_t)wg) & 15) == 0,
                  "gconv3x3: operands must be 16-byte aligned");
+    // default: tcgen05 kernel (gconv_tc.cu); SUNB_GCONV=mma keeps the warp-MMA kernel below as a cross-check
+    static int use_mma = -1;
+    if (use_mma < 0) {
+        const char* e = getenv("SUNB_GCONV");
+        use_mma = (e && strcmp(e, "mma") == 0) ? 1 : 0;
+    }
+    if (!use_mma)
+        return sunb_launch_gconv_tc(reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<const bf16*>(wg), reinterpret_cast<bf16*>(y),
+                                    ldy, reinterpret_cast<bf16*>(y2), ldy2, reinterpret_cast<const bf16*>(aux), ldaux, B, act, dact,
+                                    reinterpret_cast<cudaStream_t>(stream));
     static bool configured = false;
     if (!configured) {
         SUNB_CHECK_CUDA(cudaFuncSetAttribute(gconv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));

@@ -68,6 +68,13 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
+// One lane of a converged warp.  Issuing TMA / MMA under elect.sync (instead of `lane == 0`) lets ptxas keep the whole
+// issue sequence in uniform registers; a plain divergent branch wraps every UTCHMMA / UBLKCP in a uniformisation loop.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -190,9 +197,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        // whole warp walks the schedule; one elected lane issues the TMA traffic
+        {
+            if (elect_one()) {
+                asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+                asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+            }
+            __syncwarp();
             const int nimg = p.a_mode ? BM / (p.bw * p.bh) : 1;
             const int tiles_x = p.a_mode ? p.W / p.bw : 1;
             const int spi = p.a_mode ? tiles_x * (p.H / p.bh) : 1;
@@ -200,10 +211,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             if (BSTAT && tile0 < total_tiles) {          // the whole weight operand of this CTA's (n-tile, group), once
                 const int n0 = (tile0 % n_tiles) * BN;
                 const int g = (tile0 / n_tiles) % p.groups;
-                mbar_expect_tx(b_full, nk * L::B_BYTES);
-                for (int kb = 0; kb < nk; ++kb)
-                    tma_load_2d(smem_base + kb * L::B_BYTES, &tmB, b_full, (kb % kpt) * BK,
-                                (g * p.taps + kb / kpt) * p.N + n0);
+                if (elect_one()) {
+                    mbar_expect_tx(b_full, nk * L::B_BYTES);
+                    for (int kb = 0; kb < nk; ++kb)
+                        tma_load_2d(smem_base + kb * L::B_BYTES, &tmB, b_full, (kb % kpt) * BK,
+                                    (g * p.taps + kb / kpt) * p.N + n0);
+                }
+                __syncwarp();
             }
             for (int tile = tile0; tile < total_tiles; tile += tstep) {
                 const int n0 = (tile % n_tiles) * BN;
@@ -215,23 +229,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                     mbar_wait(empty_bar(s), ph ^ 1);
                     const uint32_t a_dst = ring_base + s * RING_STRIDE;
                     const uint32_t b_dst = a_dst + L::A_BYTES;
-                    mbar_expect_tx(full_bar(s), BSTAT ? L::A_BYTES : L::STAGE_BYTES);
                     const int tap = kb / kpt, kc = kb % kpt;
-                    if (p.a_mode == 0) {
-                        tma_load_2d(a_dst, &tmA, full_bar(s), g * p.a_goff + kc * BK, m_tile * BM);
-                    } else {
-                        // one box: (64 channels, bw, bh, nimg images) of spatial block `blk`, shifted by the tap
-                        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-                        const int blk = m_tile % spi, img0 = (m_tile / spi) * nimg;
-                        tma_load_4d(a_dst, &tmA, full_bar(s), g * p.a_goff + kc * BK, (blk % tiles_x) * p.bw + dx,
-                                    (blk / tiles_x) * p.bh + dy, img0);
+                    if (elect_one()) {
+                        mbar_expect_tx(full_bar(s), BSTAT ? L::A_BYTES : L::STAGE_BYTES);
+                        if (p.a_mode == 0) {
+                            tma_load_2d(a_dst, &tmA, full_bar(s), g * p.a_goff + kc * BK, m_tile * BM);
+                        } else {
+                            // one box: (64 channels, bw, bh, nimg images) of spatial block `blk`, shifted by the tap
+                            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                            const int blk = m_tile % spi, img0 = (m_tile / spi) * nimg;
+                            tma_load_4d(a_dst, &tmA, full_bar(s), g * p.a_goff + kc * BK, (blk % tiles_x) * p.bw + dx,
+                                        (blk / tiles_x) * p.bh + dy, img0);
+                        }
+                        if (!BSTAT) tma_load_2d(b_dst, &tmB, full_bar(s), kc * BK, (g * p.taps + tap) * p.N + n0);
                     }
-                    if (!BSTAT) tma_load_2d(b_dst, &tmB, full_bar(s), kc * BK, (g * p.taps + tap) * p.N + n0);
+                    __syncwarp();
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             constexpr uint32_t idesc = make_idesc(BM, BN);
             uint32_t it = 0, lt = 0;
             if (BSTAT && tile0 < total_tiles) mbar_wait(b_full, 0);
@@ -248,12 +265,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                     const uint32_t a_addr = ring_base + s * RING_STRIDE;
                     const uint64_t a_desc = make_sw128_desc(a_addr);
                     const uint64_t b_desc = make_sw128_desc(BSTAT ? smem_base + kb * L::B_BYTES : a_addr + L::A_BYTES);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)   // advance 32 bytes (2 x 16-byte units) per UMMA_K = 16
-                        umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) ? 1u : 0u);
-                    umma_commit(empty_bar(s));            // frees the smem slot when these MMAs retire
+                        for (int k = 0; k < BK / 16; ++k)   // advance 32 bytes (2 x 16-byte units) per UMMA_K = 16
+                            umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                        umma_commit(empty_bar(s));            // frees the smem slot when these MMAs retire
+                    }
+                    __syncwarp();
                 }
-                umma_commit(acc_full(acc));               // accumulator complete
+                if (elect_one()) umma_commit(acc_full(acc));  // accumulator complete
+                __syncwarp();
             }
         }
     } else {

@@ -19,6 +19,12 @@ constexpr int NUM_THREADS = 192;
 constexpr int ATOM_BYTES = BKP * 128; // one [64 pixels x 64 channels] box
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// one lane of a converged warp (see gemm_tc.cu: keeps TMA / MMA issue in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
@@ -165,7 +171,7 @@ __global__ void __launch_bounds__(NUM_THREADS) wgrad_tc_kernel(const __grid_cons
 
     if (nk > 0) {
         if (warp == 0) {
-            if (lane == 0) {
+            {
                 const int dy = p.mode ? tap / 3 - 1 : 0, dx = p.mode ? tap % 3 - 1 : 0;
                 const int ca = g * p.a_goff + m_tile * BM;
                 const int cb = g * p.b_goff + n_tile * BN;
@@ -176,6 +182,7 @@ __global__ void __launch_bounds__(NUM_THREADS) wgrad_tc_kernel(const __grid_cons
                     mbar_wait(empty_bar(s), ph ^ 1);
                     const uint32_t a_dst = smem_base + s * L::STAGE_BYTES;
                     const uint32_t b_dst = a_dst + L::A_BYTES;
+                    if (elect_one()) {
                     mbar_expect_tx(full_bar(s), L::STAGE_BYTES);
                     if (p.mode == 0) {
 #pragma unroll
@@ -192,10 +199,12 @@ __global__ void __launch_bounds__(NUM_THREADS) wgrad_tc_kernel(const __grid_cons
                         for (int a = 0; a < BN / 64; ++a)
                             tma_load_4d(b_dst + a * ATOM_BYTES, &tmX, full_bar(s), cb + a * 64, x0 + dx, y0 + dy, img0);
                     }
+                    }
+                    __syncwarp();
                 }
             }
         } else if (warp == 1) {
-            if (lane == 0) {
+            {
                 constexpr uint32_t idesc = make_idesc_mn(BM, BN);
                 for (int i = 0; i < nk; ++i) {
                     const int s = i % STAGES;
@@ -204,13 +213,17 @@ __global__ void __launch_bounds__(NUM_THREADS) wgrad_tc_kernel(const __grid_cons
                     tc_fence_after();
                     const uint32_t a_addr = smem_base + s * L::STAGE_BYTES;
                     const uint32_t b_addr = a_addr + L::A_BYTES;
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BKP / 16; ++k)      // 16 pixel rows = 2048 bytes per UMMA_K step
-                        umma_bf16(tmem_base, make_mn_sw128_desc(a_addr + k * 2048), make_mn_sw128_desc(b_addr + k * 2048),
-                                  idesc, (i | k) ? 1u : 0u);
-                    umma_commit(empty_bar(s));
+                        for (int k = 0; k < BKP / 16; ++k)      // 16 pixel rows = 2048 bytes per UMMA_K step
+                            umma_bf16(tmem_base, make_mn_sw128_desc(a_addr + k * 2048), make_mn_sw128_desc(b_addr + k * 2048),
+                                      idesc, (i | k) ? 1u : 0u);
+                        umma_commit(empty_bar(s));
+                    }
+                    __syncwarp();
                 }
-                umma_commit(accum_bar);
+                if (elect_one()) umma_commit(accum_bar);
+                __syncwarp();
             }
         } else {
             const int q = warp & 3;

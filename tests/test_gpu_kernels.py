@@ -189,6 +189,36 @@ def test_layernorm_wrapper():
     assert max_err(ln(x), ref) < 1e-5
 
 
+def test_gelu_device_accuracy():
+    """The device GELU (tanh-form fit, common.cuh gelu_fast) and its training derivative (erf form) against exact erf
+    GELU in fp64: identity GEMM -> fp32 output, so the only error is the activation's own."""
+    x = torch.linspace(-12, 12, 64 * 4096, device=DEV).bfloat16().view(-1, 64).contiguous()
+    eye = torch.eye(64, device=DEV).bfloat16().contiguous()
+    out = run_gemm(x, eye, x.shape[0], 64, 64, act=2, out_f32=True)
+    xd = x.double()
+    ref = 0.5 * xd * (1 + torch.erf(xd * 0.70710678118654752))
+    err = (out.double() - ref).abs()
+    # absolute error bound everywhere, and relative to the bf16 rounding step of the value wherever |gelu| >= 0.05
+    assert err.max().item() < 1.5e-3, err.max().item()
+    big = ref.abs() >= 0.05
+    assert (err[big] / ref[big].abs()).max().item() < 2e-3          # bf16 half-ulp is 3.9e-3
+    assert err[xd.abs() <= 2].max().item() < 4e-4
+    # derivative through the chain-rule epilogue: out = 1 * gelu'(aux)
+    ones = torch.zeros_like(x); ones[:, 0] = 1
+    w1 = torch.zeros(64, 64, device=DEV).bfloat16(); w1[:, 0] = 1
+    d = N.GemmDesc()
+    d.M, d.N, d.K, d.taps, d.groups = x.shape[0], 64, 64, 1, 1
+    d.A, d.lda, d.Wt, d.ldw = ones.data_ptr(), 64, w1.data_ptr(), 64
+    d.dact_aux, d.ld_aux, d.dact = x.data_ptr(), 64, 2
+    g = torch.zeros(x.shape[0], 64, device=DEV)
+    d.out_f32, d.ldc_f32 = g.data_ptr(), 64
+    import ctypes as C
+    N.check(N.lib().sunb_gemm(C.byref(d), 0, N.current_stream()), "sunb_gemm")
+    torch.cuda.synchronize()
+    gref = 0.5 * (1 + torch.erf(xd * 0.70710678118654752)) + xd * torch.exp(-0.5 * xd * xd) * 0.3989422804014327
+    assert (g.double() - gref).abs().max().item() < 1e-5
+
+
 def test_gconv3x3_forward_and_dgrad():
     """Warp-MMA grouped conv (sunb_gconv3x3) vs torch conv2d(groups=8) forward, GELU, pre-activation copy and dgrad."""
     from sunb200 import packing
