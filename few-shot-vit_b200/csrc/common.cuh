@@ -351,5 +351,7 @@ struct WgradParams {
 
 // launchers (gemm_tc.cu / gemm_simt.cu)
 int sunb_launch_gemm_tc(const GemmParams& p, cudaStream_t stream);
+int sunb_conv_slab_supported(const GemmParams& p);
+int sunb_launch_conv_slab(const GemmParams& p, cudaStream_t stream);
 int sunb_launch_gemm_simt(const GemmParams& p, cudaStream_t stream);
 int sunb_launch_gemm(const GemmParams& p, cudaStream_t stream);   // dispatch (tcgen05 unless SUNB_GEMM=simt)

@@ -207,7 +207,7 @@ gconv3x3_tc_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__
         // the whole warp walks the pipeline; one elected lane issues (keeps the MMA sequence in uniform registers)
         {
             constexpr uint32_t idesc = make_idesc(128, GC);
-            const uint64_t a_desc0 = make_noswz_desc(PLANE_BYTES, 128);
+            const uint64_t a_desc0 = make_noswz_desc((dbg & 8) ? 2 * PLANE_BYTES : PLANE_BYTES, 128);
             const uint64_t b_desc0 = make_noswz_desc(512, 128);
             for (int k = 0; k < n_items; ++k) {
                 const int s = k % STAGES, ph = (k / STAGES) & 1, buf = k & 1, bph = (k >> 1) & 1;
@@ -229,7 +229,8 @@ gconv3x3_tc_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__
                             if ((dbg & 1) && tap > 0) break;
 #pragma unroll
                             for (int ks = 0; ks < 2; ++ks) {
-                                const uint32_t a_addr = a_tile + ks * 2 * PLANE_BYTES + ((tap / 3) * HP + tap % 3) * 16;
+                                uint32_t a_addr = a_tile + ks * 2 * PLANE_BYTES + ((tap / 3) * HP + tap % 3) * 16;
+                                if (dbg & 8) a_addr = a_tile + tap * 128;      // timing experiment: 128-byte aligned core matrices
                                 const uint32_t b_addr = b_grp + tap * W_TAP_BYTES + ks * 2 * 512;
                                 umma_bf16(d, a_desc0 | (uint64_t)((a_addr >> 4) & 0x3FFF), b_desc0 | (uint64_t)((b_addr >> 4) & 0x3FFF),
                                           idesc, (tap | ks) != 0);

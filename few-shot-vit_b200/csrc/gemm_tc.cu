@@ -623,6 +623,11 @@ int launch_bn(const GemmParams& p, const CUtensorMap& tmA, const CUtensorMap& tm
 
 }  // namespace
 
+int sunb_encode_tensor_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                           const cuuint32_t* box) {
+    return encode_map(map, base, rank, dims, strides_bytes, box);
+}
+
 int sunb_gemm_tc_pick_bn(const GemmParams& p) {
     if (p.N <= 64) return 64;
     if (p.N <= 128) return 128;
@@ -638,6 +643,7 @@ int sunb_launch_gemm_tc(const GemmParams& p, cudaStream_t stream) {
     SUNB_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm_tc: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
     SUNB_REQUIRE((p.lda % 8) == 0 && (p.ldw % 8) == 0, "gemm_tc: lda/ldw must be multiples of 8 elements (16 B)");
     SUNB_REQUIRE((((size_t)p.A) & 15) == 0 && (((size_t)p.Wt) & 15) == 0, "gemm_tc: operands must be 16-byte aligned");
+    if (sunb_conv_slab_supported(p)) return sunb_launch_conv_slab(p, stream);     // dense 3x3: resident haloed slab (conv_slab.cu)
     const int BN = sunb_gemm_tc_pick_bn(p);
     CUtensorMap tmA, tmB;
     if (p.a_mode == 0) {
