@@ -28,7 +28,7 @@ int sunb_encode_tensor_map(CUtensorMap* map, const void* base, int rank, const c
 namespace {
 
 constexpr int THREADS = 32 * 11;
-constexpr int SLAB_STAGES = 2;
+constexpr int ATOM_SLOTS = 3;          // ring of 64-channel slab atoms (an atom is released as soon as its 9 taps are issued)
 constexpr int SMEM_LIMIT = 232448;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -135,23 +135,22 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int KC = p.K / 64;
-    const uint32_t slab_bytes = (uint32_t)g.atom_bytes * KC;
     constexpr uint32_t B_BYTES = BN * 128;
-    const uint32_t bring = base + SLAB_STAGES * slab_bytes;
+    const uint32_t bring = base + ATOM_SLOTS * g.atom_bytes;
     const uint32_t bars = bring + g.b_stages * B_BYTES;
-    auto slab_full = [&](int s) { return bars + 8u * s; };
-    auto slab_empty = [&](int s) { return bars + 8u * (2 + s); };
-    auto acc_full = [&](int a) { return bars + 8u * (4 + a); };
-    auto acc_empty = [&](int a) { return bars + 8u * (6 + a); };
-    auto b_full = [&](int s) { return bars + 8u * (8 + s); };
-    auto b_empty = [&](int s) { return bars + 8u * (16 + s); };
-    const uint32_t tmem_slot_addr = bars + 8u * 24;
+    auto atom_full = [&](int s) { return bars + 8u * s; };
+    auto atom_empty = [&](int s) { return bars + 8u * (3 + s); };
+    auto acc_full = [&](int a) { return bars + 8u * (6 + a); };
+    auto acc_empty = [&](int a) { return bars + 8u * (8 + a); };
+    auto b_full = [&](int s) { return bars + 8u * (10 + s); };
+    auto b_empty = [&](int s) { return bars + 8u * (18 + s); };
+    const uint32_t tmem_slot_addr = bars + 8u * 26;
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot_addr - smem_u32(smem_raw)));
     constexpr int TMEM_COLS = 4 * BN;      // 2 buffers x 2 halves x BN (256 or 512: powers of two)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int s = 0; s < SLAB_STAGES; ++s) { mbar_init(slab_full(s), 1); mbar_init(slab_empty(s), 1); }
+        for (int s = 0; s < ATOM_SLOTS; ++s) { mbar_init(atom_full(s), 1); mbar_init(atom_empty(s), 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(acc_full(a), 1); mbar_init(acc_empty(a), 8); }
         for (int s = 0; s < g.b_stages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -170,17 +169,18 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ================================================================ slab producer
         if (elect_one()) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         __syncwarp();
-        int lt = 0;
-        for (int tile = blockIdx.x; tile < g.tiles; tile += gridDim.x, ++lt) {
-            const int s = lt % SLAB_STAGES, ph = (lt / SLAB_STAGES) & 1;
+        uint32_t ai = 0;
+        for (int tile = blockIdx.x; tile < g.tiles; tile += gridDim.x) {
             const int img = tile / g.bands, y0 = (tile % g.bands) * g.RB;
-            mbar_wait(slab_empty(s), ph ^ 1);
-            if (elect_one()) {
-                mbar_expect_tx(slab_full(s), slab_bytes);
-                for (int kc = 0; kc < KC; ++kc)
-                    tma_load_4d(base + s * slab_bytes + kc * g.atom_bytes, &tmA, slab_full(s), kc * 64, -1, y0 - 1, img);
+            for (int kc = 0; kc < KC; ++kc, ++ai) {
+                const int s = ai % ATOM_SLOTS, ph = (ai / ATOM_SLOTS) & 1;
+                mbar_wait(atom_empty(s), ph ^ 1);
+                if (elect_one()) {
+                    mbar_expect_tx(atom_full(s), g.atom_bytes);
+                    tma_load_4d(base + s * g.atom_bytes, &tmA, atom_full(s), kc * 64, -1, y0 - 1, img);
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else if (warp == 2) {
         // ================================================================ weight producer: (tap, 64-channel) blocks
@@ -193,7 +193,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 mbar_wait(b_empty(s), ph ^ 1);
                 if (elect_one()) {
                     mbar_expect_tx(b_full(s), B_BYTES);
-                    tma_load_2d(bring + s * B_BYTES, &tmB, b_full(s), (blk % KC) * 64, (blk / KC) * p.N);
+                    tma_load_2d(bring + s * B_BYTES, &tmB, b_full(s), (blk / 9) * 64, (blk % 9) * p.N);    // (kc, tap) order
                 }
                 __syncwarp();
             }
@@ -201,39 +201,40 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else if (warp == 1) {
         // ================================================================ MMA issuer
         constexpr uint32_t idesc = make_idesc(128, BN);
-        uint32_t it = 0;
+        uint32_t it = 0, ai = 0;
         int lt = 0;
         for (int tile = blockIdx.x; tile < g.tiles; tile += gridDim.x, ++lt) {
-            const int s = lt % SLAB_STAGES, ph = (lt / SLAB_STAGES) & 1;
             const int acc = lt & 1, aph = (lt >> 1) & 1;
             mbar_wait(acc_empty(acc), aph ^ 1);
-            mbar_wait(slab_full(s), ph);
             tc_fence_after();
-            const uint32_t slab = base + s * slab_bytes;
             const uint32_t d0 = tmem_base + acc * 2 * BN;
-            for (int blk = 0; blk < nblk; ++blk, ++it) {
-                const int bs = it % g.b_stages, bph = (it / g.b_stages) & 1;
-                const int tap = blk / KC, kc = blk - tap * KC;
-                mbar_wait(b_full(bs), bph);
+            for (int kc = 0; kc < KC; ++kc, ++ai) {
+                const int s = ai % ATOM_SLOTS, ph = (ai / ATOM_SLOTS) & 1;
+                mbar_wait(atom_full(s), ph);
                 tc_fence_after();
-                const uint32_t a_addr = slab + kc * g.atom_bytes + ((tap / 3) * g.P + tap % 3) * 128;
-                const uint32_t b_addr = bring + bs * B_BYTES;
-                if (elect_one()) {
+                const uint32_t atom = base + s * g.atom_bytes;
+                for (int tap = 0; tap < 9; ++tap, ++it) {
+                    const int bs = it % g.b_stages, bph = (it / g.b_stages) & 1;
+                    mbar_wait(b_full(bs), bph);
+                    tc_fence_after();
+                    const uint32_t a_addr = atom + ((tap / 3) * g.P + tap % 3) * 128;
+                    const uint32_t b_addr = bring + bs * B_BYTES;
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
+                        for (int k = 0; k < 4; ++k) {
 #pragma unroll
-                        for (int half = 0; half < 2; ++half)
-                            umma_bf16(d0 + half * BN, make_sw128_desc(a_addr + half * 128 * 128 + k * 32),
-                                      make_sw128_desc(b_addr + k * 32), idesc, (blk | k) ? 1u : 0u);
+                            for (int half = 0; half < 2; ++half)
+                                umma_bf16(d0 + half * BN, make_sw128_desc(a_addr + half * 128 * 128 + k * 32),
+                                          make_sw128_desc(b_addr + k * 32), idesc, (kc | tap | k) ? 1u : 0u);
+                        }
+                        umma_commit(b_empty(bs));
                     }
-                    umma_commit(b_empty(bs));
+                    __syncwarp();
                 }
+                if (elect_one()) umma_commit(atom_empty(s));       // the atom's slot refills while the next atom / tile computes
                 __syncwarp();
             }
-            if (elect_one()) {
-                umma_commit(slab_empty(s));
-                umma_commit(acc_full(acc));
-            }
+            if (elect_one()) umma_commit(acc_full(acc));
             __syncwarp();
         }
     } else {
@@ -322,10 +323,9 @@ int sunb_launch_conv_slab(const GemmParams& p, cudaStream_t stream) {
     g.bands = (p.H + g.RB - 1) / g.RB;
     const int B = p.M / (p.H * p.W);
     g.tiles = B * g.bands;
-    const int KC = p.K / 64;
     const int BN = p.N;
     // the junk rows of the second accumulator read up to 2P+2 rows past the 256-row window: keep that inside the allocation
-    const int slab_total = SLAB_STAGES * g.atom_bytes * KC;
+    const int slab_total = ATOM_SLOTS * g.atom_bytes;
     int b_stages = (SMEM_LIMIT - 1024 - 256 - slab_total) / (BN * 128);
     if (b_stages > 8) b_stages = 8;
     SUNB_REQUIRE(b_stages >= 2, "conv_slab: slab of %d bytes leaves no room for the weight ring", slab_total);
