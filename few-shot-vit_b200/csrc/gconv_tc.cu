@@ -30,8 +30,12 @@ constexpr int W_TAP_BYTES = GC * GC * 2;            // 2 KB: [4 k chunks][32 n][
 constexpr int W_BYTES = 2 * 9 * W_TAP_BYTES;        // 36,864 B
 constexpr int LAST_ROW = (HW - 1) * HP + HW - 1;    // 437: last valid output raster position
 constexpr int M_TILES = 4;                          // 4 x 128 raster rows cover 0..437
-constexpr int LOAD_WARPS = 4, EPI_WARPS = 8;
-constexpr int THREADS = 32 * (1 + LOAD_WARPS + EPI_WARPS);   // 416
+#ifndef SUNB_GCONV_EPI_WARPS
+#define SUNB_GCONV_EPI_WARPS 8
+#endif
+constexpr int LOAD_WARPS = 4, EPI_WARPS = SUNB_GCONV_EPI_WARPS;   // 8 (16 = split tiles by parity: measured slower, 80-register cap spills)
+constexpr int TSTEP = EPI_WARPS / 8;
+constexpr int THREADS = 32 * (1 + LOAD_WARPS + EPI_WARPS);
 constexpr int BAR_BYTES = 256;
 constexpr int SMEM_BYTES = STAGES * SLAB_BYTES + W_BYTES + BAR_BYTES + 128;   // 223,104 B
 constexpr int TMEM_COLS = 512;                      // 2 buffers x 2 groups x 4 tiles x 32 columns
@@ -187,7 +191,7 @@ gconv3x3_tc_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__
         for (int b = 0; b < 2; ++b)
             for (int g2 = 0; g2 < 2; ++g2) {
                 mbar_init(acc_full(b, g2), 1);
-                mbar_init(acc_empty(b, g2), 4);
+                mbar_init(acc_empty(b, g2), EPI_WARPS / 2);
             }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -277,23 +281,30 @@ gconv3x3_tc_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__
     } else {
         // ================================================================ epilogue: 2 groups x 4 TMEM lane quadrants
         const int e = warp - 1 - LOAD_WARPS;
-        const int g2 = e >> 2, q = warp & 3;             // a warp may only touch TMEM lanes 32 * (warp % 4) ...
+        const int g2 = (e >> 2) & 1, q = warp & 3;       // a warp may only touch TMEM lanes 32 * (warp % 4) ...
+        const int t0 = e >> 3;                           // first tile of this warp (tiles t0, t0 + TSTEP, ...)
         const int ch = (gp * 2 + g2) * GC;
+        // the last tile this quadrant has valid rows in, and the last one THIS warp drains
+        const int last_tile = min(M_TILES - 1, (LAST_ROW - q * 32) / 128);
+        const int my_last = last_tile - ((last_tile - t0) % TSTEP + TSTEP) % TSTEP;
         for (int k = 0; k < n_items; ++k) {
             const int buf = k & 1, bph = (k >> 1) & 1;
             const int img = img0 + k * img_step;
             mbar_wait(acc_full(buf, g2), bph);
             tc_fence_after();
-            // the last tile this quadrant has valid rows in
-            const int last_tile = (LAST_ROW - q * 32) >= 0 ? min(M_TILES - 1, (LAST_ROW - q * 32) / 128) : -1;
+            if (my_last < t0) {                          // no tile for this warp in this quadrant: just hand the buffer back
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty(buf, g2));
+            }
 #pragma unroll 1
-            for (int tile = 0; tile <= last_tile; ++tile) {
+            for (int tile = t0; tile <= last_tile; tile += TSTEP) {
                 const int o = tile * 128 + q * 32 + lane;
                 const int oy = o / HP, ox = o - oy * HP;
                 const bool valid = (oy < HW) && (ox < HW);
                 float v[32];
                 tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256 + g2 * 128 + tile * GC, v);
-                if (tile == last_tile) {                 // accumulators are in registers: hand the TMEM buffer back
+                if (tile == my_last) {                   // accumulators are in registers: hand the TMEM buffer back
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(acc_empty(buf, g2));

@@ -17,7 +17,16 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;                      // 64 bf16 = one 128-byte swizzle row
 constexpr int NUM_EPI_WARPS = 8;
-constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;   // TMA warp, MMA warp, 8 epilogue warps
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;   // TMA warp, MMA warp, 8 epilogue warps (2-CTA variant)
+#ifndef SUNB_EPI_WARPS1
+#define SUNB_EPI_WARPS1 16
+#endif
+// 1-CTA kernel: the accumulator drain (tcgen05.ld -> bias/GELU/residual -> store) is latency bound with two warps per SM
+// sub-partition; four per TMEM lane quarter measured +7 % on the whole eval forward (8: 11.15 ms, 12: 10.74, 16: 10.39).
+// Prefetching the next chunk's TMEM load / residual inside a warp measured slower (register pressure) and was dropped.
+constexpr int EPI_WARPS1 = SUNB_EPI_WARPS1;
+constexpr int THREADS1 = 64 + 32 * EPI_WARPS1;
+constexpr int CSTEP1 = EPI_WARPS1 / 4;
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -142,7 +151,7 @@ struct SmemLayout {
 // BSTAT (weight-stationary): a CTA keeps one (n-tile, group) for its whole life, loads that tile's complete weight
 // operand (all taps x K blocks) into shared memory once, and streams only activation tiles through the ring.
 template <int BN, bool BSTAT>
-__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(THREADS1, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                  const __grid_constant__ CUtensorMap tmB,
                                                                  const GemmParams p, const int n_tiles,
                                                                  const int total_tiles, const int a_stages) {
@@ -181,7 +190,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(acc_full(a), 1);
-            mbar_init(acc_empty(a), NUM_EPI_WARPS);
+            mbar_init(acc_empty(a), EPI_WARPS1);
         }
         mbar_init(b_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -280,7 +289,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     } else {
         // epilogue warps 2..9: TMEM lanes [32*(warp%4), +32); the two warps of a lane quarter split the columns
         const int q = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int half = (warp - 2) >> 2;      // which share of the column chunks (0 .. CSTEP1-1)
         const int r = q * 32 + lane;
         uint32_t lt = 0;
         for (int tile = tile0; tile < total_tiles; tile += tstep, ++lt) {
@@ -293,7 +302,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             // sub-boxes past the last image map to m >= M and are dropped by the epilogue
             const int mm = p.a_mode ? conv_tile_row_to_pixel(p, m_tile, r) : m_tile * BM + r;
 #pragma unroll 1
-            for (int c = half; c < BN / 32; c += 2) {
+            for (int c = half; c < BN / 32; c += CSTEP1) {
                 if (n0 + c * 32 >= p.N) break;            // warp-uniform
                 float v[32];
                 tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
@@ -304,7 +313,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             if (lane == 0) mbar_arrive(acc_empty(acc));
         }
     }
-
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -612,10 +620,10 @@ int launch_bn(const GemmParams& p, const CUtensorMap& tmA, const CUtensorMap& tm
         int a_stages = (int)((L::TILE_BYTES - b_bytes) / L::A_BYTES);
         if (a_stages > 10) a_stages = 10;
         const int grid = (sms / slots) * slots;
-        gemm_tc_kernel<BN, true><<<grid, NUM_THREADS, L::TOTAL, stream>>>(tmA, tmB, p, n_tiles, (int)total, a_stages);
+        gemm_tc_kernel<BN, true><<<grid, THREADS1, L::TOTAL, stream>>>(tmA, tmB, p, n_tiles, (int)total, a_stages);
     } else {
         const int grid = (int)(total < sms ? total : sms);     // persistent: one CTA per SM
-        gemm_tc_kernel<BN, false><<<grid, NUM_THREADS, L::TOTAL, stream>>>(tmA, tmB, p, n_tiles, (int)total, L::STAGES);
+        gemm_tc_kernel<BN, false><<<grid, THREADS1, L::TOTAL, stream>>>(tmA, tmB, p, n_tiles, (int)total, L::STAGES);
     }
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsunb200.so")
+# SUNB200_LIB: developer override to A/B two builds of the same ABI on one box
+LIB_PATH = os.environ.get("SUNB200_LIB") or os.path.join(_HERE, "libsunb200.so")
 
 vp = C.c_void_p
 fp = C.c_void_p      # float* passed as raw address
