@@ -9,7 +9,7 @@
 int sunb_launch_stem_in(const float* x, const float* w1, const float* b1, const float* wd, const float* bd, bf16* a1,
                         bf16* idn, int B, int lrelu, cudaStream_t stream);
 int sunb_launch_pool_pos(const bf16* in, const float* pos, bf16* out, int B, int H, int W, int C, cudaStream_t stream);
-int sunb_launch_attention(const bf16* qkv, bf16* out, int B, int S, int d, int heads, int ld_qkv, int ld_out,
+int sunb_launch_attention(const bf16* qkv, bf16* out, int B, int S, int d, int ds, int heads, int ld_qkv, int ld_out,
                           cudaStream_t stream);
 int sunb_launch_final_norm_pool(const bf16* x, const float* scale, const float* shift, float* dense, bf16* dense_bf16,
                                 float* pooled, bf16* pooled_bf16, int B, int T, int C, cudaStream_t stream);
@@ -72,13 +72,13 @@ Workspace carve(void* base, int B) {
     w.h2 = take(b * 400 * 256);
     w.s1d = take(b * 400 * 128);
     w.t2 = take(b * 100 * 256);
-    w.qkv2 = take(b * 100 * 768);
-    w.ao2 = take(b * 100 * 256);
+    w.qkv2 = take(b * 100 * 864);      // 3 x 6 heads x 48 (d = 42 padded)
+    w.ao2 = take(b * 100 * 288);
     w.hid2 = take(b * 100 * 1024);
     w.t2d = take(b * 100 * 256);
     w.t3 = take(b * 25 * 512);
-    w.qkv3 = take(b * 25 * 1536);
-    w.ao3 = take(b * 25 * 512);
+    w.qkv3 = take(b * 25 * 1728);      // 3 x 6 heads x 96 (d = 85 padded)
+    w.ao3 = take(b * 25 * 576);
     w.hid3 = take(b * 25 * 2048);
     w.bytes = off;
     return w;
@@ -105,14 +105,15 @@ int tap_copy(void* dst, const bf16* src, size_t elems, cudaStream_t s) {
 
 // stage-2/3 Block (visformer.py:259-263 with attention enabled); x is updated in place, last block may store
 // its output 2x2 space-to-depth for the following PatchEmbed.
-int attn_block(const SunbAttnBlockW& w, bf16* x, int B, int S, int C, int d, bf16* qkv, int ld_qkv, bf16* ao, int ld_ao,
+int attn_block(const SunbAttnBlockW& w, bf16* x, int B, int S, int C, int d, int dp, bf16* qkv, bf16* ao,
                bf16* hid, bf16* s2d_out, int side, cudaStream_t st) {
-    const int M = B * S, inner = HEADS * d;
-    GemmParams p = base_gemm(M, 3 * inner, C, x, C, w.wqkv, C, qkv, ld_qkv);
+    // heads are padded to dp channels (zero weights): qkv rows are [3][6][dp], attention output rows [6][dp]
+    const int M = B * S, inner = HEADS * dp;
+    GemmParams p = base_gemm(M, 3 * inner, C, x, C, w.wqkv, C, qkv, 3 * inner);
     p.bias = w.bqkv;
     SUNB_TRY(sunb_launch_gemm(p, st));
-    SUNB_TRY(sunb_launch_attention(qkv, ao, B, S, d, HEADS, ld_qkv, ld_ao, st));
-    p = base_gemm(M, C, inner, ao, ld_ao, w.wproj, ld_ao, x, C);
+    SUNB_TRY(sunb_launch_attention(qkv, ao, B, S, d, dp, HEADS, 3 * inner, inner, st));
+    p = base_gemm(M, C, inner, ao, inner, w.wproj, inner, x, C);
     p.resid = x; p.ldr = C;
     SUNB_TRY(sunb_launch_gemm(p, st));
     p = base_gemm(M, 4 * C, C, x, C, w.w1, C, hid, 4 * C);
@@ -226,7 +227,7 @@ int sunb_encoder_forward(const SunbEncoderWeights* w, const float* x, int B, voi
     SUNB_TRY(tap_copy(tp.patch_embed2, ws.t2, (size_t)B * 100 * 256, st));
     for (int i = 0; i < 2; ++i) {
         const bool last = (i == 1);
-        SUNB_TRY(attn_block(w->s2[i], ws.t2, B, 100, 256, 42, ws.qkv2, 768, ws.ao2, 256, ws.hid2,
+        SUNB_TRY(attn_block(w->s2[i], ws.t2, B, 100, 256, 42, 48, ws.qkv2, ws.ao2, ws.hid2,
                             last ? ws.t2d : nullptr, 10, st));
         if (tp.stage2[i]) {
             if (last) {   // t2 still holds the pre-MLP stream: redo the last GEMM identity-mapped for the tap
@@ -248,7 +249,7 @@ int sunb_encoder_forward(const SunbEncoderWeights* w, const float* x, int B, voi
     }
     SUNB_TRY(tap_copy(tp.patch_embed3, ws.t3, (size_t)B * 25 * 512, st));
     for (int i = 0; i < 3; ++i) {
-        SUNB_TRY(attn_block(w->s3[i], ws.t3, B, 25, 512, 85, ws.qkv3, 1536, ws.ao3, 512, ws.hid3, nullptr, 5, st));
+        SUNB_TRY(attn_block(w->s3[i], ws.t3, B, 25, 512, 85, 96, ws.qkv3, ws.ao3, ws.hid3, nullptr, 5, st));
         SUNB_TRY(tap_copy(tp.stage3[i], ws.t3, (size_t)B * 25 * 512, st));
     }
 
@@ -258,9 +259,10 @@ int sunb_encoder_forward(const SunbEncoderWeights* w, const float* x, int B, voi
     return SUNB_OK;
 }
 
-int sunb_attention(const void* qkv, void* out, int B, int S, int d, int heads, int ld_qkv, int ld_out, void* stream) {
+int sunb_attention(const void* qkv, void* out, int B, int S, int d, int d_stride, int heads, int ld_qkv, int ld_out,
+                   void* stream) {
     SUNB_REQUIRE(qkv && out, "attention: null argument");
-    return sunb_launch_attention(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B, S, d, heads, ld_qkv,
+    return sunb_launch_attention(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B, S, d, d_stride, heads, ld_qkv,
                                  ld_out, reinterpret_cast<cudaStream_t>(stream));
 }
 

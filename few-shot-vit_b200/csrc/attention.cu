@@ -1,6 +1,9 @@
 // Multi-head self-attention core (reference: test_phase/models/visformer.py:183-190).
-//   qkv : bf16 [B*S, ld_qkv], channel c = x*(heads*d) + y*d + z   (x in {q,k,v}, y head, z in [0,d))
-//   out : bf16 [B*S, ld_out], channel y*d + z
+//   qkv : bf16 [B*S, ld_qkv], channel c = x*(heads*ds) + y*ds + z   (x in {q,k,v}, y head, z in [0,d), ds = head stride >= d)
+//   out : bf16 [B*S, ld_out], channel y*ds + z
+// ds == d is the reference's packed layout (visformer.py:186).  The eval engine pads every head to ds = 48 / 96 channels
+// (zero weight rows -> the pad channels of q, k, v are exact zeros): every (token, head) segment then starts on a 16-byte
+// boundary, the tiles are staged with 16-byte cp.async and the output (pad channels = 0) is written as bf16 pairs.
 //   P = softmax(q k^T * d^-0.5), O = P v.
 // Warp-level tensor-core kernel: the whole sequence (S = 100 or 25 tokens) of one (image, head) problem sits in
 // shared memory (zero-padded to MMA shapes: S -> 112 / 32 keys, d 42 -> 48, 85 -> 96); each warp owns 16 query rows,
@@ -36,23 +39,33 @@ struct AttnCfg {
 
 template <int S_PAD, int D_PAD, int PAIRS>
 __global__ void __launch_bounds__(AttnCfg<S_PAD, D_PAD, PAIRS>::THREADS)
-attention_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int n_pairs, int S, int d, int heads,
+attention_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int n_pairs, int S, int d, int ds, int heads,
                      int ld_qkv, int ld_out, float scale_log2e) {
     using Cfg = AttnCfg<S_PAD, D_PAD, PAIRS>;
     constexpr int QK_LD = Cfg::QK_LD;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     bf16* smem = reinterpret_cast<bf16*>(smem_raw);
-    const int inner = heads * d;
+    const int inner = heads * ds;
 
     // ---- stage Q, K, V (all row-major [token][d]) for the PAIRS problems of this CTA.  Padding must read as zero:
     //      clear the tiles, then fill the valid part -- with 4-byte cp.async when every row segment is 4-byte aligned
     //      (d even: stage 2), else with scalar loads (d = 85: odd heads start on a 2-byte boundary).
-    {
+    // fast path: head segments are 16-byte aligned and padded with zeros up to ds (a multiple of 8 channels)
+    const bool vec16 = ((ds & 7) == 0) && ((ld_qkv & 7) == 0) && ((((size_t)qkv) & 15) == 0);
+    const int ncopy = ds < D_PAD ? ds : D_PAD;        // channels taken from global memory per row (fast path)
+    if (!vec16 || ncopy < D_PAD) {                      // something in the tiles is not overwritten: clear everything
         uint4* z = reinterpret_cast<uint4*>(smem_raw);
         for (int i = threadIdx.x; i < (int)(Cfg::SMEM / 16); i += Cfg::THREADS) z[i] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+    } else {                                            // only the key / value rows past the sequence (P = 0 there, V must be finite)
+        constexpr int RCH = QK_LD / 8;                  // 16-byte chunks per row
+        for (int i = threadIdx.x; i < PAIRS * 2 * (S_PAD - S) * RCH; i += Cfg::THREADS) {
+            const int ch = i % RCH, row = (i / RCH) % (S_PAD - S), kv = (i / (RCH * (S_PAD - S))) % 2, pl = i / (2 * RCH * (S_PAD - S));
+            *reinterpret_cast<uint4*>(smem + pl * Cfg::PAIR_ELEMS + (1 + kv) * S_PAD * QK_LD + (S + row) * QK_LD + ch * 8) =
+                make_uint4(0, 0, 0, 0);
+        }
     }
-    __syncthreads();
-    const bool vec2 = ((d & 1) == 0) && ((ld_qkv & 1) == 0);
+    const bool vec2 = ((d & 1) == 0) && ((ds & 1) == 0) && ((ld_qkv & 1) == 0);
     for (int pl = 0; pl < PAIRS; ++pl) {
         const int pair = blockIdx.x * PAIRS + pl;
         if (pair >= n_pairs) break;
@@ -60,8 +73,20 @@ attention_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int n
         bf16* sk = sq + S_PAD * QK_LD;
         bf16* sv = sk + S_PAD * QK_LD;
         const int img = pair / heads, head = pair % heads;
-        const bf16* base = qkv + (size_t)img * S * ld_qkv + head * d;
-        if (vec2) {
+        const bf16* base = qkv + (size_t)img * S * ld_qkv + head * ds;
+        if (vec16) {
+            const int cpr = ncopy >> 3;
+            for (int i = threadIdx.x; i < S * cpr; i += Cfg::THREADS) {
+                const int t = i / cpr, z = (i % cpr) * 8;
+                const bf16* row = base + (size_t)t * ld_qkv + z;
+                const uint32_t dq = (uint32_t)__cvta_generic_to_shared(sq + t * QK_LD + z);
+                const uint32_t dk = (uint32_t)__cvta_generic_to_shared(sk + t * QK_LD + z);
+                const uint32_t dv = (uint32_t)__cvta_generic_to_shared(sv + t * QK_LD + z);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dq), "l"(row) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dk), "l"(row + inner) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dv), "l"(row + 2 * inner) : "memory");
+            }
+        } else if (vec2) {
             const int dh = d >> 1;
             for (int i = threadIdx.x; i < S * dh; i += Cfg::THREADS) {
                 const int t = i / dh, z = (i % dh) * 2;
@@ -172,8 +197,20 @@ attention_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int n
     const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
     const int img = pair / heads, head = pair % heads;
     const int row0 = r0 + g, row1 = r0 + g + 8;
-    bf16* o0 = out + (size_t)(img * S + row0) * ld_out + head * d;
-    bf16* o1 = out + (size_t)(img * S + row1) * ld_out + head * d;
+    bf16* o0 = out + (size_t)(img * S + row0) * ld_out + head * ds;
+    bf16* o1 = out + (size_t)(img * S + row1) * ld_out + head * ds;
+    if (vec16 && ((ld_out & 1) == 0) && ((((size_t)out) & 3) == 0)) {
+        // padded layout: write all min(ds, D_PAD) channels (the pad channels are exact zeros) as bf16 pairs
+#pragma unroll
+        for (int j = 0; j < OT; ++j) {
+            const int c = j * 8 + t * 2;
+            if (c < ncopy) {
+                if (row0 < S) *reinterpret_cast<__nv_bfloat162*>(o0 + c) = __floats2bfloat162_rn(oc[j][0] * inv0, oc[j][1] * inv0);
+                if (row1 < S) *reinterpret_cast<__nv_bfloat162*>(o1 + c) = __floats2bfloat162_rn(oc[j][2] * inv1, oc[j][3] * inv1);
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int j = 0; j < OT; ++j) {
         const int c = j * 8 + t * 2;
@@ -189,7 +226,7 @@ attention_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int n
 }
 
 template <int S_PAD, int D_PAD, int PAIRS>
-int launch_cfg(const bf16* qkv, bf16* out, int n_pairs, int S, int d, int heads, int ld_qkv, int ld_out, float scale,
+int launch_cfg(const bf16* qkv, bf16* out, int n_pairs, int S, int d, int ds, int heads, int ld_qkv, int ld_out, float scale,
                cudaStream_t stream) {
     using Cfg = AttnCfg<S_PAD, D_PAD, PAIRS>;
     static bool configured = false;
@@ -200,22 +237,23 @@ int launch_cfg(const bf16* qkv, bf16* out, int n_pairs, int S, int d, int heads,
     }
     const int blocks = (n_pairs + PAIRS - 1) / PAIRS;
     attention_mma_kernel<S_PAD, D_PAD, PAIRS><<<blocks, Cfg::THREADS, Cfg::SMEM, stream>>>(
-        qkv, out, n_pairs, S, d, heads, ld_qkv, ld_out, scale * 1.4426950408889634f);
+        qkv, out, n_pairs, S, d, ds, heads, ld_qkv, ld_out, scale * 1.4426950408889634f);
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
 }
 
 }  // namespace
 
-int sunb_launch_attention(const bf16* qkv, bf16* out, int B, int S, int d, int heads, int ld_qkv, int ld_out,
+int sunb_launch_attention(const bf16* qkv, bf16* out, int B, int S, int d, int ds, int heads, int ld_qkv, int ld_out,
                           cudaStream_t stream) {
     SUNB_REQUIRE(B > 0 && heads > 0, "attention: empty problem");
+    SUNB_REQUIRE(ds >= d && ld_qkv >= 3 * heads * ds && ld_out >= heads * ds, "attention: head stride %d / row strides too small", ds);
     const float scale = 1.0f / sqrtf((float)d);
     const int n_pairs = B * heads;
-    if (S <= 32 && d <= 96 && d > 48) return launch_cfg<32, 96, 4>(qkv, out, n_pairs, S, d, heads, ld_qkv, ld_out, scale, stream);
-    if (S <= 32 && d <= 48) return launch_cfg<32, 48, 4>(qkv, out, n_pairs, S, d, heads, ld_qkv, ld_out, scale, stream);
-    if (S <= 112 && d <= 48) return launch_cfg<112, 48, 1>(qkv, out, n_pairs, S, d, heads, ld_qkv, ld_out, scale, stream);
-    if (S <= 112 && d <= 96) return launch_cfg<112, 96, 1>(qkv, out, n_pairs, S, d, heads, ld_qkv, ld_out, scale, stream);
+    if (S <= 32 && d <= 96 && d > 48) return launch_cfg<32, 96, 4>(qkv, out, n_pairs, S, d, ds, heads, ld_qkv, ld_out, scale, stream);
+    if (S <= 32 && d <= 48) return launch_cfg<32, 48, 4>(qkv, out, n_pairs, S, d, ds, heads, ld_qkv, ld_out, scale, stream);
+    if (S <= 112 && d <= 48) return launch_cfg<112, 48, 1>(qkv, out, n_pairs, S, d, ds, heads, ld_qkv, ld_out, scale, stream);
+    if (S <= 112 && d <= 96) return launch_cfg<112, 96, 1>(qkv, out, n_pairs, S, d, ds, heads, ld_qkv, ld_out, scale, stream);
     sunb_set_error("attention: unsupported shape S=%d d=%d (supported: S <= 112, d <= 96)", S, d);
     return SUNB_ERR_ARG;
 }

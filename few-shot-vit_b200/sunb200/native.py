@@ -84,7 +84,7 @@ SIGNATURES = {
     "sunb_encoder_workspace_bytes": (C.c_int, [C.c_int, C.POINTER(C.c_size_t)]),
     "sunb_encoder_forward": (C.c_int, [C.POINTER(EncoderWeights), fp, C.c_int, vp, C.c_size_t, fp, fp, vp, vp,
                                        C.POINTER(EncoderTaps), vp]),
-    "sunb_attention": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "sunb_attention": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "sunb_episode_logits": (C.c_int, [fp, fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fp, C.c_float, vp]),
     "sunb_logits_ce_acc": (C.c_int, [fp, vp, C.c_int, C.c_int, fp, vp]),
     "sunb_hard_ce_backward": (C.c_int, [fp, vp, C.c_int, C.c_int, fp, C.c_float, fp, vp]),
@@ -122,7 +122,7 @@ SIGNATURES = {
 }
 
 _lib = None
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 def lib() -> C.CDLL:

@@ -58,6 +58,17 @@ def _pad_cols(w: torch.Tensor, mult: int = 8) -> torch.Tensor:
     return w if kp == k else F.pad(w, (0, kp - k))
 
 
+HEAD_PAD = {42: 48, 85: 96}      # head_dim -> padded head stride of the eval engine (16-byte aligned head segments)
+
+
+def _pad_heads_rows(w: torch.Tensor, d: int, dp: int, blocks: int) -> torch.Tensor:
+    """[blocks*d, ...] -> [blocks*dp, ...]: every block of d rows is followed by dp - d zero rows."""
+    w = w.reshape(blocks, d, *w.shape[1:])
+    out = w.new_zeros(blocks, dp, *w.shape[2:])
+    out[:, :d] = w
+    return out.reshape(blocks * dp, *w.shape[2:])
+
+
 def pack_encoder(sd: Dict[str, torch.Tensor], prefix: str = "", wdtype: torch.dtype = torch.bfloat16) -> Dict[str, torch.Tensor]:
     """state_dict (reference names) -> dict of packed tensors keyed like SunbEncoderWeights fields.
     `wdtype=torch.float32` keeps GEMM weights in fp32 (CPU emulation tests)."""
@@ -102,10 +113,13 @@ def pack_encoder(sd: Dict[str, torch.Tensor], prefix: str = "", wdtype: torch.dt
         for i in range(depth):
             b = f"stage{stage}.{i}."
             s, t = bn_affine(g, b + "norm1.bn")
-            wq = w2d(b + "attn.qkv.weight")
-            P[f"s{stage}.{i}.wqkv"] = (wq * s[None, :]).to(wdtype).contiguous()
-            P[f"s{stage}.{i}.bqkv"] = (wq @ t).contiguous()
-            P[f"s{stage}.{i}.wproj"] = _pad_cols(w2d(b + "attn.proj.weight")).to(wdtype).contiguous()
+            wq = w2d(b + "attn.qkv.weight")                       # [3*6*d, C]
+            d = wq.shape[0] // (3 * HEADS)
+            dp = HEAD_PAD[d]
+            P[f"s{stage}.{i}.wqkv"] = _pad_heads_rows(wq * s[None, :], d, dp, 3 * HEADS).to(wdtype).contiguous()
+            P[f"s{stage}.{i}.bqkv"] = _pad_heads_rows(wq @ t, d, dp, 3 * HEADS).contiguous()
+            wp = w2d(b + "attn.proj.weight")                      # [C, 6*d] -> zero columns at the head pads
+            P[f"s{stage}.{i}.wproj"] = _pad_heads_rows(wp.t().contiguous(), d, dp, HEADS).t().to(wdtype).contiguous()
             s, t = bn_affine(g, b + "norm2.bn")
             w1 = w2d(b + "mlp.conv1.weight")
             P[f"s{stage}.{i}.w1"] = (w1 * s[None, :]).to(wdtype).contiguous()
@@ -188,11 +202,12 @@ def emulate_forward(P: Dict[str, torch.Tensor], x: torch.Tensor, taps: Dict[str,
         Bb, H, W, Cc = t.shape
         S = H * W
         x2 = t.reshape(Bb * S, Cc)
-        qkv = x2 @ f[pre + "wqkv"].t() + f[pre + "bqkv"]
-        qkv = qkv.reshape(Bb, S, 3, HEADS, d).permute(2, 0, 3, 1, 4)
+        dp = HEAD_PAD[d]
+        qkv = x2 @ f[pre + "wqkv"].t() + f[pre + "bqkv"]                 # padded heads: pad channels are exact zeros
+        qkv = qkv.reshape(Bb, S, 3, HEADS, dp).permute(2, 0, 3, 1, 4)
         pr = torch.softmax(qkv[0] @ qkv[1].transpose(-1, -2) * d ** -0.5, dim=-1)
-        ao = (pr @ qkv[2]).permute(0, 2, 1, 3).reshape(Bb * S, HEADS * d)
-        x2 = x2 + ao @ f[pre + "wproj"][:, : HEADS * d].t()
+        ao = (pr @ qkv[2]).permute(0, 2, 1, 3).reshape(Bb * S, HEADS * dp)
+        x2 = x2 + ao @ f[pre + "wproj"].t()
         hid = _gelu(x2 @ f[pre + "w1"].t() + f[pre + "b1"])
         return (x2 + hid @ f[pre + "w3"].t()).reshape(Bb, H, W, Cc)
 

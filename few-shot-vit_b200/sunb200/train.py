@@ -261,7 +261,7 @@ class TrainEngine:
                 xn1 = self.bn_apply(cur, bnA, M)
                 qkv = gemm(xn1, W[name + ".qkv.f"], M, 3 * inner, dim, out=self.empty(M, ld3))
                 ao = self.empty(M, ldi)
-                N.check(lib.sunb_attention(qkv.data_ptr(), ao.data_ptr(), B, S, d, HEADS, ld3, ldi, _st()), "sunb_attention")
+                N.check(lib.sunb_attention(qkv.data_ptr(), ao.data_ptr(), B, S, d, d, HEADS, ld3, ldi, _st()), "sunb_attention")
                 mid = gemm(ao, W[name + ".proj.f"], M, dim, inner, out=self.empty(M, dim), resid=cur, row_scale=rr[0],
                            rows_per_img=S)
                 bnM = self.bn_forward(mid, name + ".norm2.bn", dim, M, P, Bf, update_running)

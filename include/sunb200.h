@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SUNB_ABI_VERSION 2
+#define SUNB_ABI_VERSION 3
 
 int sunb_abi_version(void);
 const char* sunb_last_error(void);
@@ -82,8 +82,11 @@ typedef struct SunbConvMlpW {        /* stage-1 Block: norm2 folded into conv1 *
 } SunbConvMlpW;
 
 typedef struct SunbAttnBlockW {      /* stage-2/3 Block: norm1 folded into qkv, norm2 into mlp.conv1 */
-    const void* wqkv; const float* bqkv;   /* bf16 [3*6*d][C], fp32 [3*6*d] */
-    const void* wproj;                     /* bf16 [C][ld_inner], ld_inner = round_up(6*d, 8) */
+    /* heads padded to dp = 48 (stage 2, d = 42) / 96 (stage 3, d = 85) channels with zero rows / columns, so every
+     * (token, head) segment of the qkv buffer is 16-byte aligned: row (x*6 + y)*dp + z of wqkv is qkv.weight row
+     * x*6*d + y*d + z for z < d and zero for d <= z < dp; the same for bqkv; column y*dp + z of wproj likewise. */
+    const void* wqkv; const float* bqkv;   /* bf16 [3*6*dp][C], fp32 [3*6*dp] */
+    const void* wproj;                     /* bf16 [C][6*dp] */
     const void* w1; const float* b1;       /* bf16 [4C][C], fp32 [4C] */
     const void* w3;                        /* bf16 [C][4C] */
 } SunbAttnBlockW;
@@ -120,8 +123,11 @@ int sunb_encoder_forward(const SunbEncoderWeights* w, const float* x, int B, voi
                          float* pooled, float* dense, void* dense_bf16, void* pooled_bf16, const SunbEncoderTaps* taps,
                          void* stream);
 
-/* Attention core (visformer.py:183-190).  qkv bf16 [B*S, ld_qkv] with channels (qkv, head, d); out bf16 [B*S, ld_out]. */
-int sunb_attention(const void* qkv, void* out, int B, int S, int d, int heads, int ld_qkv, int ld_out, void* stream);
+/* Attention core (visformer.py:183-190).  qkv bf16 [B*S, ld_qkv], channel (x*heads + y)*d_stride + z for x in {q,k,v},
+ * head y, z < d; out bf16 [B*S, ld_out], channel y*d_stride + z.  d_stride == d is the reference's packed layout;
+ * d_stride > d (a multiple of 8) is the padded layout, whose pad channels must be zero on input and are written as zero. */
+int sunb_attention(const void* qkv, void* out, int B, int S, int d, int d_stride, int heads, int ld_qkv, int ld_out,
+                   void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Episode head: MetaBaseline (test_phase/models/meta_baseline.py:36-46) and utils.compute_logits

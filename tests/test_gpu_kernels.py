@@ -118,13 +118,33 @@ def test_attention(S, d, C):
     qkv = torch.full((B * S, ld_qkv), float("nan"), device=DEV, dtype=torch.bfloat16)
     qkv[:, : 3 * inner] = rnd(B * S, 3 * inner, seed=17).bfloat16()
     out = torch.zeros(B * S, C, device=DEV, dtype=torch.bfloat16)
-    N.check(N.lib().sunb_attention(qkv.data_ptr(), out.data_ptr(), B, S, d, heads, ld_qkv, C, N.current_stream()), "attention")
+    N.check(N.lib().sunb_attention(qkv.data_ptr(), out.data_ptr(), B, S, d, d, heads, ld_qkv, C, N.current_stream()), "attention")
     torch.cuda.synchronize()
     t = qkv[:, : 3 * inner].float().reshape(B, S, 3, heads, d).permute(2, 0, 3, 1, 4)
     p = torch.softmax(t[0] @ t[1].transpose(-1, -2) * d ** -0.5, dim=-1)
     ref = (p @ t[2]).permute(0, 2, 1, 3).reshape(B * S, inner)
     assert rel_err(out[:, :inner], ref) < BF16_OUT
     assert (out[:, inner:] == 0).all()
+
+
+@pytest.mark.parametrize("S,d,dp", [(100, 42, 48), (25, 85, 96)])
+def test_attention_padded_heads(S, d, dp):
+    """Eval-engine layout: heads padded to dp channels (zeros in, zeros out), 16-byte staged fast path."""
+    B, heads = 7, 6
+    real = rnd(B * S, 3, heads, d, seed=21).bfloat16()
+    qkv = torch.zeros(B * S, 3, heads, dp, device=DEV, dtype=torch.bfloat16)
+    qkv[..., :d] = real
+    qkv = qkv.reshape(B * S, 3 * heads * dp).contiguous()
+    out = torch.full((B * S, heads * dp), float("nan"), device=DEV, dtype=torch.bfloat16)
+    N.check(N.lib().sunb_attention(qkv.data_ptr(), out.data_ptr(), B, S, d, dp, heads, 3 * heads * dp, heads * dp,
+                                   N.current_stream()), "attention")
+    torch.cuda.synchronize()
+    t = real.float().reshape(B, S, 3, heads, d).permute(2, 0, 3, 1, 4)
+    p = torch.softmax(t[0] @ t[1].transpose(-1, -2) * d ** -0.5, dim=-1)
+    ref = (p @ t[2]).permute(0, 2, 1, 3)                      # [B, S, heads, d]
+    o = out.reshape(B, S, heads, dp)
+    assert rel_err(o[..., :d], ref) < BF16_OUT
+    assert (o[..., d:] == 0).all()                            # pad channels written as exact zeros
 
 
 @pytest.mark.parametrize("metric", ["cos", "dot", "sqr"])

@@ -35,9 +35,15 @@ def test_packed_layouts():
     blk = packing._grouped_pairs(sd["stage1.0.mlp.conv2.weight"])
     assert blk.shape == (4, 9, 64, 64)
     assert (blk[:, :, :32, 32:] == 0).all() and (blk[:, :, 32:, :32] == 0).all()      # block-diagonal pairs
-    assert P["s2.0.wqkv"].shape == (756, 256) and P["s3.0.wqkv"].shape == (1530, 512)
-    assert P["s2.0.wproj"].shape == (256, 256) and (P["s2.0.wproj"][:, 252:] == 0).all()
-    assert P["s3.0.wproj"].shape == (512, 512) and (P["s3.0.wproj"][:, 510:] == 0).all()
+    # heads padded 42 -> 48 and 85 -> 96 channels with zero rows / bias / columns (16-byte aligned head segments)
+    assert P["s2.0.wqkv"].shape == (864, 256) and P["s3.0.wqkv"].shape == (1728, 512)
+    assert P["s2.0.bqkv"].shape == (864,) and P["s3.0.bqkv"].shape == (1728,)
+    for name, d, dp in (("s2.0", 42, 48), ("s3.0", 85, 96)):
+        wq = P[name + ".wqkv"].float().reshape(18, dp, -1)
+        assert (wq[:, d:] == 0).all() and wq[:, :d].abs().sum() > 0
+        assert (P[name + ".bqkv"].reshape(18, dp)[:, d:] == 0).all()
+        wp = P[name + ".wproj"].float()
+        assert wp.shape[1] == 6 * dp and (wp.reshape(-1, 6, dp)[:, :, d:] == 0).all()
     assert P["pe2_w"].shape == (256, 512) and P["pe2_bias"].shape == (100, 256)
     assert P["pe3_w"].shape == (512, 1024) and P["pe3_bias"].shape == (25, 512)
     for k, v in P.items():
