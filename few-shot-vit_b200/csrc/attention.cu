@@ -13,6 +13,9 @@
 // too small (100x100x42) for a 128-row tcgen05 tile, so this stays on the legacy warp MMA path by design.
 #include "common.cuh"
 
+#ifndef SUNB_ATT_CTAS
+#define SUNB_ATT_CTAS 3
+#endif
 namespace {
 
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
@@ -35,10 +38,12 @@ struct AttnCfg {
     static constexpr int THREADS = 32 * WARPS_PER_PAIR * PAIRS;
     static constexpr int PAIR_ELEMS = 3 * S_PAD * QK_LD;
     static constexpr size_t SMEM = (size_t)PAIRS * PAIR_ELEMS * sizeof(bf16);
+    // the S = 100 kernel is latency bound at 2 CTAs (14 warps) per SM: cap the registers for 3
+    static constexpr int MIN_CTAS = (S_PAD > 32 && D_PAD <= 48) ? SUNB_ATT_CTAS : 1;
 };
 
 template <int S_PAD, int D_PAD, int PAIRS>
-__global__ void __launch_bounds__(AttnCfg<S_PAD, D_PAD, PAIRS>::THREADS)
+__global__ void __launch_bounds__(AttnCfg<S_PAD, D_PAD, PAIRS>::THREADS, AttnCfg<S_PAD, D_PAD, PAIRS>::MIN_CTAS)
 attention_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int n_pairs, int S, int d, int ds, int heads,
                      int ld_qkv, int ld_out, float scale_log2e) {
     using Cfg = AttnCfg<S_PAD, D_PAD, PAIRS>;
