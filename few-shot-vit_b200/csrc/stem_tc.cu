@@ -6,15 +6,16 @@
 // tile with ordinary loads, writes it to shared memory in the 128-byte-swizzled K-major layout the UMMA descriptor expects
 // (fence.proxy.async makes it visible to the tensor core), issues two tcgen05.mma (K = 32) into TMEM and runs the
 // bias / LeakyReLU / bf16-store epilogue from tcgen05.ld.  The weight tile [192][32] is built once per CTA.
-// Single-buffered; two CTAs per SM overlap gather, MMA and epilogue.
+// Persistent warp-specialised CTA per SM: gather warps, an MMA warp and drain warps work on consecutive tiles concurrently.
 #include "common.cuh"
 
 namespace {
 
 constexpr int IMG = 80, OUTP = 40, NPIX = OUTP * OUTP, NOUT = 192, KREAL = 27;
-constexpr int THREADS = 256;
+constexpr int GATHER_THREADS = 256, MMA_WARP = GATHER_THREADS / 32, THREADS = GATHER_THREADS + 32 + 256;   // 8 gather warps, MMA warp, 8 epilogue warps
+constexpr int A_STAGES = 3;
 constexpr int B_BYTES = NOUT * 128, A_BYTES = 128 * 128;
-constexpr int SMEM_BYTES = B_BYTES + A_BYTES + 64 + 1024;
+constexpr int SMEM_BYTES = B_BYTES + A_STAGES * A_BYTES + 128 + 1024;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t sw128_off(int row, int k) {       // byte offset of element (row, k) in a SW128 K-major tile
@@ -54,7 +55,32 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__global__ void __launch_bounds__(THREADS, 2) stem_in_tc_kernel(const float* __restrict__ x, const float* __restrict__ w1,
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {   // bounded: a broken pipeline traps instead of hanging
+    const long long t0 = clock64();
+    for (;;) {
+#pragma unroll 1
+        for (int i = 0; i < 4096; ++i)
+            if (mbar_try_wait(bar, parity)) return;
+        if (clock64() - t0 > 4000000000LL) {
+            printf("sunb stem_in_tc: mbarrier timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+// Persistent, warp-specialised: warps 0-7 gather im2col tiles into a 3-deep ring, warp 8 issues the MMAs into
+// double-buffered TMEM (2 x 192 columns), warps 9-16 drain (bias / LeakyReLU / bf16 stores).  The three phases of
+// consecutive tiles overlap; the first version ran them back to back in one CTA and was limited to two CTAs per SM by its
+// 256-column TMEM allocation.
+__global__ void __launch_bounds__(THREADS, 1) stem_in_tc_kernel(const float* __restrict__ x, const float* __restrict__ w1,
                                                                 const float* __restrict__ b1, const float* __restrict__ wd,
                                                                 const float* __restrict__ bd, bf16* __restrict__ a1,
                                                                 bf16* __restrict__ idn, int B, int lrelu, int n_tiles) {
@@ -62,18 +88,28 @@ __global__ void __launch_bounds__(THREADS, 2) stem_in_tc_kernel(const float* __r
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
     uint8_t* sB = gen;                                  // [192][64] bf16, SW128
-    uint8_t* sA = gen + B_BYTES;                        // [128][64] bf16, SW128
-    const uint32_t bar = base + B_BYTES + A_BYTES;
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + B_BYTES + A_BYTES + 16);
+    const uint32_t bars = base + B_BYTES + A_STAGES * A_BYTES;
+    auto a_full = [&](int s) { return bars + 8u * s; };
+    auto a_empty = [&](int s) { return bars + 8u * (A_STAGES + s); };
+    auto acc_full = [&](int a) { return bars + 8u * (2 * A_STAGES + a); };
+    auto acc_empty = [&](int a) { return bars + 8u * (2 * A_STAGES + 2 + a); };
+    const uint32_t tmem_slot_addr = bars + 8u * (2 * A_STAGES + 4);
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + B_BYTES + A_STAGES * A_BYTES + 8 * (2 * A_STAGES + 4));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        for (int s = 0; s < A_STAGES; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a_full(s)), "r"(GATHER_THREADS) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a_empty(s)) : "memory");
+        }
+        for (int a = 0; a < 2; ++a) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(acc_full(a)) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;" ::"r"(acc_empty(a)) : "memory");
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;"
-                     ::"r"(smem_u32((const void*)tmem_slot)) : "memory");
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot_addr) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     // weight tile: rows 0..63 conv1, 64..191 downsample; k >= 27 zero (k in [32,64) is never read: K = 32)
@@ -83,6 +119,7 @@ __global__ void __launch_bounds__(THREADS, 2) stem_in_tc_kernel(const float* __r
         if (k < KREAL) v = n < 64 ? w1[n * KREAL + k] : wd[(n - 64) * KREAL + k];
         *reinterpret_cast<bf16*>(sB + sw128_off(n, k)) = __float2bfloat16(v);
     }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -90,15 +127,15 @@ __global__ void __launch_bounds__(THREADS, 2) stem_in_tc_kernel(const float* __r
     // kind::f16: D fp32, A/B bf16 K-major, M = 128, N = 192
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NOUT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const int total = B * NPIX;
-    const int q = warp & 3, half = warp >> 2;
-    uint32_t phase = 0;
 
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        // ---- gather the im2col tile: element (r, k) = x[img][ci][2*oy-1+ky][2*ox-1+kx], k = (ci*3+ky)*3+kx.
-        //      thread = (pixel row r, 16-wide k half): the pixel decode happens once, the 16 values leave as two 16-byte
-        //      swizzled chunks; lanes walk consecutive pixels so the stride-2 image reads stay within a few sectors.
-        {
-            const int r = tid & 127, kh = tid >> 7;
+    if (warp < GATHER_THREADS / 32) {
+        // ================================================================ gather: element (r, k) = x[img][ci][2*oy-1+ky][2*ox-1+kx],
+        // k = (ci*3+ky)*3+kx.  thread = (pixel row r, 16-wide k half): the pixel decode happens once, the 16 values leave as two
+        // 16-byte swizzled chunks; lanes walk consecutive pixels so the stride-2 image reads stay within a few sectors.
+        const int r = tid & 127, kh = tid >> 7;
+        int lt = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+            const int s = lt % A_STAGES, ph = (lt / A_STAGES) & 1;
             const int m = tile * 128 + r;
             float v[16];
 #pragma unroll
@@ -116,6 +153,8 @@ __global__ void __launch_bounds__(THREADS, 2) stem_in_tc_kernel(const float* __r
                     }
                 }
             }
+            mbar_wait(a_empty(s), ph ^ 1);               // loads are already in flight / landed: only the smem slot is awaited
+            uint8_t* sA = gen + B_BYTES + s * A_BYTES;
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 uint4 u;
@@ -124,70 +163,75 @@ __global__ void __launch_bounds__(THREADS, 2) stem_in_tc_kernel(const float* __r
                 for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[c * 8 + 2 * j], v[c * 8 + 2 * j + 1]);
                 *reinterpret_cast<uint4*>(sA + sw128_off(r, kh * 16 + c * 8)) = u;
             }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the tensor core
+            mbar_arrive(a_full(s));
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the tensor core
-        __syncthreads();
-        if (tid == 0) {
+    } else if (warp == MMA_WARP) {
+        // ================================================================ MMA issuer
+        int lt = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+            const int s = lt % A_STAGES, ph = (lt / A_STAGES) & 1, acc = lt & 1, aph = (lt >> 1) & 1;
+            mbar_wait(acc_empty(acc), aph ^ 1);
+            mbar_wait(a_full(s), ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint64_t a_desc = make_sw128_desc(base + B_BYTES), b_desc = make_sw128_desc(base);
+            if (elect_one()) {
+                const uint64_t a_desc = make_sw128_desc(base + B_BYTES + s * A_BYTES), b_desc = make_sw128_desc(base);
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                asm volatile(
-                    "{\n\t.reg .pred p;\n\t"
-                    "setp.ne.b32 p, %4, 0;\n\t"
-                    "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                    ::"r"(tmem), "l"(a_desc + 2 * k), "l"(b_desc + 2 * k), "r"(idesc), "r"((uint32_t)k) : "memory");
+                for (int k = 0; k < 2; ++k) {
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\t"
+                        "setp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                        ::"r"(tmem + acc * 256), "l"(a_desc + 2 * k), "l"(b_desc + 2 * k), "r"(idesc), "r"((uint32_t)k) : "memory");
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(a_empty(s)) : "memory");
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(acc_full(acc)) : "memory");
             }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+            __syncwarp();
         }
-        {   // bounded wait: a broken pipeline traps instead of hanging the GPU
-            const long long t0 = clock64();
-            for (;;) {
-                bool done = false;
+    } else {
+        // ================================================================ epilogue: thread = one pixel row, 3 chunks of 32 channels
+        const int q = warp & 3, half = (warp - MMA_WARP - 1) >> 2;
+        int lt = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+            const int acc = lt & 1, aph = (lt >> 1) & 1;
+            mbar_wait(acc_full(acc), aph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int m = tile * 128 + q * 32 + lane;
 #pragma unroll 1
-                for (int i = 0; i < 1024 && !done; ++i) done = mbar_try_wait(bar, phase);
-                if (done) break;
-                if (clock64() - t0 > 4000000000LL) __trap();
-            }
-        }
-        phase ^= 1;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- epilogue: thread = one pixel row, 3 chunks of 32 channels
-        const int m = tile * 128 + q * 32 + lane;
-#pragma unroll 1
-        for (int cc = 0; cc < 3; ++cc) {
-            const int c = half * 3 + cc;                 // chunk 0,1 -> conv1 channels; 2..5 -> downsample channels
-            float v[32];
-            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-            if (m < total) {
-                const bool is1 = c < 2;
-                const float* bias = is1 ? b1 + c * 32 : bd + (c - 2) * 32;
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float4 bb = *reinterpret_cast<const float4*>(bias + i);
-                    v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
+            for (int cc = 0; cc < 3; ++cc) {
+                const int c = half * 3 + cc;                 // chunk 0,1 -> conv1 channels; 2..5 -> downsample channels
+                float v[32];
+                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + c * 32), v);
+                if (cc == 2) {                               // accumulator in registers: release the TMEM buffer
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty(acc));
                 }
-                if (is1 && lrelu) {
+                if (m < total) {
+                    const bool is1 = c < 2;
+                    const float* bias = is1 ? b1 + c * 32 : bd + (c - 2) * 32;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : 0.1f * v[i];
-                }
-                bf16* o = is1 ? a1 + (size_t)m * 64 + c * 32 : idn + (size_t)m * 128 + (c - 2) * 32;
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 bb = *reinterpret_cast<const float4*>(bias + i);
+                        v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
+                    }
+                    if (is1 && lrelu) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                    uint4 u;
-                    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[i + 2 * j], v[i + 2 * j + 1]);
-                    *reinterpret_cast<uint4*>(o + i) = u;
+                        for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : 0.1f * v[i];
+                    }
+                    bf16* o = is1 ? a1 + (size_t)m * 64 + c * 32 : idn + (size_t)m * 128 + (c - 2) * 32;
+                    store16_bf16(o, v);                      // rows are 128 / 256 B and chunks 64 B: always 32-byte aligned
+                    store16_bf16(o + 16, v + 16);
                 }
             }
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();                                  // TMEM and the A tile are free again
     }
-    if (warp == 0) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == MMA_WARP) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
     }
 }
 
@@ -197,6 +241,7 @@ int sunb_launch_stem_in_tc(const float* x, const float* w1, const float* b1, con
                            bf16* idn, int B, int lrelu, cudaStream_t stream) {
     SUNB_REQUIRE(B > 0, "stem_in: B must be positive");
     SUNB_REQUIRE((((size_t)b1) & 15) == 0 && (((size_t)bd) & 15) == 0, "stem_in: biases must be 16-byte aligned");
+    SUNB_REQUIRE((((size_t)a1) & 31) == 0 && (((size_t)idn) & 31) == 0, "stem_in: outputs must be 32-byte aligned");
     static bool configured = false;
     if (!configured) {
         SUNB_CHECK_CUDA(cudaFuncSetAttribute(stem_in_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -206,7 +251,7 @@ int sunb_launch_stem_in_tc(const float* x, const float* w1, const float* b1, con
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int grid = n_tiles < 2 * sms ? n_tiles : 2 * sms;
+    const int grid = n_tiles < sms ? n_tiles : sms;      // persistent: one CTA per SM
     stem_in_tc_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(x, w1, b1, wd, bd, a1, idn, B, lrelu, n_tiles);
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
