@@ -4,6 +4,10 @@
 // ConvBlock tail (visformer.py:232-237), drop_path (visformer.py:89-97).
 #include "common.cuh"
 
+#include <string.h>
+
+int sunb_launch_wgrad_tc(WgradParams p, cudaStream_t stream);
+
 namespace {
 
 // ------------------------------------------------------------------------------------------------
@@ -359,43 +363,27 @@ __global__ void pool_bwd_kernel(const float* __restrict__ dpooled, const float* 
 }
 
 // stem K=27 weight gradients: dW1[64][27] += sum_p da1[p, c] * patch(x)[p, :],  dWd[128][27] likewise from didn.
-// block = one image half (20 output rows), 192 threads = channel lanes (0..63 conv1, 64..191 downsample); the input rows
-// are staged once in shared memory and every thread keeps its 27 partial sums in registers -> 27 atomics per thread
-// per half image (the atomics, not the FMAs, bound this kernel).
-constexpr int SW_ROWS = 20;
-__global__ void __launch_bounds__(192) stem_wgrad_kernel(const float* __restrict__ x, const bf16* __restrict__ da1,
-                                                         const bf16* __restrict__ didn, float* __restrict__ dw1,
-                                                         float* __restrict__ dwd, int B) {
-    extern __shared__ float in_s[];                 // [3][2*SW_ROWS+1][82]
-    constexpr int RS = 2 * SW_ROWS + 1;
-    const int img = blockIdx.x / (40 / SW_ROWS), oy0 = (blockIdx.x % (40 / SW_ROWS)) * SW_ROWS;
-    for (int i = threadIdx.x; i < 3 * RS * 82; i += blockDim.x) {
-        const int c = i / (RS * 82), r = (i / 82) % RS, xx = i % 82;
-        const int iy = 2 * oy0 - 1 + r, ix = xx - 1;
-        in_s[i] = (iy >= 0 && iy < 80 && ix >= 0 && ix < 80) ? x[((size_t)(img * 3 + c) * 80 + iy) * 80 + ix] : 0.f;
-    }
-    __syncthreads();
-    const int t = threadIdx.x;
-    float acc[27];
+// The im2col matrix of the fp32 input image is materialised once as bf16 [B*1600, 32] (columns >= 27 zero; k = (ci*3+ky)*3+kx,
+// the same K order as the forward kernel in stem_tc.cu) and the two gradients are plain split-K tcgen05 weight-gradient GEMMs
+// over it (wgrad_tc.cu).  The first version kept 27 register accumulators per channel lane and was bound by its
+// shared-memory broadcast loads (869 us at 480 images).
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x, bf16* __restrict__ patches, int total) {
+    for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < total; m += gridDim.x * blockDim.x) {
+        const int img = m / 1600, rem = m - img * 1600, oy = rem / 40, ox = rem - oy * 40;
+        const float* xi = x + (size_t)img * 3 * 80 * 80;
+        float v[32];
 #pragma unroll
-    for (int i = 0; i < 27; ++i) acc[i] = 0.f;
-    for (int r = 0; r < SW_ROWS; ++r) {
-        for (int ox = 0; ox < 40; ++ox) {
-            const size_t px = (size_t)(img * 40 + oy0 + r) * 40 + ox;
-            const float gv = t < 64 ? __bfloat162float(da1[px * 64 + t]) : __bfloat162float(didn[px * 128 + (t - 64)]);
-#pragma unroll
-            for (int ci = 0; ci < 3; ++ci)
-#pragma unroll
-                for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-                    for (int kx = 0; kx < 3; ++kx)
-                        acc[(ci * 3 + ky) * 3 + kx] =
-                            fmaf(gv, in_s[(ci * RS + 2 * r + ky) * 82 + 2 * ox + kx], acc[(ci * 3 + ky) * 3 + kx]);
+        for (int k = 0; k < 32; ++k) {
+            v[k] = 0.f;
+            if (k < 27) {
+                const int ci = k / 9, ky = (k % 9) / 3, kx = k % 3;
+                const int iy = 2 * oy - 1 + ky, ix = 2 * ox - 1 + kx;
+                if (iy >= 0 && iy < 80 && ix >= 0 && ix < 80) v[k] = __ldg(xi + (ci * 80 + iy) * 80 + ix);
+            }
         }
+        store16_bf16(patches + (size_t)m * 32, v);
+        store16_bf16(patches + (size_t)m * 32 + 16, v + 16);
     }
-    float* dst = t < 64 ? dw1 + t * 27 : dwd + (t - 64) * 27;
-#pragma unroll
-    for (int i = 0; i < 27; ++i) atomicAdd(dst + i, acc[i]);
 }
 
 inline int grid_for(long total, int threads = 256) {
@@ -545,12 +533,22 @@ int sunb_pool_backward(const float* dpooled, const float* ddense, void* dy, int 
     return SUNB_OK;
 }
 
-int sunb_stem_wgrad(const float* x, const void* da1, const void* didn, float* dw1, float* dwd, int B, void* stream) {
-    SUNB_REQUIRE(x && da1 && didn && dw1 && dwd && B > 0, "stem_wgrad: bad arguments");
-    const size_t smem = (size_t)3 * (2 * SW_ROWS + 1) * 82 * sizeof(float);      // 40 KB
-    stem_wgrad_kernel<<<B * (40 / SW_ROWS), 192, smem, ST(stream)>>>(x, reinterpret_cast<const bf16*>(da1),
-                                                                      reinterpret_cast<const bf16*>(didn), dw1, dwd, B);
+int sunb_stem_wgrad(const float* x, const void* da1, const void* didn, float* dw1, float* dwd, int B, void* scratch,
+                    void* stream) {
+    SUNB_REQUIRE(x && da1 && didn && dw1 && dwd && scratch && B > 0, "stem_wgrad: bad arguments");
+    SUNB_REQUIRE((((size_t)scratch) & 31) == 0, "stem_wgrad: scratch must be 32-byte aligned");
+    const int P = B * 1600;
+    bf16* patches = reinterpret_cast<bf16*>(scratch);
+    stem_im2col_kernel<<<grid_for(P), 256, 0, ST(stream)>>>(x, patches, P);
     SUNB_CHECK_CUDA(cudaGetLastError());
+    WgradParams p;
+    memset(&p, 0, sizeof(p));
+    p.P = P; p.Nb = 27; p.Cb = 32; p.groups = 1; p.taps = 1;
+    p.X = patches; p.ldx = 32; p.ldo = 27;
+    p.Ma = 64; p.Ca = 64; p.dY = reinterpret_cast<const bf16*>(da1); p.ldy = 64; p.out = dw1;
+    SUNB_TRY(sunb_launch_wgrad_tc(p, ST(stream)));
+    p.Ma = 128; p.Ca = 128; p.dY = reinterpret_cast<const bf16*>(didn); p.ldy = 128; p.out = dwd; p.ksplit = 0;
+    SUNB_TRY(sunb_launch_wgrad_tc(p, ST(stream)));
     return SUNB_OK;
 }
 

@@ -96,7 +96,7 @@ SIGNATURES = {
     # train-mode building blocks
     "sunb_wgrad": (C.c_int, [C.POINTER(WgradDesc), vp]),
     "sunb_stem_in": (C.c_int, [fp, fp, fp, fp, fp, vp, vp, C.c_int, C.c_int, vp]),
-    "sunb_stem_wgrad": (C.c_int, [fp, vp, vp, fp, fp, C.c_int, vp]),
+    "sunb_stem_wgrad": (C.c_int, [fp, vp, vp, fp, fp, C.c_int, vp, vp]),
     "sunb_colstats": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_long, C.c_int, fp, fp, vp]),
     "sunb_bn_finalize": (C.c_int, [fp, fp, C.c_float, fp, fp, fp, fp, vp, C.c_float, C.c_float, C.c_int, fp, fp, fp, fp, vp]),
     "sunb_bn_apply": (C.c_int, [vp, C.c_int, fp, fp, C.c_int, fp, C.c_int, vp, C.c_int, C.c_long, C.c_int, vp]),

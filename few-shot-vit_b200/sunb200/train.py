@@ -427,6 +427,8 @@ class TrainEngine:
         da1 = gemm(da2r, W["stem.conv2.d"], M0, 64, 128, out=self.empty(M0, 64), taps=9, conv=(40, 40, 8, 8),
                    dact_aux=s["a1"], dact=ACT_LRELU)
         da1r = self.bn_backward(da1, bn1, M0, P, G)
+        patches = self.empty(M0, 32)                                  # bf16 im2col scratch of the input images
         N.check(lib.sunb_stem_wgrad(ctx["x"].data_ptr(), da1r.data_ptr(), didr.data_ptr(),
-                                    G["stem.conv1.weight"].data_ptr(), G["stem.downsample.0.weight"].data_ptr(), B, _st()),
+                                    G["stem.conv1.weight"].data_ptr(), G["stem.downsample.0.weight"].data_ptr(), B,
+                                    patches.data_ptr(), _st()),
                 "sunb_stem_wgrad")

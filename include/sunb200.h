@@ -181,7 +181,9 @@ int sunb_wgrad(const SunbWgradDesc* desc, void* stream);
  * w1 fp32 [64][27], wd fp32 [128][27], biases fp32; lrelu != 0 applies LeakyReLU(0.1) to the conv1 branch. */
 int sunb_stem_in(const float* x, const float* w1, const float* b1, const float* wd, const float* bd, void* a1, void* idn,
                  int B, int lrelu, void* stream);
-int sunb_stem_wgrad(const float* x, const void* da1, const void* didn, float* dw1, float* dwd, int B, void* stream);
+/* scratch: bf16 [B*1600*32] (the im2col matrix of x), 32-byte aligned; dw1 [64][27] / dwd [128][27] are accumulated into. */
+int sunb_stem_wgrad(const float* x, const void* da1, const void* didn, float* dw1, float* dwd, int B, void* scratch,
+                    void* stream);
 
 /* BatchNorm2d, training mode (visformer.py:118-124): column statistics, finalize (+ running stats, momentum),
  * apply (+ activation, + positional table), and the backward pair. */

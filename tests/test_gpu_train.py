@@ -149,6 +149,33 @@ def test_episode_logits_backward(metric):
     assert abs(temp.grad.item() - t2.grad.item()) < 1e-3 * max(1.0, abs(t2.grad.item()))
 
 
+def test_stem_wgrad_matches_conv2d_weight_grad():
+    """sunb_stem_wgrad (im2col + tcgen05 split-K weight-gradient GEMMs) vs autograd of the two stride-2 3x3 stem convs."""
+    B = 6
+    x = rnd(B, 3, 80, 80, seed=70)
+    da1 = rnd(B * 1600, 64, seed=71).bfloat16()
+    didn = rnd(B * 1600, 128, seed=72).bfloat16()
+    dw1 = torch.zeros(64, 27, device=DEV)
+    dwd = torch.zeros(128, 27, device=DEV)
+    scratch = torch.empty(B * 1600, 32, device=DEV, dtype=torch.bfloat16)
+    lib = N.lib()
+    N.check(lib.sunb_stem_wgrad(x.data_ptr(), da1.data_ptr(), didn.data_ptr(), dw1.data_ptr(), dwd.data_ptr(), B,
+                                scratch.data_ptr(), N.current_stream()), "stem_wgrad")
+    torch.cuda.synchronize()
+    xb = x.bfloat16().float()                     # the kernel multiplies bf16-rounded pixels
+    for g, dw, Cc in ((da1, dw1, 64), (didn, dwd, 128)):
+        w = torch.zeros(Cc, 3, 3, 3, device=DEV, requires_grad=True)
+        y = F.conv2d(xb, w, stride=2, padding=1)
+        y.backward(g.float().view(B, 40, 40, Cc).permute(0, 3, 1, 2))
+        assert rel_err(dw, w.grad.reshape(Cc, 27)) < 2e-3
+    first = dw1.clone()
+    # accumulates into the gradient buffers
+    N.check(lib.sunb_stem_wgrad(x.data_ptr(), da1.data_ptr(), didn.data_ptr(), dw1.data_ptr(), dwd.data_ptr(), B,
+                                scratch.data_ptr(), N.current_stream()), "stem_wgrad")
+    torch.cuda.synchronize()
+    assert rel_err(dw1, 2 * first) < 1e-5
+
+
 def test_stem_tail_forward_backward():
     B = 3
     c3, idn = rnd(B * 1600, 128, seed=18).bfloat16(), rnd(B * 1600, 128, seed=19).bfloat16()
