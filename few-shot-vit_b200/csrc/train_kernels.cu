@@ -110,6 +110,40 @@ __global__ void bn_apply_kernel(const bf16* __restrict__ x, int ldx, const float
                                 const float* __restrict__ shift, int act, const float* __restrict__ tab, int tab_mod,
                                 bf16* __restrict__ out, int ldo, long M, int C) {
     const int nvec = C / 8;
+    if (blockDim.x % nvec == 0) {
+        // a thread keeps one 8-channel vector for its whole life (scale / shift in registers) and walks the rows
+        const int c0 = (threadIdx.x % nvec) * 8, lanes = blockDim.x / nvec;
+        float sc[8], sh[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { sc[j] = scale[c0 + j]; sh[j] = shift[c0 + j]; }
+        for (long m = (long)blockIdx.x * lanes + threadIdx.x / nvec; m < M; m += (long)gridDim.x * lanes) {
+            const uint4 a = *reinterpret_cast<const uint4*>(x + m * ldx + c0);
+            const bf16* ah = reinterpret_cast<const bf16*>(&a);
+            float v[8];
+            if (act == ACT_GELU) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = gelu_fast(fmaf(__bfloat162float(ah[j]), sc[j], sh[j]));
+            } else if (act == ACT_LRELU) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { const float t = fmaf(__bfloat162float(ah[j]), sc[j], sh[j]); v[j] = t > 0.f ? t : 0.1f * t; }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = fmaf(__bfloat162float(ah[j]), sc[j], sh[j]);
+            }
+            if (tab) {
+                const float4* t = reinterpret_cast<const float4*>(tab + (size_t)(m % tab_mod) * C + c0);
+                const float4 t0 = t[0], t1 = t[1];
+                v[0] += t0.x; v[1] += t0.y; v[2] += t0.z; v[3] += t0.w; v[4] += t1.x; v[5] += t1.y; v[6] += t1.z; v[7] += t1.w;
+            }
+            uint4 o;
+            __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            *reinterpret_cast<uint4*>(out + m * ldo + c0) = o;
+        }
+        return;
+    }
+
     const long total = M * nvec;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const long m = i / nvec;
@@ -240,6 +274,38 @@ __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dz, int lddz, const
                                     const float* __restrict__ c2, const float* __restrict__ mean,
                                     const bf16* __restrict__ res, int ldr, bf16* __restrict__ out, int ldo, long M, int C) {
     const int nvec = C / 8;
+    if (blockDim.x % nvec == 0) {
+        // fixed 8-channel vector per thread: dx = k1*dz + k2*x + k3 with k1 = a, k2 = -a*c2, k3 = a*(c2*mean - c1) in registers
+        const int c0 = (threadIdx.x % nvec) * 8, lanes = blockDim.x / nvec;
+        float k1[8], k2[8], k3[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float A = a[c0 + j], C2 = c2[c0 + j];
+            k1[j] = A; k2[j] = -A * C2; k3[j] = A * (C2 * mean[c0 + j] - c1[c0 + j]);
+        }
+        for (long m = (long)blockIdx.x * lanes + threadIdx.x / nvec; m < M; m += (long)gridDim.x * lanes) {
+            const uint4 d4 = *reinterpret_cast<const uint4*>(dz + m * lddz + c0);
+            const uint4 x4 = *reinterpret_cast<const uint4*>(x + m * ldx + c0);
+            const bf16* dh = reinterpret_cast<const bf16*>(&d4);
+            const bf16* xh = reinterpret_cast<const bf16*>(&x4);
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaf(k1[j], __bfloat162float(dh[j]), fmaf(k2[j], __bfloat162float(xh[j]), k3[j]));
+            if (res) {
+                const uint4 r4 = *reinterpret_cast<const uint4*>(res + m * ldr + c0);
+                const bf16* rh = reinterpret_cast<const bf16*>(&r4);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] += __bfloat162float(rh[j]);
+            }
+            uint4 o;
+            __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            *reinterpret_cast<uint4*>(out + m * ldo + c0) = o;
+        }
+        return;
+    }
+
     const long total = M * nvec;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const long m = i / nvec;
