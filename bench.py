@@ -360,21 +360,35 @@ def run_product(args):
     ready = [torch.cuda.Event() for _ in range(2)]
     free = [torch.cuda.Event() for _ in range(2)]
 
+    e2e_state = {"g": 0, "prefetched": False}
+    done = torch.cuda.Event()
+
+    def issue_h2d(chunk, slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(free[slot])                           # the slot's previous occupant has been consumed
+            stage[slot].copy_(host_chunks[chunk], non_blocking=True)     # H2D inside the timed region
+            ready[slot].record(copy_stream)
+
     def step_e2e():
-        """Public API with HOST inputs: pinned H2D of every chunk (double-buffered on a copy stream so the transfer of
-        chunk c+1 overlaps the encoder on chunk c), model call, D2H of the logits -- all inside the timed region."""
+        """Public API with HOST inputs: pinned H2D of every chunk, model call, D2H of the logits -- all inside the timed
+        region.  Transfers are double-buffered on a copy stream: while chunk g runs, chunk g+1 (of this step, or the first
+        chunk of the next step) is already on its way, so a stream of batches keeps the encoder busy.  The step returns
+        when ITS logits are on the host."""
         main = torch.cuda.current_stream()
         for c in range(n_chunks):
-            buf = stage[c % 2]
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(free[c % 2])
-                buf.copy_(host_chunks[c], non_blocking=True)             # H2D inside the timed region
-                ready[c % 2].record(copy_stream)
-            main.wait_event(ready[c % 2])
-            xs, xq = fs.split_shot_query(buf, WAY, SHOT, QUERY, ep_per_batch=CHUNK)
+            g = e2e_state["g"]
+            slot = g % 2
+            if not (c == 0 and e2e_state["prefetched"]):
+                issue_h2d(c, slot)
+            main.wait_event(ready[slot])
+            issue_h2d((c + 1) % n_chunks, (g + 1) % 2)                   # next chunk; at c == last: chunk 0 of the next step
+            xs, xq = fs.split_shot_query(stage[slot], WAY, SHOT, QUERY, ep_per_batch=CHUNK)
             host_out[c].copy_(model(xs, xq), non_blocking=True)          # D2H of the step's result (logits)
-            free[c % 2].record(main)
-        main.synchronize()
+            free[slot].record(main)
+            e2e_state["g"] = g + 1
+        e2e_state["prefetched"] = True
+        done.record(main)
+        done.synchronize()
 
     def barrier():
         if world > 1:
