@@ -27,6 +27,7 @@ __global__ void __launch_bounds__(256) colstats_kernel(const bf16* __restrict__ 
     const int m0 = blockIdx.x * rows_per_block;
     const int m1 = min(m0 + rows_per_block, M);
     if (rl < lanes) {
+#pragma unroll 4
         for (int m = m0 + rl; m < m1; m += lanes) {
             const uint4 a = *reinterpret_cast<const uint4*>(x + (size_t)m * ldx + vec * 8);
             const bf16* ah = reinterpret_cast<const bf16*>(&a);
@@ -116,6 +117,7 @@ __global__ void bn_apply_kernel(const bf16* __restrict__ x, int ldx, const float
         float sc[8], sh[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) { sc[j] = scale[c0 + j]; sh[j] = shift[c0 + j]; }
+#pragma unroll 4
         for (long m = (long)blockIdx.x * lanes + threadIdx.x / nvec; m < M; m += (long)gridDim.x * lanes) {
             const uint4 a = *reinterpret_cast<const uint4*>(x + m * ldx + c0);
             const bf16* ah = reinterpret_cast<const bf16*>(&a);
@@ -283,6 +285,7 @@ __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dz, int lddz, const
             const float A = a[c0 + j], C2 = c2[c0 + j];
             k1[j] = A; k2[j] = -A * C2; k3[j] = A * (C2 * mean[c0 + j] - c1[c0 + j]);
         }
+#pragma unroll 4
         for (long m = (long)blockIdx.x * lanes + threadIdx.x / nvec; m < M; m += (long)gridDim.x * lanes) {
             const uint4 d4 = *reinterpret_cast<const uint4*>(dz + m * lddz + c0);
             const uint4 x4 = *reinterpret_cast<const uint4*>(x + m * ldx + c0);
