@@ -52,6 +52,26 @@ class ClockSampler:
         self.th = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
+        # NVML in-process (nvidia_ml_py) samples every 20 ms; nvidia-smi (one process per sample) is the fallback
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            bits = ((0x8, 2), (0x40, 3), (0x20, 4), (0x4, 5))       # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap
+            while not self.stop.is_set():
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                except Exception:
+                    reasons = 0
+                row = [str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx), "", "", "", ""]
+                for bit, col in bits:
+                    row[col] = "Active" if reasons & bit else "Not Active"
+                self.rows.append(row)
+                self.stop.wait(0.02)
+            return
+        except Exception:
+            pass
         while not self.stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",

@@ -27,7 +27,12 @@ int sunb_encode_tensor_map(CUtensorMap* map, const void* base, int rank, const c
 
 namespace {
 
-constexpr int THREADS = 32 * 11;
+#ifndef SUNB_SLAB_EPI_WARPS
+#define SUNB_SLAB_EPI_WARPS 16
+#endif
+constexpr int EPI_WARPS = SUNB_SLAB_EPI_WARPS;          // 8 or 16: (chunk parity) x 2 accumulator halves x 4 TMEM lane quarters
+constexpr int CSTEP = EPI_WARPS / 8;
+constexpr int THREADS = 32 * (3 + EPI_WARPS);
 constexpr int ATOM_SLOTS = 3;          // ring of 64-channel slab atoms (an atom is released as soon as its 9 taps are issued)
 constexpr int SMEM_LIMIT = 232448;
 
@@ -151,7 +156,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int s = 0; s < ATOM_SLOTS; ++s) { mbar_init(atom_full(s), 1); mbar_init(atom_empty(s), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(acc_full(a), 1); mbar_init(acc_empty(a), 8); }
+        for (int a = 0; a < 2; ++a) { mbar_init(acc_full(a), 1); mbar_init(acc_empty(a), EPI_WARPS); }
         for (int s = 0; s < g.b_stages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -240,7 +245,8 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else {
         // ================================================================ epilogue: warps 3..10
         const int q = warp & 3;                      // TMEM lane quarter this warp may read
-        const int half = (warp - 3) >> 2;
+        const int half = ((warp - 3) >> 2) & 1;
+        const int c0 = (warp - 3) >> 3;              // first 32-column chunk of this warp
         const int r = half * 128 + q * 32 + lane;    // raster position inside the band
         const int yy = r / g.P, xx = r - yy * g.P;
         int lt = 0;
@@ -252,10 +258,10 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_wait(acc_full(acc), aph);
             tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = c0; c < BN / 32; c += CSTEP) {
                 float v[32];
                 tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * BN + half * BN + c * 32), v);
-                if (c == BN / 32 - 1) {              // accumulator fully in registers: release the TMEM buffer
+                if (c + CSTEP >= BN / 32) {          // this warp's last chunk is in registers: release the TMEM buffer
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(acc_empty(acc));
@@ -288,6 +294,224 @@ int launch(const GemmParams& p, const SlabGeom& g, const CUtensorMap& tmA, const
     }
     const int grid = g.tiles < sms ? g.tiles : sms;
     conv_slab_kernel<BN><<<grid, THREADS, smem, stream>>>(tmA, tmB, p, g);
+    SUNB_CHECK_CUDA(cudaGetLastError());
+    return SUNB_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// 2-CTA variant: a cluster of two CTAs (one TPC) works on two bands with ONE weight stream.  Each CTA loads its own
+// band's slab atoms but only HALF of every weight block (BN/2 rows); the leader issues tcgen05.mma.cta_group::2 (M = 256:
+// 128 raster rows from each CTA's slab, written to that CTA's TMEM).  Per SM the weight bytes fetched from L2 and the
+// weight bytes the tensor core re-reads from shared memory per MMA are halved (12 KB instead of 16 KB of operands per pair
+// of MMAs).  Both CTAs run the same schedule in lock-step, so slot / stage indices -- and with them the shared-memory
+// offsets inside the descriptors -- are identical in the pair.
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;     // clears the CTA-rank bit of a shared::cluster address -> leader's copy
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    __syncwarp();
+    asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar & PEER_MASK), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar & PEER_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    const uint32_t z = 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(z) : "memory");
+}
+__device__ __forceinline__ void umma2_commit_both(uint32_t bar) {     // arrive on `bar` in both CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+conv_slab2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p,
+                  const SlabGeom g) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int KC = p.K / 64;
+    constexpr uint32_t B_BYTES = (BN / 2) * 128;          // this CTA's half of a (tap, 64-channel) weight block
+    const uint32_t bring = base + ATOM_SLOTS * g.atom_bytes;
+    const uint32_t bars = bring + g.b_stages * B_BYTES;
+    auto atom_full = [&](int s) { return bars + 8u * s; };
+    auto atom_empty = [&](int s) { return bars + 8u * (3 + s); };
+    auto acc_full = [&](int a) { return bars + 8u * (6 + a); };
+    auto acc_empty = [&](int a) { return bars + 8u * (8 + a); };
+    auto b_full = [&](int s) { return bars + 8u * (10 + s); };
+    auto b_empty = [&](int s) { return bars + 8u * (26 + s); };
+    const uint32_t tmem_slot_addr = bars + 8u * 42;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot_addr - smem_u32(smem_raw)));
+    constexpr int TMEM_COLS = 4 * BN;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair0 = blockIdx.x >> 1, pstep = gridDim.x >> 1;
+    const int pairs = (g.tiles + 1) >> 1;
+    if (tid == 0) {
+        for (int s = 0; s < ATOM_SLOTS; ++s) { mbar_init(atom_full(s), 1); mbar_init(atom_empty(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(acc_full(a), 1); mbar_init(acc_empty(a), 2 * EPI_WARPS); }     // drain warps of both CTAs
+        for (int s = 0; s < g.b_stages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot_addr), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================================================ slab producer (own band; bytes reported to the leader)
+        if (elect_one()) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        __syncwarp();
+        uint32_t ai = 0;
+        for (int t = pair0; t < pairs; t += pstep) {
+            const int tile = 2 * t + (int)rank;            // tile == g.tiles (odd count): image index past the batch -> zero box
+            const int img = tile / g.bands, y0 = (tile % g.bands) * g.RB;
+            for (int kc = 0; kc < KC; ++kc, ++ai) {
+                const int s = ai % ATOM_SLOTS, ph = (ai / ATOM_SLOTS) & 1;
+                mbar_wait(atom_empty(s), ph ^ 1);
+                if (elect_one()) {
+                    if (rank == 0) mbar_expect_tx(atom_full(s), 2 * g.atom_bytes);
+                    tma2_load_4d(base + s * g.atom_bytes, &tmA, atom_full(s), kc * 64, -1, y0 - 1, img);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 2) {
+        // ================================================================ weight producer: this CTA's half of every block
+        if (elect_one()) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        __syncwarp();
+        uint32_t it = 0;
+        const int nblk = 9 * KC;
+        for (int t = pair0; t < pairs; t += pstep) {
+            for (int blk = 0; blk < nblk; ++blk, ++it) {
+                const int s = it % g.b_stages, ph = (it / g.b_stages) & 1;
+                mbar_wait(b_empty(s), ph ^ 1);
+                if (elect_one()) {
+                    if (rank == 0) mbar_expect_tx(b_full(s), 2 * B_BYTES);
+                    tma2_load_2d(bring + s * B_BYTES, &tmB, b_full(s), (blk / 9) * 64, (blk % 9) * p.N + (int)rank * (BN / 2));
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================================ MMA issuer (leader CTA only)
+        if (rank == 0) {
+            constexpr uint32_t idesc = make_idesc(256, BN);
+            uint32_t it = 0, ai = 0;
+            int lt = 0;
+            for (int t = pair0; t < pairs; t += pstep, ++lt) {
+                const int acc = lt & 1, aph = (lt >> 1) & 1;
+                mbar_wait(acc_empty(acc), aph ^ 1);
+                tc_fence_after();
+                const uint32_t d0 = tmem_base + acc * 2 * BN;
+                for (int kc = 0; kc < KC; ++kc, ++ai) {
+                    const int s = ai % ATOM_SLOTS, ph = (ai / ATOM_SLOTS) & 1;
+                    mbar_wait(atom_full(s), ph);
+                    tc_fence_after();
+                    const uint32_t atom = base + s * g.atom_bytes;
+                    for (int tap = 0; tap < 9; ++tap, ++it) {
+                        const int bs = it % g.b_stages, bph = (it / g.b_stages) & 1;
+                        mbar_wait(b_full(bs), bph);
+                        tc_fence_after();
+                        const uint32_t a_addr = atom + ((tap / 3) * g.P + tap % 3) * 128;
+                        const uint32_t b_addr = bring + bs * B_BYTES;
+                        if (elect_one()) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                                for (int half = 0; half < 2; ++half)
+                                    umma2_bf16(d0 + half * BN, make_sw128_desc(a_addr + half * 128 * 128 + k * 32),
+                                               make_sw128_desc(b_addr + k * 32), idesc, (kc | tap | k) ? 1u : 0u);
+                            }
+                            umma2_commit_both(b_empty(bs));
+                        }
+                        __syncwarp();
+                    }
+                    if (elect_one()) umma2_commit_both(atom_empty(s));
+                    __syncwarp();
+                }
+                if (elect_one()) umma2_commit_both(acc_full(acc));
+                __syncwarp();
+            }
+        }
+    } else {
+        // ================================================================ epilogue: warps 3..10 of each CTA drain that CTA's TMEM
+        const int q = warp & 3;
+        const int half = ((warp - 3) >> 2) & 1;
+        const int c0 = (warp - 3) >> 3;              // first 32-column chunk of this warp
+        const int r = half * 128 + q * 32 + lane;
+        const int yy = r / g.P, xx = r - yy * g.P;
+        int lt = 0;
+        for (int t = pair0; t < pairs; t += pstep, ++lt) {
+            const int acc = lt & 1, aph = (lt >> 1) & 1;
+            const int tile = 2 * t + (int)rank;
+            const int img = tile / g.bands, y0 = (tile % g.bands) * g.RB;
+            const bool valid = (tile < g.tiles) && (yy < g.RB) && (xx < p.W) && (y0 + yy < p.H);
+            const int m = valid ? (img * p.H + y0 + yy) * p.W + xx : p.M;
+            mbar_wait(acc_full(acc), aph);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = c0; c < BN / 32; c += CSTEP) {
+                float v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * BN + half * BN + c * 32), v);
+                if (c + CSTEP >= BN / 32) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(acc_empty(acc) & PEER_MASK);      // the leader's barrier
+                }
+                epilogue_row<32>(p, 0, m, c * 32, v);
+            }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();        // nobody leaves (or frees TMEM) while the partner may still read its smem / signal its barriers
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+template <int BN>
+int launch2(const GemmParams& p, const SlabGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmB2, int smem, cudaStream_t stream) {
+    static int configured = 0;
+    if (configured < smem) {
+        SUNB_CHECK_CUDA(cudaFuncSetAttribute(conv_slab2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = smem;
+    }
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        SUNB_CHECK_CUDA(cudaGetDevice(&dev));
+        SUNB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int pairs = (g.tiles + 1) / 2, cl = sms / 2;
+    const int grid = 2 * (pairs < cl ? pairs : cl);
+    conv_slab2_kernel<BN><<<grid, THREADS, smem, stream>>>(tmA, tmB2, p, g);
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
 }
@@ -326,12 +550,19 @@ int sunb_launch_conv_slab(const GemmParams& p, cudaStream_t stream) {
     const int BN = p.N;
     // the junk rows of the second accumulator read up to 2P+2 rows past the 256-row window: keep that inside the allocation
     const int slab_total = ATOM_SLOTS * g.atom_bytes;
-    int b_stages = (SMEM_LIMIT - 1024 - 256 - slab_total) / (BN * 128);
-    if (b_stages > 8) b_stages = 8;
+    static int two_cta = -1;
+    if (two_cta < 0) {
+        const char* e = getenv("SUNB_CONV_SLAB_2CTA");
+        two_cta = (e && e[0] == '0') ? 0 : 1;
+    }
+    const bool pair = two_cta && g.tiles >= 2;
+    const int b_block = (pair ? BN / 2 : BN) * 128;
+    int b_stages = (SMEM_LIMIT - 1024 - 512 - slab_total) / b_block;
+    if (b_stages > (pair ? 16 : 8)) b_stages = pair ? 16 : 8;
     SUNB_REQUIRE(b_stages >= 2, "conv_slab: slab of %d bytes leaves no room for the weight ring", slab_total);
     g.b_stages = b_stages;
-    const int smem = 1024 + slab_total + b_stages * BN * 128 + 256;
-    SUNB_REQUIRE((256 + 2 * g.P + 2) * 128 <= g.atom_bytes + b_stages * BN * 128, "conv_slab: over-read guard");
+    const int smem = 1024 + slab_total + b_stages * b_block + 512;
+    SUNB_REQUIRE((256 + 2 * g.P + 2) * 128 <= g.atom_bytes + b_stages * b_block, "conv_slab: over-read guard");
 
     CUtensorMap tmA, tmB;
     {
@@ -343,8 +574,9 @@ int sunb_launch_conv_slab(const GemmParams& p, cudaStream_t stream) {
     {
         cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.taps * p.N};
         cuuint64_t strides[1] = {(cuuint64_t)p.ldw * 2};
-        cuuint32_t box[2] = {64, (cuuint32_t)BN};
+        cuuint32_t box[2] = {64, (cuuint32_t)(pair ? BN / 2 : BN)};
         SUNB_TRY(sunb_encode_tensor_map(&tmB, p.Wt, 2, dims, strides, box));
     }
+    if (pair) return BN == 64 ? launch2<64>(p, g, tmA, tmB, smem, stream) : launch2<128>(p, g, tmA, tmB, smem, stream);
     return BN == 64 ? launch<64>(p, g, tmA, tmB, smem, stream) : launch<128>(p, g, tmA, tmB, smem, stream);
 }
