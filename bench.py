@@ -193,7 +193,7 @@ def time_dominant_kernel(model_state, device, peaks_tf):
     if os.path.exists(tpath):        # dram bytes per launch from the committed `ncu --set full` capture of this same launch
         t = json.load(open(tpath))
         traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
-    return {"bound": "tensor", "kernel": "conv_slab_kernel<128> (stem conv3 implicit GEMM over a resident haloed slab, M=%d N=128 K=9x128)" % (B * 1600),
+    return {"bound": "tensor", "kernel": "conv_slab2_kernel<128> (stem conv3: implicit GEMM over a resident haloed slab, cta_group::2 pairs, M=%d N=128 K=9x128)" % (B * 1600),
             "achieved": achieved, "peak": peaks_tf, "unit": "TFLOP/s", "frac": achieved / peaks_tf, "traffic": traffic,
             "ms_per_launch": ms, "flops_per_launch": flops}
 
