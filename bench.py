@@ -331,8 +331,9 @@ def measure_train_step(args, device, world, rank, sd):
 
 def run_product(args):
     # stdout carries exactly one JSON line: keep NCCL's version banner off it unless the caller asked for NCCL logging
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
         os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/sunb200_nccl.%h.%p.log")   # the banner / warnings go to a file, not stdout
     import torch
     import torch.distributed as dist
     import models
