@@ -10,6 +10,10 @@
 // Probabilities / dS are rounded to bf16 only as MMA operands; statistics and accumulators stay fp32.
 #include "common.cuh"
 
+#ifndef SUNB_ATTB_CTAS
+#define SUNB_ATTB_CTAS 2
+#endif
+
 namespace {
 
 __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
@@ -35,6 +39,8 @@ struct BwdCfg {
     static constexpr int PAIR_BF16 = 4 * ROW_ELEMS + 3 * T_ELEMS;                 // Q K V dO | Qt Kt dOt
     static constexpr size_t PAIR_BYTES = (size_t)PAIR_BF16 * 2 + 3 * S_PAD * sizeof(float);   // + rowmax, 1/rowsum, D
     static constexpr size_t SMEM = PAIRS * PAIR_BYTES;
+    // S = 100: shared memory allows two CTAs per SM, so cap the registers for two (175 -> <= 144) -- the kernel is latency bound
+    static constexpr int MIN_CTAS = (S_PAD > 32 && D_PAD <= 48) ? SUNB_ATTB_CTAS : 1;
 };
 
 // C = A(16 rows starting at a_row0 of a row-major tile, K = KD) x B^T(rows n of a row-major tile), NT n-tiles of 8
@@ -75,7 +81,7 @@ __device__ __forceinline__ void mma_regs_x_t(float (&out)[OT][4], const float (&
 }
 
 template <int S_PAD, int D_PAD, int PAIRS>
-__global__ void __launch_bounds__(BwdCfg<S_PAD, D_PAD, PAIRS>::THREADS)
+__global__ void __launch_bounds__(BwdCfg<S_PAD, D_PAD, PAIRS>::THREADS, BwdCfg<S_PAD, D_PAD, PAIRS>::MIN_CTAS)
 attention_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout, bf16* __restrict__ dqkv, int n_pairs,
                          int S, int d, int heads, int ld_qkv, int ld_out, float scale) {
     using Cfg = BwdCfg<S_PAD, D_PAD, PAIRS>;
