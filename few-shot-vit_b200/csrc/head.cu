@@ -166,6 +166,9 @@ int sunb_launch_logits_ce_acc(const float* logits, const long long* label, int R
 // ------------------------------------------------------------------------------------------------
 namespace {
 
+// Kernel A, grid (E, QS): block (e, j) owns every QS-th group of 8 queries of episode e.  It rebuilds the (normalised)
+// prototypes, writes dquery for its queries (accumulated per warp in shared memory, one global store per element) and adds
+// its partial prototype gradient into dshot[e, w, 0, :] (zeroed by the launcher) with global atomics; dtemp likewise.
 __global__ void __launch_bounds__(256) episode_logits_bwd_kernel(const float* __restrict__ feat_shot,
                                                                  const float* __restrict__ feat_query,
                                                                  const float* __restrict__ dlogits,
@@ -175,8 +178,8 @@ __global__ void __launch_bounds__(256) episode_logits_bwd_kernel(const float* __
                                                                  float temp_host) {
     extern __shared__ float smh[];
     float* proto = smh;                    // [way][D]  (normalised for cos)
-    float* dph = proto + way * D;          // [way][D]  gradient w.r.t. the (normalised) prototype
-    float* pinv = dph + way * D;           // [way]     1 / ||proto||
+    float* dph = proto + way * D;          // [way][D]  partial gradient w.r.t. the (normalised) prototype
+    float* sdq = dph + way * D;            // [8 warps][D] gradient w.r.t. the normalised query, one row per warp
     __shared__ float s_dtemp;
     const int e = blockIdx.x;
     const float temp = temp_dev ? *temp_dev : temp_host;
@@ -191,20 +194,19 @@ __global__ void __launch_bounds__(256) episode_logits_bwd_kernel(const float* __
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-    for (int w = warp; w < way; w += nwarp) {
-        float inv = 1.f;
-        if (metric == 1) {
+    if (metric == 1) {
+        for (int w = warp; w < way; w += nwarp) {
             float ss = 0.f;
             for (int dd = lane; dd < D; dd += 32) ss += proto[w * D + dd] * proto[w * D + dd];
             ss = warp_sum(ss);
-            inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+            const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
             for (int dd = lane; dd < D; dd += 32) proto[w * D + dd] *= inv;
         }
-        if (lane == 0) pinv[w] = inv;
+        __syncthreads();
     }
-    __syncthreads();
     float dt_local = 0.f;
-    for (int qi = warp; qi < Q; qi += nwarp) {
+    float* mydq = sdq + warp * D;
+    for (int qi = blockIdx.y * nwarp + warp; qi < Q; qi += gridDim.y * nwarp) {
         const float* fq = feat_query + ((size_t)e * Q + qi) * D;
         const float* dl = dlogits + ((size_t)e * Q + qi) * way;
         float qinv = 1.f;
@@ -214,10 +216,7 @@ __global__ void __launch_bounds__(256) episode_logits_bwd_kernel(const float* __
             ss = warp_sum(ss);
             qinv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
         }
-        float* dq = dquery + ((size_t)e * Q + qi) * D;
-        // dqh (gradient w.r.t. the normalised query) is accumulated per lane over its D/32 strided elements
-        float proj = 0.f;          // qhat . dqh  (cos only)
-        for (int dd = lane; dd < D; dd += 32) dq[dd] = 0.f;
+        for (int dd = lane; dd < D; dd += 32) mydq[dd] = 0.f;
         for (int w = 0; w < way; ++w) {
             const float g = dl[w];
             float dot = 0.f;
@@ -226,39 +225,72 @@ __global__ void __launch_bounds__(256) episode_logits_bwd_kernel(const float* __
                 if (metric == 2) {
                     const float df = qh - ph;
                     dot = fmaf(df, df, dot);
-                    dq[dd] += -2.f * temp * g * df;
+                    mydq[dd] += -2.f * temp * g * df;
                     atomicAdd(&dph[w * D + dd], 2.f * temp * g * df);
                 } else {
                     dot = fmaf(qh, ph, dot);
-                    dq[dd] += temp * g * ph;
+                    mydq[dd] += temp * g * ph;
                     atomicAdd(&dph[w * D + dd], temp * g * qh);
                 }
             }
             dot = warp_sum(dot);
             dt_local += g * (metric == 2 ? -dot : dot);
         }
-        if (metric == 1) {
-            for (int dd = lane; dd < D; dd += 32) proj = fmaf(fq[dd] * qinv, dq[dd], proj);
+        float* dq = dquery + ((size_t)e * Q + qi) * D;
+        if (metric == 1) {                 // back through the query normalisation
+            float proj = 0.f;
+            for (int dd = lane; dd < D; dd += 32) proj = fmaf(fq[dd] * qinv, mydq[dd], proj);
             proj = warp_sum(proj);
-            for (int dd = lane; dd < D; dd += 32) dq[dd] = (dq[dd] - fq[dd] * qinv * proj) * qinv;
+            for (int dd = lane; dd < D; dd += 32) dq[dd] = (mydq[dd] - fq[dd] * qinv * proj) * qinv;
+        } else {
+            for (int dd = lane; dd < D; dd += 32) dq[dd] = mydq[dd];
         }
     }
     if (lane == 0) atomicAdd(&s_dtemp, dt_local);
     __syncthreads();
+    for (int i = threadIdx.x; i < way * D; i += blockDim.x) {
+        const int w = i / D, dd = i % D;
+        atomicAdd(dshot + ((size_t)(e * way + w) * shot) * D + dd, dph[i]);
+    }
+    if (threadIdx.x == 0 && dtemp) atomicAdd(dtemp, s_dtemp);
+}
+
+// Kernel B, grid E: dshot[e, w, 0, :] holds the summed gradient w.r.t. the (normalised) prototype; go back through the
+// normalisation and the mean over shots, and write every shot's row.
+__global__ void __launch_bounds__(256) episode_logits_bwd_finish_kernel(const float* __restrict__ feat_shot,
+                                                                        float* __restrict__ dshot, int way, int shot, int D,
+                                                                        int metric) {
+    extern __shared__ float smh[];
+    float* proto = smh;                    // [way][D]
+    float* dph = proto + way * D;          // [way][D]
+    const int e = blockIdx.x;
+    const float* fs = feat_shot + (size_t)e * way * shot * D;
+    for (int i = threadIdx.x; i < way * D; i += blockDim.x) {
+        const int w = i / D, dd = i % D;
+        float s = 0.f;
+        for (int k = 0; k < shot; ++k) s += fs[((size_t)w * shot + k) * D + dd];
+        proto[i] = s / (float)shot;
+        dph[i] = dshot[((size_t)(e * way + w) * shot) * D + dd];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     for (int w = warp; w < way; w += nwarp) {
-        float proj = 0.f;
+        float inv = 1.f, proj = 0.f;
         if (metric == 1) {
-            for (int dd = lane; dd < D; dd += 32) proj = fmaf(proto[w * D + dd], dph[w * D + dd], proj);
+            float ss = 0.f;
+            for (int dd = lane; dd < D; dd += 32) ss += proto[w * D + dd] * proto[w * D + dd];
+            ss = warp_sum(ss);
+            inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+            for (int dd = lane; dd < D; dd += 32) proj = fmaf(proto[w * D + dd] * inv, dph[w * D + dd], proj);
             proj = warp_sum(proj);
         }
         for (int dd = lane; dd < D; dd += 32) {
             float g = dph[w * D + dd];
-            if (metric == 1) g = (g - proto[w * D + dd] * proj) * pinv[w];
+            if (metric == 1) g = (g - proto[w * D + dd] * inv * proj) * inv;
             g /= (float)shot;
             for (int k = 0; k < shot; ++k) dshot[((size_t)(e * way + w) * shot + k) * D + dd] = g;
         }
     }
-    if (threadIdx.x == 0 && dtemp) atomicAdd(dtemp, s_dtemp);
 }
 
 }  // namespace
@@ -267,15 +299,22 @@ int sunb_launch_episode_logits_bwd(const float* feat_shot, const float* feat_que
                                    float* dquery, float* dtemp, int E, int way, int shot, int Q, int D, int metric,
                                    const float* temp_dev, float temp_host, cudaStream_t stream) {
     SUNB_REQUIRE(E > 0 && way > 0 && shot > 0 && Q > 0 && D > 0 && metric >= 0 && metric <= 2, "episode_logits_bwd: bad shape");
-    const size_t smem = (size_t)(2 * way * D + way) * sizeof(float);
+    const size_t smem = (size_t)(2 * way * D + 8 * D) * sizeof(float);
     SUNB_REQUIRE(smem <= 200 * 1024, "episode_logits_bwd: way*D too large for shared memory");
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         SUNB_CHECK_CUDA(cudaFuncSetAttribute(episode_logits_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SUNB_CHECK_CUDA(cudaFuncSetAttribute(episode_logits_bwd_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    episode_logits_bwd_kernel<<<E, 256, smem, stream>>>(feat_shot, feat_query, dlogits, dshot, dquery, dtemp, way, shot, Q, D,
-                                                        metric, temp_dev, temp_host);
+    // an episode is split over QS blocks (8 queries per block and pass) so that a few episodes still fill the GPU
+    int qs = (Q + 7) / 8;
+    if (qs > 16) qs = 16;
+    SUNB_CHECK_CUDA(cudaMemsetAsync(dshot, 0, (size_t)E * way * shot * D * sizeof(float), stream));
+    episode_logits_bwd_kernel<<<dim3(E, qs), 256, smem, stream>>>(feat_shot, feat_query, dlogits, dshot, dquery, dtemp, way, shot, Q,
+                                                                  D, metric, temp_dev, temp_host);
+    SUNB_CHECK_CUDA(cudaGetLastError());
+    episode_logits_bwd_finish_kernel<<<E, 256, (size_t)(2 * way * D) * sizeof(float), stream>>>(feat_shot, dshot, way, shot, D, metric);
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
 }
