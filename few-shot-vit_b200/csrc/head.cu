@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(256) episode_logits_kernel(const float* __rest
         }
         __syncthreads();
     }
-    for (int qi = warp; qi < Q; qi += nwarp) {
+    // blockIdx.y: query slice (an episode is split over gridDim.y blocks; each rebuilds the prototypes)
+    for (int qi = blockIdx.y * nwarp + warp; qi < Q; qi += gridDim.y * nwarp) {
         const float* fq = feat_query + ((size_t)e * Q + qi) * D;
         float qn = 1.f;
         if (metric == 1) {
@@ -147,7 +148,9 @@ int sunb_launch_episode_logits(const float* feat_shot, const float* feat_query, 
         SUNB_CHECK_CUDA(cudaFuncSetAttribute(episode_logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    episode_logits_kernel<<<E, 256, smem, stream>>>(feat_shot, feat_query, logits, way, shot, Q, D, metric, temp_dev,
+    int qs = E >= 64 ? 1 : (Q + 7) / 8;           // few episodes: split the queries of an episode over several blocks
+    if (qs > 16) qs = 16;
+    episode_logits_kernel<<<dim3(E, qs), 256, smem, stream>>>(feat_shot, feat_query, logits, way, shot, Q, D, metric, temp_dev,
                                                     temp_host);
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;

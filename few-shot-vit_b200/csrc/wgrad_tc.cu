@@ -10,6 +10,7 @@
 #include "common.cuh"
 
 #include <mutex>
+#include <stdlib.h>
 
 
 namespace {
@@ -342,9 +343,11 @@ int sunb_launch_wgrad_tc(WgradParams p, cudaStream_t stream) {
     const int box = conv ? p.bw * p.bh : BKP;
     const int kblocks = conv ? (p.W / p.bw) * (p.H / p.bh) * ((p.P / (p.H * p.W) + BKP / box - 1) / (BKP / box))
                              : (p.P + BKP - 1) / BKP;
-    if (p.ksplit <= 0) {       // ~2 waves of CTAs, at least 4 K blocks per CTA
+    if (p.ksplit <= 0) {       // ~1.5 waves of CTAs (fewer split-K atomics than 2 waves), at least 4 K blocks per CTA
         const int tiles = n_tiles * m_tiles * p.taps * p.groups;
-        int ks = (2 * 148 + tiles - 1) / tiles;
+        static int waves_x2 = -1;                        // CTA waves x 2 (SUNB_WGRAD_WAVES_X2).  Measured on the train step: 2 -> 11.4 ms, 3 -> 11.15, 4 -> 11.4, 6 -> 11.5
+        if (waves_x2 < 0) { const char* e = getenv("SUNB_WGRAD_WAVES_X2"); waves_x2 = e ? atoi(e) : 3; if (waves_x2 < 1) waves_x2 = 3; }
+        int ks = (waves_x2 * 74 + tiles - 1) / tiles;
         ks = ks < 1 ? 1 : ks;
         const int max_ks = kblocks / 4 > 0 ? kblocks / 4 : 1;
         p.ksplit = ks < max_ks ? ks : max_ks;
