@@ -12,11 +12,14 @@
 //     XOR is a function of the absolute shared-memory address, so a row-shifted descriptor still addresses what the TMA
 //     wrote (rows are 128 B, the 8-row pattern repeats every 1024 B, slabs are 1024-byte aligned);
 //   * each weight block (tap, 64 channels) is fetched once per 256 raster rows and used by both accumulators.
-// L2 -> SMEM traffic drops to (slab 84 KB + weights 288 KB) per 240 useful pixels of conv3: 3x less.
+// L2 -> SMEM traffic drops to (slab 84 KB + weights 288 KB, 144 KB per SM in a pair) per 240 useful pixels of conv3: 3x less.
 // Raster positions on halo columns / past the band are computed and dropped in the epilogue (useful: 240 of 256 rows).
 //
-// Roles (352 threads): warp 0 slab producer, warp 1 MMA issuer (+ TMEM owner), warp 2 weight producer, warps 3-10 epilogue
-// (2 accumulator halves x 4 TMEM lane quarters).  Accumulators are double-buffered in TMEM (2 x 2 x BN columns).
+// Roles (608 threads): warp 0 slab producer, warp 1 MMA issuer (+ TMEM owner), warp 2 weight producer, warps 3-18 epilogue
+// (chunk parity x 2 accumulator halves x 4 TMEM lane quarters).  Accumulators are double-buffered in TMEM (2 x 2 x BN columns).
+// Slab atoms (64 channels each) sit in a ring of three and are released as soon as their nine taps are issued; weight blocks
+// stream through a 6-12 deep ring.  Default: conv_slab2_kernel, clusters of two CTAs sharing one weight stream through
+// tcgen05.mma.cta_group::2 (below); SUNB_CONV_SLAB_2CTA=0 selects the single-CTA kernel, SUNB_CONV_SLAB=0 the GEMM fall-back.
 #include "common.cuh"
 
 #include <cuda.h>

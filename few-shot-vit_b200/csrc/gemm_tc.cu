@@ -1,12 +1,13 @@
 // tcgen05 / TMEM / TMA implicit-GEMM kernel for sm_100a.
 //
-// Persistent kernel, one CTA per SM, 128 x BN output tiles.  Warp roles (320 threads):
-//   warp 0   : TMA producer  (cp.async.bulk.tensor into a STAGES-deep ring of 128B-swizzled K-major tiles)
-//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (two fp32 accumulators in TMEM, ping-pong)
-//   warps 2-9: epilogue (tcgen05.ld -> bias / residual / activation -> bf16 or fp32 global stores), overlapped
-//              with the MMAs of the next tile
-// The K loop runs over taps x 64-wide K blocks: a 3x3 convolution is nine shifted 4-D TMA box loads of the
-// NHWC activation (TMA zero-fills the padding), a 1x1 convolution / linear layer is the taps == 1 case.
+// Persistent kernel, one CTA per SM, 128 x BN output tiles.  Warp roles (576 threads):
+//   warp 0    : TMA producer  (cp.async.bulk.tensor into a STAGES-deep ring of 128B-swizzled K-major tiles)
+//   warp 1    : TMEM allocator + tcgen05.mma issuer (one elect.sync lane; two fp32 accumulators in TMEM, ping-pong)
+//   warps 2-17: epilogue (tcgen05.ld -> bias / residual / activation -> bf16 or fp32 global stores), four warps per TMEM
+//               lane quarter, overlapped with the MMAs of the next tile
+// The K loop runs over taps x 64-wide K blocks: a 1x1 convolution / linear layer is the taps == 1 case; in conv mode a 3x3
+// convolution is nine shifted 4-D TMA box loads of the NHWC activation (TMA zero-fills the padding) -- the grouped-pair and
+// odd-shape fall-back; the dense stem 3x3 convolutions go to conv_slab.cu, the grouped 3x3 to gconv_tc.cu.
 #include "common.cuh"
 
 #include <mutex>
