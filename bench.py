@@ -48,7 +48,22 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
+        # `index` is the CUDA ordinal; NVML / nvidia-smi enumerate physical GPUs (CUDA_VISIBLE_DEVICES may remap), so the
+        # device is addressed by UUID whenever torch exposes it
         self.index, self.rows, self.stop = index, [], threading.Event()
+        self.uuid = None
+        try:
+            import torch
+            u = str(torch.cuda.get_device_properties(index).uuid)
+            self.uuid = u if u.startswith("GPU-") else "GPU-" + u
+        except Exception:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if index < len(ids):
+                if ids[index].startswith("GPU-"):
+                    self.uuid = ids[index]
+                elif ids[index].isdigit():
+                    self.index = int(ids[index])
         self.th = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
@@ -56,7 +71,7 @@ class ClockSampler:
         try:
             import pynvml as nv
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            h = nv.nvmlDeviceGetHandleByUUID(self.uuid.encode()) if self.uuid else nv.nvmlDeviceGetHandleByIndex(self.index)
             mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
             bits = ((0x8, 2), (0x40, 3), (0x20, 4), (0x4, 5))       # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap
             while not self.stop.is_set():
@@ -75,7 +90,7 @@ class ClockSampler:
         while not self.stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                                      self.uuid or str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
