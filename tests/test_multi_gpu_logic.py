@@ -1,4 +1,4 @@
-"""CPU (gloo, world_size 2) tests of the multi-GPU host logic: episode sharding and the data-parallel gradient
+"""CPU (gloo, world_size 2 and 4) tests of the multi-GPU host logic: episode sharding and the data-parallel gradient
 all-reduce that replaces nn.DataParallel's reduce_add (meta_tuning_sun_m/train_meta.py:128-129)."""
 import os
 import socket
@@ -45,7 +45,7 @@ def _worker(rank, world, port, out_path):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.set_num_threads(2)
-    way, shot, query, ep = 3, 1, 1, 2
+    way, shot, query, ep = 3, 1, 1, world                       # one episode per rank (8 episodes on 8 GPUs in SUN-M)
     sd = O.init_meta_baseline_state_dict(5)
     data = O.make_episode_images(900, ep * way, shot + query)
     xs, xq = O.split_shot_query(data, way, shot, query, ep)
@@ -69,15 +69,16 @@ def _worker(rank, world, port, out_path):
     dist.destroy_process_group()
 
 
-def test_data_parallel_gradients_match_shard_average(tmp_path):
+@pytest.mark.parametrize("world", [2, 4])
+def test_data_parallel_gradients_match_shard_average(tmp_path, world):
     out = str(tmp_path / "avg.pt")
-    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     got = torch.load(out)
-    way, shot, query, ep = 3, 1, 1, 2
+    way, shot, query, ep = 3, 1, 1, world
     sd = O.init_meta_baseline_state_dict(5)
     data = O.make_episode_images(900, ep * way, shot + query)
     xs, xq = O.split_shot_query(data, way, shot, query, ep)
-    per_shard = [_episode_grads(sd, xs[r:r + 1], xq[r:r + 1], way, query) for r in range(2)]
+    per_shard = [_episode_grads(sd, xs[r:r + 1], xq[r:r + 1], way, query) for r in range(world)]
     for i, name in enumerate(got["names"]):
-        ref = 0.5 * (per_shard[0][1][i] + per_shard[1][1][i])
+        ref = sum(per_shard[r][1][i] for r in range(world)) / world
         assert torch.allclose(got["avg"][i], ref, rtol=1e-5, atol=1e-7), name
