@@ -89,6 +89,127 @@ def hook_taps(encoder):
     return taps, hs
 
 
+def _grad_record(model, prefix, g):
+    """Per-parameter gradient norms + values (small tensors) / strided samples (big tensors), as the GPU tests read them."""
+    for k, p in model.named_parameters():
+        gr = p.grad
+        g[prefix + "gnorm." + k] = np.array(gr.norm().item())
+        if gr.numel() <= 4096 or k in ("encoder.stem.conv1.weight", "encoder.stage3.2.attn.proj.weight"):
+            g[prefix + "grad." + k] = gr.numpy().copy()
+        else:
+            g[prefix + "gsamp." + k] = gr.flatten()[:: max(1, gr.numel() // 2048)].numpy().copy()
+
+
+def round2_fixtures():
+    """Round-2 fixtures: SUN-M-shaped shards (10-way x (1+5) = 60 images per shard, drop_path 0.5, non-trivial loss) and
+    their 2-shard gradient average; 20-episode argmax fixtures for 1-shot and 5-shot; one SUN meta-training step
+    (offline.py:263-303, scaled down to 16 images -- stated) incl. an AdamW update."""
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    sd_w1 = O.calibrate_bn(O.init_meta_baseline_state_dict(12345))
+
+    # ---------------- SUN-M shards (meta_tuning_sun_m/train_meta.py:161-174, configs/train_meta_mini_visformer_1shot.yaml:13-20)
+    models, utils = _load_pkg("meta_tuning_sun_m", ["models", "visformer", "meta_baseline"])
+    fs = sys.modules["utils.few_shot"]
+    way, shot, query = 10, 1, 5
+    g, shard_grads = {}, []
+    for s in range(2):
+        model = models.make("meta-baseline", encoder="visformer_micro_80", encoder_args={"drop_path_rate": 0.5})
+        model.load_state_dict(sd_w1)
+        model.train()
+        data = O.make_episode_images(600 + s, way, shot + query, noise=1.0)
+        xs, xq = fs.split_shot_query(data, way, shot, query, ep_per_batch=1)
+        label = fs.make_nk_label(way, query, 1)
+        torch.manual_seed(77 + s)                  # DropPath draws of this replica (global CPU RNG, visformer.py:94)
+        logits = model(xs, xq).view(-1, way)
+        loss = F.cross_entropy(logits, label)
+        model.zero_grad()
+        loss.backward()
+        g[f"s{s}.x_checksum"] = _checksum(data)
+        g[f"s{s}.logits"] = logits.detach().numpy()
+        g[f"s{s}.loss"] = np.array(loss.item())
+        shard_grads.append({k: p.grad.clone() for k, p in model.named_parameters()})
+        if s == 0:
+            _grad_record(model, "s0.", g)
+            for k, v in model.state_dict().items():
+                if k.endswith("running_mean") or k.endswith("running_var"):
+                    g["s0.bn." + k] = v.numpy().copy()
+        print("sunm shard", s, "loss", loss.item(), "acc", utils.compute_acc(logits, label))
+    # DataParallel / DDP semantics: gradient of the batch mean = mean of the per-shard gradients
+    for k, p in model.named_parameters():
+        p.grad = (shard_grads[0][k] + shard_grads[1][k]) / 2
+    _grad_record(model, "avg.", g)
+    np.savez_compressed(os.path.join(OUT, "train_step_sunm.npz"), **g)
+
+    # ---------------- argmax fixtures: 20 episodes each, BN-calibrated weights, class-structured inputs
+    models, utils = _load_pkg("test_phase", ["models", "visformer", "meta_baseline"])
+    fs = sys.modules["utils.few_shot"]
+    model = models.make("meta-baseline", encoder="visformer_micro_80", encoder_args={})
+    model.load_state_dict(sd_w1)
+    model.eval()
+    out = {}
+    for tag, shot, seed0 in (("1shot", 1, 1000), ("5shot", 5, 2000)):
+        lg = []
+        for ep in range(20):
+            data = O.make_episode_images(seed0 + ep, 5, shot + 15)
+            xs, xq = fs.split_shot_query(data, 5, shot, 15, ep_per_batch=1)
+            with torch.no_grad():
+                lg.append(model(xs, xq)[0].numpy())
+        out["logits_" + tag] = np.stack(lg)
+        print("argmax fixture", tag, out["logits_" + tag].shape)
+    np.savez_compressed(os.path.join(OUT, "episodes_argmax_w1.npz"), **out)
+
+    # ---------------- SUN meta-training step (sun_meta_training/offline.py:263-303), batch scaled 512 -> 16 (stated)
+    models, utils = _load_pkg("sun_meta_training", ["models", "visformer", "classifier", "token_label"], stub_timm=True)
+    import models.visformer as vis_sun
+    vis_sun.DEBUG = False
+    src = open(os.path.join(REF, "sun_meta_training", "offline.py")).read().splitlines()
+    ns = {"torch": torch, "nn": nn, "F": F}
+    exec("\n".join(src[33:45]), ns)      # SoftTargetCrossEntropy, offline.py:34-45
+    exec("\n".join(src[56:76]), ns)      # generate_softlabel, offline.py:57-76
+    margs = dict(encoder="visformer_micro_80", encoder_args={"drop_path_rate": 0.5}, classifier="linear-classifier",
+                 classifier_args={"n_classes": 64})
+    student = models.make("token-label", **margs)
+    teacher = models.make("token-label", **margs)
+    sd_student = O.calibrate_bn(O.init_token_label_state_dict(4321))
+    sd_teacher = O.calibrate_bn(O.init_token_label_state_dict(12345))
+    student.load_state_dict(sd_student)
+    teacher.load_state_dict(sd_teacher)
+    teacher.eval()
+    student.train()
+    bs = 16
+    strong = O.make_episode_images(800, 8, 2, noise=1.0)          # 8 classes x 2 images, "strong" view
+    weak = O.make_episode_images(800, 8, 2, noise=0.5)            # same prototypes, "weak" view
+    label = torch.arange(8).repeat_interleave(2) * 7 % 64
+    lr = 5e-4 * (bs / 512)                                        # offline.py:228
+    opt = torch.optim.AdamW(student.parameters(), betas=(0.9, 0.999), eps=1e-8, lr=lr, weight_decay=0.05)   # offline.py:229
+    torch.manual_seed(123)
+    logits_token, logits, token = student(strong)                 # offline.py:269
+    cls_loss = F.cross_entropy(logits, label)
+    with torch.no_grad():
+        logits_token_t, _, _ = teacher(weak, True)                # offline.py:289
+        soft_label = ns["generate_softlabel"](logits_token_t, k=5, bp=10, device="cpu")
+    b, c, h, w = logits_token_t.size()
+    token_loss = ns["SoftTargetCrossEntropy"]()(logits_token.permute(0, 2, 3, 1).view(-1, c + 1), soft_label)
+    loss = cls_loss + 0.5 * token_loss                            # offline.py:300
+    opt.zero_grad()
+    loss.backward()
+    g = {"loss": np.array(loss.item()), "cls_loss": np.array(cls_loss.item()), "token_loss": np.array(token_loss.item()),
+         "soft_label": soft_label.numpy(), "teacher_logits_token": logits_token_t.numpy(), "logits": logits.detach().numpy(),
+         "logits_token": logits_token.detach().numpy(), "label": label.numpy(), "lr": np.array(lr)}
+    _grad_record(student, "", g)
+    before = {k: p.detach().clone() for k, p in student.named_parameters()}
+    opt.step()
+    for k in ("classifier_local.linear.weight", "classifier.linear.bias", "encoder.stem.bn1.weight",
+              "encoder.stage3.2.mlp.conv3.weight", "encoder.stage1.0.mlp.conv2.weight"):
+        p = dict(student.named_parameters())[k]
+        g["adamw_delta." + k] = (p.detach() - before[k]).flatten()[:: max(1, p.numel() // 1024)].numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "sun_meta_step.npz"), **g)
+    print("sun_meta_step loss", loss.item(), cls_loss.item(), token_loss.item())
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -248,4 +369,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    # `python oracle/make_golden.py`         -> round-1 fixtures (main) + round-2 fixtures
+    # `python oracle/make_golden.py round2`  -> only the round-2 fixtures
+    if "round2" not in sys.argv[1:]:
+        main()
+    round2_fixtures()
