@@ -1,6 +1,11 @@
 // C ABI (include/sunb200.h) and the eval-mode encoder schedule.
 #include "common.cuh"
+#include "gemm_desc.cuh"
 #include "../../include/sunb200.h"
+
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include <stdarg.h>
 #include <string.h>
@@ -43,6 +48,34 @@ void sunb_set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+// per (kernel, device) shared-memory opt-in and per-device SM count (see common.cuh)
+int sunb_opt_in_smem(const void* kernel, int bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, int> done;
+    int dev = 0;
+    SUNB_CHECK_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    int& have = done[std::make_pair(kernel, dev)];
+    if (have < bytes) {
+        SUNB_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        have = bytes;
+    }
+    return SUNB_OK;
+}
+
+int sunb_num_sms() {
+    static std::mutex mu;
+    static std::map<int, int> sms;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    std::lock_guard<std::mutex> lock(mu);
+    int& n = sms[dev];
+    if (n <= 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
 }
 
 namespace {
@@ -135,26 +168,12 @@ const char* sunb_last_error(void) { return g_err; }
 
 int sunb_gemm(const SunbGemmDesc* d, int impl, void* stream) {
     SUNB_REQUIRE(d != nullptr, "sunb_gemm: null descriptor");
-    GemmParams p;
-    memset(&p, 0, sizeof(p));
-    p.M = d->M; p.N = d->N; p.K = d->K; p.taps = d->taps; p.groups = d->groups;
-    p.a_goff = d->a_goff; p.c_goff = d->c_goff;
-    p.a_mode = d->a_mode; p.H = d->H; p.W = d->W; p.bw = d->bw; p.bh = d->bh;
-    p.A = reinterpret_cast<const bf16*>(d->A); p.lda = d->lda;
-    p.Wt = reinterpret_cast<const bf16*>(d->Wt); p.ldw = d->ldw;
-    p.bias = d->bias; p.bias_mod = d->bias_mod > 0 ? d->bias_mod : 1; p.bias_ld = d->bias_ld;
-    p.act = d->act;
-    p.resid = reinterpret_cast<const bf16*>(d->resid); p.ldr = d->ldr;
-    p.row_scale = d->row_scale; p.rows_per_img = d->rows_per_img > 0 ? d->rows_per_img : 1;
-    p.out = reinterpret_cast<bf16*>(d->out); p.ldc = d->ldc;
-    p.out_f32 = d->out_f32; p.ldc_f32 = d->ldc_f32;
-    p.out_map = d->out_map; p.oH = d->oH; p.oW = d->oW;
-    p.out2 = reinterpret_cast<bf16*>(d->out2); p.ldc2 = d->ldc2;
-    p.dact_aux = reinterpret_cast<const bf16*>(d->dact_aux); p.ld_aux = d->ld_aux; p.dact = d->dact;
+    GemmParams p = sunb_desc_to_params(d);
     SUNB_REQUIRE(p.taps >= 1 && p.groups >= 1, "sunb_gemm: taps/groups must be >= 1");
     SUNB_REQUIRE(p.out || p.out_f32, "sunb_gemm: no output buffer");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    return impl == 1 ? sunb_launch_gemm_simt(p, st) : sunb_launch_gemm_tc(p, st);
+    SUNB_REQUIRE(impl == 0, "sunb_gemm: impl %d is not part of the product library (the SIMT checker lives in tests/native)", impl);
+    return sunb_launch_gemm_tc(p, st);
 }
 
 int sunb_encoder_workspace_bytes(int B, size_t* bytes) {

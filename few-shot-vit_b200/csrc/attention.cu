@@ -234,12 +234,7 @@ template <int S_PAD, int D_PAD, int PAIRS>
 int launch_cfg(const bf16* qkv, bf16* out, int n_pairs, int S, int d, int ds, int heads, int ld_qkv, int ld_out, float scale,
                cudaStream_t stream) {
     using Cfg = AttnCfg<S_PAD, D_PAD, PAIRS>;
-    static bool configured = false;
-    if (!configured) {
-        SUNB_CHECK_CUDA(cudaFuncSetAttribute(attention_mma_kernel<S_PAD, D_PAD, PAIRS>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-        configured = true;
-    }
+    SUNB_TRY(sunb_opt_in_smem(reinterpret_cast<const void*>(&attention_mma_kernel<S_PAD, D_PAD, PAIRS>), (int)Cfg::SMEM));
     const int blocks = (n_pairs + PAIRS - 1) / PAIRS;
     attention_mma_kernel<S_PAD, D_PAD, PAIRS><<<blocks, Cfg::THREADS, Cfg::SMEM, stream>>>(
         qkv, out, n_pairs, S, d, ds, heads, ld_qkv, ld_out, scale * 1.4426950408889634f);

@@ -236,12 +236,7 @@ template <int S_PAD, int D_PAD, int PAIRS>
 int launch_bwd(const bf16* qkv, const bf16* dout, bf16* dqkv, int n_pairs, int S, int d, int heads, int ld_qkv, int ld_out,
                cudaStream_t stream) {
     using Cfg = BwdCfg<S_PAD, D_PAD, PAIRS>;
-    static bool configured = false;
-    if (!configured) {
-        SUNB_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_mma_kernel<S_PAD, D_PAD, PAIRS>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-        configured = true;
-    }
+    SUNB_TRY(sunb_opt_in_smem(reinterpret_cast<const void*>(&attention_bwd_mma_kernel<S_PAD, D_PAD, PAIRS>), (int)Cfg::SMEM));
     const int blocks = (n_pairs + PAIRS - 1) / PAIRS;
     attention_bwd_mma_kernel<S_PAD, D_PAD, PAIRS><<<blocks, Cfg::THREADS, Cfg::SMEM, stream>>>(
         qkv, dout, dqkv, n_pairs, S, d, heads, ld_qkv, ld_out, 1.0f / sqrtf((float)d));

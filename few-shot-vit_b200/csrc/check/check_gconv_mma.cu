@@ -8,13 +8,12 @@
 // times (the tcgen05 implicit-GEMM formulation re-fetched a shifted box per tap and wasted half of each 64-wide
 // block-diagonal MMA).  5 warps x 5 m16 tiles cover the 400 pixels; a warp keeps the B fragments of a k-step in registers
 // across its 5 tiles.  Epilogue: GELU (+ pre-activation copy for training) or the chain-rule factor gelu'(aux) for dgrad.
-#include "common.cuh"
+// TEST-ONLY warp-MMA cross-check of gconv_tc.cu (tests/native/libsunb200_check.so): never linked into libsunb200.so.
+#include "../common.cuh"
 
 #include <stdlib.h>
 #include <string.h>
 
-int sunb_launch_gconv_tc(const bf16* x, int ldx, const bf16* wg, bf16* y, int ldy, bf16* y2, int ldy2, const bf16* aux,
-                         int ldaux, int B, int act, int dact, cudaStream_t stream);
 
 namespace {
 
@@ -138,53 +137,17 @@ __global__ void __launch_bounds__(THREADS, 3) gconv3x3_kernel(const bf16* __rest
     }
 }
 
-// fp32 grouped weight [256][32][3][3] -> bf16 [8][9][32 n][32 k].  transpose_flip = 1 gives the conv-transpose operand
-// for the data gradient: n = input channel, k = output channel, taps mirrored.
-__global__ void gconv_pack_kernel(const float* __restrict__ w, bf16* __restrict__ dst, int transpose_flip) {
-    const int total = 8 * 9 * GC * GC;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int k = i % GC, n = (i / GC) % GC, tap = (i / (GC * GC)) % 9, grp = i / (GC * GC * 9);
-        const int co = transpose_flip ? k : n, ci = transpose_flip ? n : k, st = transpose_flip ? 8 - tap : tap;
-        dst[i] = __float2bfloat16(w[((size_t)(grp * GC + co) * GC + ci) * 9 + st]);
-    }
-}
-
 }  // namespace
 
-extern "C" {
-
-int sunb_gconv3x3(const void* x, int ldx, const void* wg, void* y, int ldy, void* y2, int ldy2, const void* aux, int ldaux,
-                  int B, int act, int dact, void* stream) {
-    SUNB_REQUIRE(x && wg && y && B > 0, "gconv3x3: bad arguments");
+extern "C" int sunb_check_gconv3x3(const void* x, int ldx, const void* wg, void* y, int ldy, void* y2, int ldy2, const void* aux,
+                                   int ldaux, int B, int act, int dact, void* stream) {
+    SUNB_REQUIRE(x && wg && y && B > 0, "check_gconv3x3: bad arguments");
     SUNB_REQUIRE(ldx % 8 == 0 && ldy % 2 == 0 && (((size_t)x) & 15) == 0 && (((size_t)wg) & 15) == 0,
-                 "gconv3x3: operands must be 16-byte aligned");
-    // default: tcgen05 kernel (gconv_tc.cu); SUNB_GCONV=mma keeps the warp-MMA kernel below as a cross-check
-    static int use_mma = -1;
-    if (use_mma < 0) {
-        const char* e = getenv("SUNB_GCONV");
-        use_mma = (e && strcmp(e, "mma") == 0) ? 1 : 0;
-    }
-    if (!use_mma)
-        return sunb_launch_gconv_tc(reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<const bf16*>(wg), reinterpret_cast<bf16*>(y),
-                                    ldy, reinterpret_cast<bf16*>(y2), ldy2, reinterpret_cast<const bf16*>(aux), ldaux, B, act, dact,
-                                    reinterpret_cast<cudaStream_t>(stream));
-    static bool configured = false;
-    if (!configured) {
-        SUNB_CHECK_CUDA(cudaFuncSetAttribute(gconv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-        configured = true;
-    }
+                 "check_gconv3x3: operands must be 16-byte aligned");
+    SUNB_CHECK_CUDA(cudaFuncSetAttribute(gconv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     gconv3x3_kernel<<<dim3(B, 8), THREADS, SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<const bf16*>(wg), reinterpret_cast<bf16*>(y), ldy,
         reinterpret_cast<bf16*>(y2), ldy2, reinterpret_cast<const bf16*>(aux), ldaux, act, dact);
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
 }
-
-int sunb_gconv_pack(const float* w, void* dst, int transpose_flip, void* stream) {
-    SUNB_REQUIRE(w && dst, "gconv_pack: bad arguments");
-    gconv_pack_kernel<<<72, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(w, reinterpret_cast<bf16*>(dst), transpose_flip);
-    SUNB_CHECK_CUDA(cudaGetLastError());
-    return SUNB_OK;
-}
-
-}  // extern "C"

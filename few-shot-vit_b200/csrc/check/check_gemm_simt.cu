@@ -1,7 +1,7 @@
-// Plain shared-memory-tiled SIMT GEMM / implicit GEMM with the same semantics and epilogue as gemm_tc.cu.
-// It exists as an on-device cross-check for the tcgen05 kernel (tests, SUNB_GEMM=simt debugging); the encoder
-// forward does not use it unless that environment variable is set.
-#include "common.cuh"
+// Plain shared-memory-tiled SIMT GEMM / implicit GEMM with the same semantics and epilogue as gemm_tc.cu:
+// an on-device cross-check for the tcgen05 kernel, called by the -m gpu tests through sunb_check_gemm.
+// TEST-ONLY (tests/native/libsunb200_check.so): never linked into libsunb200.so.
+#include "../gemm_desc.cuh"
 
 #include <stdlib.h>
 #include <string.h>
@@ -68,19 +68,12 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmParams p) {
 
 }  // namespace
 
-int sunb_launch_gemm_simt(const GemmParams& p, cudaStream_t stream) {
+extern "C" int sunb_check_gemm(const SunbGemmDesc* d, void* stream) {
+    SUNB_REQUIRE(d != nullptr, "check_gemm: null descriptor");
+    const GemmParams p = sunb_desc_to_params(d);
     SUNB_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm_simt: empty problem");
     dim3 grid((p.N + TN - 1) / TN, (p.M + TM - 1) / TM, p.groups);
-    gemm_simt_kernel<<<grid, 256, 0, stream>>>(p);
+    gemm_simt_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
-}
-
-int sunb_launch_gemm(const GemmParams& p, cudaStream_t stream) {
-    static int use_simt = -1;
-    if (use_simt < 0) {
-        const char* e = getenv("SUNB_GEMM");
-        use_simt = (e && strcmp(e, "simt") == 0) ? 1 : 0;
-    }
-    return use_simt ? sunb_launch_gemm_simt(p, stream) : sunb_launch_gemm_tc(p, stream);
 }

@@ -349,9 +349,13 @@ struct WgradParams {
     int ksplit;
 };
 
-// launchers (gemm_tc.cu / gemm_simt.cu)
+// launchers (gemm_tc.cu / conv_slab.cu).  There is one implementation per operation: no run-time dispatch.
 int sunb_launch_gemm_tc(const GemmParams& p, cudaStream_t stream);
 int sunb_conv_slab_supported(const GemmParams& p);
 int sunb_launch_conv_slab(const GemmParams& p, cudaStream_t stream);
-int sunb_launch_gemm_simt(const GemmParams& p, cudaStream_t stream);
-int sunb_launch_gemm(const GemmParams& p, cudaStream_t stream);   // dispatch (tcgen05 unless SUNB_GEMM=simt)
+inline int sunb_launch_gemm(const GemmParams& p, cudaStream_t stream) { return sunb_launch_gemm_tc(p, stream); }
+
+// Opt a kernel in to `bytes` (> 48 KB) of dynamic shared memory on the CURRENT device.  The attribute is per device, so the
+// bookkeeping is per (kernel, device): a process that drives several GPUs configures each of them (api.cu).
+int sunb_opt_in_smem(const void* kernel, int bytes);
+int sunb_num_sms();      // SM count of the current device

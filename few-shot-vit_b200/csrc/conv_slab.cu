@@ -18,12 +18,11 @@
 // Roles (608 threads): warp 0 slab producer, warp 1 MMA issuer (+ TMEM owner), warp 2 weight producer, warps 3-18 epilogue
 // (chunk parity x 2 accumulator halves x 4 TMEM lane quarters).  Accumulators are double-buffered in TMEM (2 x 2 x BN columns).
 // Slab atoms (64 channels each) sit in a ring of three and are released as soon as their nine taps are issued; weight blocks
-// stream through a 6-12 deep ring.  Default: conv_slab2_kernel, clusters of two CTAs sharing one weight stream through
-// tcgen05.mma.cta_group::2 (below); SUNB_CONV_SLAB_2CTA=0 selects the single-CTA kernel, SUNB_CONV_SLAB=0 the GEMM fall-back.
+// stream through a 6-12 deep ring.  The kernel runs as clusters of two CTAs sharing one weight stream through
+// tcgen05.mma.cta_group::2 (the single-CTA predecessor of round 1 measured 0.61 vs 0.70 of the bf16 peak and was removed).
 #include "common.cuh"
 
 #include <cuda.h>
-#include <stdlib.h>
 
 int sunb_encode_tensor_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                            const cuuint32_t* box);     // gemm_tc.cu
@@ -135,172 +134,6 @@ struct SlabGeom {
     int b_stages;
     int tiles;        // images * bands
 };
-
-template <int BN>
-__global__ void __launch_bounds__(THREADS, 1)
-conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p,
-                 const SlabGeom g) {
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const int KC = p.K / 64;
-    constexpr uint32_t B_BYTES = BN * 128;
-    const uint32_t bring = base + ATOM_SLOTS * g.atom_bytes;
-    const uint32_t bars = bring + g.b_stages * B_BYTES;
-    auto atom_full = [&](int s) { return bars + 8u * s; };
-    auto atom_empty = [&](int s) { return bars + 8u * (3 + s); };
-    auto acc_full = [&](int a) { return bars + 8u * (6 + a); };
-    auto acc_empty = [&](int a) { return bars + 8u * (8 + a); };
-    auto b_full = [&](int s) { return bars + 8u * (10 + s); };
-    auto b_empty = [&](int s) { return bars + 8u * (18 + s); };
-    const uint32_t tmem_slot_addr = bars + 8u * 26;
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot_addr - smem_u32(smem_raw)));
-    constexpr int TMEM_COLS = 4 * BN;      // 2 buffers x 2 halves x BN (256 or 512: powers of two)
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) {
-        for (int s = 0; s < ATOM_SLOTS; ++s) { mbar_init(atom_full(s), 1); mbar_init(atom_empty(s), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(acc_full(a), 1); mbar_init(acc_empty(a), EPI_WARPS); }
-        for (int s = 0; s < g.b_stages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot_addr), "n"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    const int nblk = 9 * KC;
-
-    if (warp == 0) {
-        // ================================================================ slab producer
-        if (elect_one()) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-        __syncwarp();
-        uint32_t ai = 0;
-        for (int tile = blockIdx.x; tile < g.tiles; tile += gridDim.x) {
-            const int img = tile / g.bands, y0 = (tile % g.bands) * g.RB;
-            for (int kc = 0; kc < KC; ++kc, ++ai) {
-                const int s = ai % ATOM_SLOTS, ph = (ai / ATOM_SLOTS) & 1;
-                mbar_wait(atom_empty(s), ph ^ 1);
-                if (elect_one()) {
-                    mbar_expect_tx(atom_full(s), g.atom_bytes);
-                    tma_load_4d(base + s * g.atom_bytes, &tmA, atom_full(s), kc * 64, -1, y0 - 1, img);
-                }
-                __syncwarp();
-            }
-        }
-    } else if (warp == 2) {
-        // ================================================================ weight producer: (tap, 64-channel) blocks
-        if (elect_one()) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-        __syncwarp();
-        uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < g.tiles; tile += gridDim.x) {
-            for (int blk = 0; blk < nblk; ++blk, ++it) {
-                const int s = it % g.b_stages, ph = (it / g.b_stages) & 1;
-                mbar_wait(b_empty(s), ph ^ 1);
-                if (elect_one()) {
-                    mbar_expect_tx(b_full(s), B_BYTES);
-                    tma_load_2d(bring + s * B_BYTES, &tmB, b_full(s), (blk / 9) * 64, (blk % 9) * p.N);    // (kc, tap) order
-                }
-                __syncwarp();
-            }
-        }
-    } else if (warp == 1) {
-        // ================================================================ MMA issuer
-        constexpr uint32_t idesc = make_idesc(128, BN);
-        uint32_t it = 0, ai = 0;
-        int lt = 0;
-        for (int tile = blockIdx.x; tile < g.tiles; tile += gridDim.x, ++lt) {
-            const int acc = lt & 1, aph = (lt >> 1) & 1;
-            mbar_wait(acc_empty(acc), aph ^ 1);
-            tc_fence_after();
-            const uint32_t d0 = tmem_base + acc * 2 * BN;
-            for (int kc = 0; kc < KC; ++kc, ++ai) {
-                const int s = ai % ATOM_SLOTS, ph = (ai / ATOM_SLOTS) & 1;
-                mbar_wait(atom_full(s), ph);
-                tc_fence_after();
-                const uint32_t atom = base + s * g.atom_bytes;
-                for (int tap = 0; tap < 9; ++tap, ++it) {
-                    const int bs = it % g.b_stages, bph = (it / g.b_stages) & 1;
-                    mbar_wait(b_full(bs), bph);
-                    tc_fence_after();
-                    const uint32_t a_addr = atom + ((tap / 3) * g.P + tap % 3) * 128;
-                    const uint32_t b_addr = bring + bs * B_BYTES;
-                    if (elect_one()) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-#pragma unroll
-                            for (int half = 0; half < 2; ++half)
-                                umma_bf16(d0 + half * BN, make_sw128_desc(a_addr + half * 128 * 128 + k * 32),
-                                          make_sw128_desc(b_addr + k * 32), idesc, (kc | tap | k) ? 1u : 0u);
-                        }
-                        umma_commit(b_empty(bs));
-                    }
-                    __syncwarp();
-                }
-                if (elect_one()) umma_commit(atom_empty(s));       // the atom's slot refills while the next atom / tile computes
-                __syncwarp();
-            }
-            if (elect_one()) umma_commit(acc_full(acc));
-            __syncwarp();
-        }
-    } else {
-        // ================================================================ epilogue: warps 3..10
-        const int q = warp & 3;                      // TMEM lane quarter this warp may read
-        const int half = ((warp - 3) >> 2) & 1;
-        const int c0 = (warp - 3) >> 3;              // first 32-column chunk of this warp
-        const int r = half * 128 + q * 32 + lane;    // raster position inside the band
-        const int yy = r / g.P, xx = r - yy * g.P;
-        int lt = 0;
-        for (int tile = blockIdx.x; tile < g.tiles; tile += gridDim.x, ++lt) {
-            const int acc = lt & 1, aph = (lt >> 1) & 1;
-            const int img = tile / g.bands, y0 = (tile % g.bands) * g.RB;
-            const bool valid = (yy < g.RB) && (xx < p.W) && (y0 + yy < p.H);
-            const int m = valid ? (img * p.H + y0 + yy) * p.W + xx : p.M;
-            mbar_wait(acc_full(acc), aph);
-            tc_fence_after();
-#pragma unroll 1
-            for (int c = c0; c < BN / 32; c += CSTEP) {
-                float v[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * BN + half * BN + c * 32), v);
-                if (c + CSTEP >= BN / 32) {          // this warp's last chunk is in registers: release the TMEM buffer
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(acc_empty(acc));
-                }
-                epilogue_row<32>(p, 0, m, c * 32, v);
-            }
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
-    }
-}
-
-template <int BN>
-int launch(const GemmParams& p, const SlabGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmB, int smem, cudaStream_t stream) {
-    static int configured = 0;
-    if (configured < smem) {
-        SUNB_CHECK_CUDA(cudaFuncSetAttribute(conv_slab_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = smem;
-    }
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        SUNB_CHECK_CUDA(cudaGetDevice(&dev));
-        SUNB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    }
-    const int grid = g.tiles < sms ? g.tiles : sms;
-    conv_slab_kernel<BN><<<grid, THREADS, smem, stream>>>(tmA, tmB, p, g);
-    SUNB_CHECK_CUDA(cudaGetLastError());
-    return SUNB_OK;
-}
-
 
 // ------------------------------------------------------------------------------------------------------------------
 // 2-CTA variant: a cluster of two CTAs (one TPC) works on two bands with ONE weight stream.  Each CTA loads its own
@@ -501,17 +334,8 @@ conv_slab2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
 template <int BN>
 int launch2(const GemmParams& p, const SlabGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmB2, int smem, cudaStream_t stream) {
-    static int configured = 0;
-    if (configured < smem) {
-        SUNB_CHECK_CUDA(cudaFuncSetAttribute(conv_slab2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = smem;
-    }
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        SUNB_CHECK_CUDA(cudaGetDevice(&dev));
-        SUNB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    SUNB_TRY(sunb_opt_in_smem(reinterpret_cast<const void*>(&conv_slab2_kernel<BN>), smem));
+    const int sms = sunb_num_sms();
     const int pairs = (g.tiles + 1) / 2, cl = sms / 2;
     const int grid = 2 * (pairs < cl ? pairs : cl);
     conv_slab2_kernel<BN><<<grid, THREADS, smem, stream>>>(tmA, tmB2, p, g);
@@ -523,12 +347,6 @@ int launch2(const GemmParams& p, const SlabGeom& g, const CUtensorMap& tmA, cons
 
 // 1 when the problem fits the slab kernel (then sunb_launch_conv_slab runs it), 0 to keep the tap-per-K-block GEMM
 int sunb_conv_slab_supported(const GemmParams& p) {
-    static int enabled = -1;
-    if (enabled < 0) {
-        const char* e = getenv("SUNB_CONV_SLAB");
-        enabled = (e && e[0] == '0') ? 0 : 1;
-    }
-    if (!enabled) return 0;
     if (p.a_mode != 1 || p.taps != 9 || p.groups != 1 || p.out_map != 0) return 0;
     if (!(p.K == 64 || p.K == 128) || !(p.N == 64 || p.N == 128)) return 0;
     if (p.W + 2 > 128 || p.H < 1 || p.M % (p.H * p.W) != 0) return 0;
@@ -553,12 +371,7 @@ int sunb_launch_conv_slab(const GemmParams& p, cudaStream_t stream) {
     const int BN = p.N;
     // the junk rows of the second accumulator read up to 2P+2 rows past the 256-row window: keep that inside the allocation
     const int slab_total = ATOM_SLOTS * g.atom_bytes;
-    static int two_cta = -1;
-    if (two_cta < 0) {
-        const char* e = getenv("SUNB_CONV_SLAB_2CTA");
-        two_cta = (e && e[0] == '0') ? 0 : 1;
-    }
-    const bool pair = two_cta && g.tiles >= 2;
+    const bool pair = true;      // cta_group::2 pairs share one weight stream (a lone last tile is padded with an empty partner)
     const int b_block = (pair ? BN / 2 : BN) * 128;
     int b_stages = (SMEM_LIMIT - 1024 - 512 - slab_total) / b_block;
     if (b_stages > (pair ? 16 : 8)) b_stages = pair ? 16 : 8;
@@ -580,6 +393,5 @@ int sunb_launch_conv_slab(const GemmParams& p, cudaStream_t stream) {
         cuuint32_t box[2] = {64, (cuuint32_t)(pair ? BN / 2 : BN)};
         SUNB_TRY(sunb_encode_tensor_map(&tmB, p.Wt, 2, dims, strides, box));
     }
-    if (pair) return BN == 64 ? launch2<64>(p, g, tmA, tmB, smem, stream) : launch2<128>(p, g, tmA, tmB, smem, stream);
-    return BN == 64 ? launch<64>(p, g, tmA, tmB, smem, stream) : launch<128>(p, g, tmA, tmB, smem, stream);
+    return BN == 64 ? launch2<64>(p, g, tmA, tmB, smem, stream) : launch2<128>(p, g, tmA, tmB, smem, stream);
 }

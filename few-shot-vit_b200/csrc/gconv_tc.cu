@@ -17,7 +17,6 @@
 #include "common.cuh"
 
 #include <cuda.h>
-#include <stdlib.h>
 
 namespace {
 
@@ -153,7 +152,7 @@ __device__ __forceinline__ void load32_bf16(const bf16* p, float* v) {
 // x, y, y2, aux: bf16 [B*400, ld] NHWC rows; wg: bf16 [8 groups][9 taps][32 n][32 k] (sunb_gconv_pack)
 __global__ void __launch_bounds__(THREADS, 1)
 gconv3x3_tc_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ wg, bf16* __restrict__ y, int ldy,
-                   bf16* __restrict__ y2, int ldy2, const bf16* __restrict__ aux, int ldaux, int B, int act, int dact, int dbg) {
+                   bf16* __restrict__ y2, int ldy2, const bf16* __restrict__ aux, int ldaux, int B, int act, int dact) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -212,7 +211,7 @@ gconv3x3_tc_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__
         // the whole warp walks the pipeline; one elected lane issues (keeps the MMA sequence in uniform registers)
         {
             constexpr uint32_t idesc = make_idesc(128, GC);
-            const uint64_t a_desc0 = make_noswz_desc((dbg & 8) ? 2 * PLANE_BYTES : PLANE_BYTES, 128);
+            const uint64_t a_desc0 = make_noswz_desc(PLANE_BYTES, 128);
             const uint64_t b_desc0 = make_noswz_desc(512, 128);
             for (int k = 0; k < n_items; ++k) {
                 const int s = k % STAGES, ph = (k / STAGES) & 1, buf = k & 1, bph = (k >> 1) & 1;
@@ -231,11 +230,9 @@ gconv3x3_tc_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__
                         if (elect_one()) {
 #pragma unroll
                         for (int tap = 0; tap < 9; ++tap) {
-                            if ((dbg & 1) && tap > 0) break;
 #pragma unroll
                             for (int ks = 0; ks < 2; ++ks) {
-                                uint32_t a_addr = a_tile + ks * 2 * PLANE_BYTES + ((tap / 3) * HP + tap % 3) * 16;
-                                if (dbg & 8) a_addr = a_tile + tap * 128;      // timing experiment: 128-byte aligned core matrices
+                                const uint32_t a_addr = a_tile + ks * 2 * PLANE_BYTES + ((tap / 3) * HP + tap % 3) * 16;
                                 const uint32_t b_addr = b_grp + tap * W_TAP_BYTES + ks * 2 * 512;
                                 umma_bf16(d, a_desc0 | (uint64_t)((a_addr >> 4) & 0x3FFF), b_desc0 | (uint64_t)((b_addr >> 4) & 0x3FFF),
                                           idesc, (tap | ks) != 0);
@@ -261,7 +258,7 @@ gconv3x3_tc_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__
             const bf16* src = x + (size_t)img * NPIX * ldx + gp * 2 * GC;
             const uint32_t slab = slab0 + s * SLAB_BYTES;
 #pragma unroll 5
-            for (int i = ltid; i < ((dbg & 4) ? 0 : NPIX * 8); i += LOAD_WARPS * 32) {
+            for (int i = ltid; i < NPIX * 8; i += LOAD_WARPS * 32) {
                 const int p = i >> 3, c = i & 7;
                 const int py = p / HW, px = p - py * HW;
                 cp_async16(slab + (c >> 2) * GROUP_BYTES + (c & 3) * PLANE_BYTES + ((py + 1) * HP + px + 1) * 16,
@@ -310,190 +307,6 @@ gconv3x3_tc_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__
                     __syncwarp();
                     if (lane == 0) mbar_arrive(acc_empty(buf, g2));
                 }
-                if (valid && !(dbg & 2)) {
-                    const size_t row = (size_t)img * NPIX + oy * HW + ox;
-                    if (y2) store32_bf16(y2 + row * ldy2 + ch, v);
-                    if (act == ACT_GELU) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
-                    }
-                    if (aux) {
-                        float a[32];
-                        load32_bf16(aux + row * ldaux + ch, a);
-                        if (dact == ACT_GELU) {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] *= gelu_grad(a[i]);
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] *= act_grad(a[i], dact);
-                        }
-                    }
-                    store32_bf16(y + row * ldy + ch, v);
-                }
-            }
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
-    }
-}
-
-
-// ------------------------------------------------------------------------------------------------------------------
-// TMA-fed variant (SUNB_GCONV_TMA=1).  The pair of groups is 64 channels = one 128-byte row, so the haloed raster is ONE 4-D TMA box
-// (64 ch, 22, 22, 1 image) at coordinates (-1, -1) with hardware zero fill, landing as a K-major SWIZZLE_128B operand whose row
-// index is the raster position -- the layout conv_slab.cu uses.  A tap is the slab read through a descriptor shifted by whole
-// 128-byte rows; group g2 / K step ks select the 32-byte column block inside the row (+64*g2 + 32*ks).  No loader warps: the
-// freed threads are 16 drain warps (2 per TMEM lane quarter and group, splitting the tiles by parity) at 112 registers.
-constexpr int T_STAGE_BYTES = 62464;                 // 484 rows x 128 B = 61,952, rounded up to the 1 KB swizzle period
-constexpr int T_W_TAP_BYTES = 32 * 128;              // weights of one tap for the pair: [32 n][64 k of group 0 | group 1] bf16, SW128
-constexpr int T_W_BYTES = 9 * T_W_TAP_BYTES;         // 36,864
-constexpr int T_EPI_WARPS = 16;
-constexpr int T_THREADS = 32 * (2 + T_EPI_WARPS);    // producer warp, MMA warp, drain warps
-constexpr int T_SMEM_BYTES = 1024 + STAGES * T_STAGE_BYTES + T_W_BYTES + BAR_BYTES;
-
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-
-__global__ void __launch_bounds__(T_THREADS, 1)
-gconv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmX, const bf16* __restrict__ wg, bf16* __restrict__ y, int ldy,
-                    bf16* __restrict__ y2, int ldy2, const bf16* __restrict__ aux, int ldaux, int B, int act, int dact) {
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t wsm = base + STAGES * T_STAGE_BYTES;
-    const uint32_t bars = wsm + T_W_BYTES;
-    auto full_bar = [&](int s) { return bars + 8u * s; };
-    auto empty_bar = [&](int s) { return bars + 8u * (3 + s); };
-    auto acc_full = [&](int buf, int g2) { return bars + 8u * (6 + buf * 2 + g2); };
-    auto acc_empty = [&](int buf, int g2) { return bars + 8u * (10 + buf * 2 + g2); };
-    const uint32_t tmem_slot_addr = bars + 8u * 14;
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * T_STAGE_BYTES + T_W_BYTES + 8 * 14);
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int gp = blockIdx.x & 3;
-    const int img0 = blockIdx.x >> 2, img_step = gridDim.x >> 2;
-    const int n_items = img0 < B ? (B - img0 + img_step - 1) / img_step : 0;
-
-    // weights of the pair, hand-swizzled: element (tap, n, kk = g2*32 + k) at tap*4096 + n*128 + ((kk>>3 ^ n&7) << 4) + (kk&7)*2
-    {
-        uint8_t* wdst = base_ptr + STAGES * T_STAGE_BYTES;
-        for (int i = tid; i < 2 * 9 * GC * 4; i += T_THREADS) {
-            const int c = i & 3, n = (i >> 2) & 31, gt = i >> 7;          // gt = g2 * 9 + tap; c = 16-byte chunk of the group's 32 k
-            const int g2 = gt / 9, tap = gt - g2 * 9;
-            const uint4 u = *reinterpret_cast<const uint4*>(wg + ((size_t)((gp * 2 + g2) * 9 + tap) * GC + n) * GC + c * 8);
-            const int chunk = g2 * 4 + c;                                  // 16-byte chunk index inside the 128-byte row
-            *reinterpret_cast<uint4*>(wdst + tap * T_W_TAP_BYTES + n * 128 + ((chunk ^ (n & 7)) << 4)) = u;
-        }
-    }
-    if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int b = 0; b < 2; ++b)
-            for (int g2 = 0; g2 < 2; ++g2) { mbar_init(acc_full(b, g2), 1); mbar_init(acc_empty(b, g2), T_EPI_WARPS / 2); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot_addr), "n"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    fence_async_proxy();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        // ================================================================ TMA producer: one haloed box per item
-        if (elect_one()) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
-        __syncwarp();
-        for (int k = 0; k < n_items; ++k) {
-            const int s = k % STAGES, ph = (k / STAGES) & 1;
-            mbar_wait(empty_bar(s), ph ^ 1);
-            if (elect_one()) {
-                mbar_expect_tx(full_bar(s), PLANE_ROWS * 128);
-                tma_load_4d(base + s * T_STAGE_BYTES, &tmX, full_bar(s), gp * 2 * GC, -1, -1, img0 + k * img_step);
-            }
-            __syncwarp();
-        }
-    } else if (warp == 1) {
-        // ================================================================ MMA issuer
-        constexpr uint32_t idesc = make_idesc(128, GC);
-        for (int k = 0; k < n_items; ++k) {
-            const int s = k % STAGES, ph = (k / STAGES) & 1, buf = k & 1, bph = (k >> 1) & 1;
-            mbar_wait(full_bar(s), ph);
-            tc_fence_after();
-            const uint32_t slab = base + s * T_STAGE_BYTES;
-#pragma unroll 1
-            for (int g2 = 0; g2 < 2; ++g2) {
-                mbar_wait(acc_empty(buf, g2), bph ^ 1);
-                tc_fence_after();
-#pragma unroll 1
-                for (int tile = 0; tile < M_TILES; ++tile) {
-                    const uint32_t d = tmem_base + buf * 256 + g2 * 128 + tile * GC;
-                    const uint32_t a_tile = slab + tile * 128 * 128 + g2 * 64;
-                    const uint32_t b_grp = wsm + g2 * 64;
-                    if (elect_one()) {
-#pragma unroll
-                        for (int tap = 0; tap < 9; ++tap) {
-#pragma unroll
-                            for (int ks = 0; ks < 2; ++ks) {
-                                const uint32_t a_addr = a_tile + ((tap / 3) * HP + tap % 3) * 128 + ks * 32;
-                                const uint32_t b_addr = b_grp + tap * T_W_TAP_BYTES + ks * 32;
-                                umma_bf16(d, make_sw128_desc(a_addr), make_sw128_desc(b_addr), idesc, (tap | ks) != 0);
-                            }
-                        }
-                    }
-                    __syncwarp();
-                }
-                if (elect_one()) umma_commit(acc_full(buf, g2));
-                __syncwarp();
-            }
-            if (elect_one()) umma_commit(empty_bar(s));
-            __syncwarp();
-        }
-    } else {
-        // ================================================================ drain: (tile parity) x 2 groups x 4 TMEM lane quarters
-        const int e = warp - 2;
-        const int g2 = (e >> 2) & 1, q = warp & 3, t0 = e >> 3;
-        const int ch = (gp * 2 + g2) * GC;
-        const int last_tile = min(M_TILES - 1, (LAST_ROW - q * 32) / 128);
-        const int my_last = last_tile - ((last_tile - t0) & 1);
-        for (int k = 0; k < n_items; ++k) {
-            const int buf = k & 1, bph = (k >> 1) & 1;
-            const int img = img0 + k * img_step;
-            mbar_wait(acc_full(buf, g2), bph);
-            tc_fence_after();
-#pragma unroll 1
-            for (int tile = t0; tile <= last_tile; tile += 2) {
-                const int o = tile * 128 + q * 32 + lane;
-                const int oy = o / HP, ox = o - oy * HP;
-                const bool valid = (oy < HW) && (ox < HW);
-                float v[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256 + g2 * 128 + tile * GC, v);
-                if (tile == my_last) {                   // this warp's accumulators are in registers: hand the TMEM buffer back
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(acc_empty(buf, g2));
-                }
                 if (valid) {
                     const size_t row = (size_t)img * NPIX + oy * HW + ox;
                     if (y2) store32_bf16(y2 + row * ldy2 + ch, v);
@@ -520,16 +333,25 @@ gconv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmX, const bf16* __restr
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == 0) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
     }
 }
 
-}  // namespace
 
-int sunb_encode_tensor_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                           const cuuint32_t* box);     // gemm_tc.cu
+// fp32 grouped weight [256][32][3][3] -> bf16 [8][9][32 n][32 k].  transpose_flip = 1 gives the conv-transpose operand
+// for the data gradient: n = input channel, k = output channel, taps mirrored.
+__global__ void gconv_pack_kernel(const float* __restrict__ w, bf16* __restrict__ dst, int transpose_flip) {
+    const int total = 8 * 9 * GC * GC;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int k = i % GC, n = (i / GC) % GC, tap = (i / (GC * GC)) % 9, grp = i / (GC * GC * 9);
+        const int co = transpose_flip ? k : n, ci = transpose_flip ? n : k, st = transpose_flip ? 8 - tap : tap;
+        dst[i] = __float2bfloat16(w[((size_t)(grp * GC + co) * GC + ci) * 9 + st]);
+    }
+}
+
+}  // namespace
 
 int sunb_launch_gconv_tc(const bf16* x, int ldx, const bf16* wg, bf16* y, int ldy, bf16* y2, int ldy2, const bf16* aux,
                          int ldaux, int B, int act, int dact, cudaStream_t stream) {
@@ -537,48 +359,28 @@ int sunb_launch_gconv_tc(const bf16* x, int ldx, const bf16* wg, bf16* y, int ld
                  "gconv3x3: operands must be 16-byte aligned with row strides that are multiples of 8 elements");
     SUNB_REQUIRE(!y2 || (ldy2 % 8 == 0 && (((size_t)y2) & 15) == 0), "gconv3x3: y2 must be 16-byte aligned");
     SUNB_REQUIRE(!aux || (ldaux % 8 == 0 && (((size_t)aux) & 15) == 0), "gconv3x3: aux must be 16-byte aligned");
-    static int use_tma = -1;
-    if (use_tma < 0) {
-        // SUNB_GCONV_TMA=1: one haloed TMA box per item + SW128 slab + 16 drain warps.  Measured equal to the default
-        // (cp.async loader warps + no-swizzle slab + 8 drain warps): 345 vs 340 us at 2500 images -- the kernel is bound by the
-        // operand fetch of its N = 32 MMAs either way.
-        const char* e = getenv("SUNB_GCONV_TMA");
-        use_tma = (e && e[0] == '1') ? 1 : 0;
-    }
-    if (use_tma) {
-        static bool configured_t = false;
-        static int sms_t = 148;
-        if (!configured_t) {
-            SUNB_CHECK_CUDA(cudaFuncSetAttribute(gconv3x3_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM_BYTES));
-            int dev = 0;
-            SUNB_CHECK_CUDA(cudaGetDevice(&dev));
-            SUNB_CHECK_CUDA(cudaDeviceGetAttribute(&sms_t, cudaDevAttrMultiProcessorCount, dev));
-            configured_t = true;
-        }
-        SUNB_REQUIRE(ldx >= 256, "gconv3x3: x rows must hold the 256 grouped channels");
-        CUtensorMap tmX;
-        cuuint64_t dims[4] = {256, (cuuint64_t)HW, (cuuint64_t)HW, (cuuint64_t)B};
-        cuuint64_t strides[3] = {(cuuint64_t)ldx * 2, (cuuint64_t)ldx * 2 * HW, (cuuint64_t)ldx * 2 * NPIX};
-        cuuint32_t box[4] = {64, (cuuint32_t)HP, (cuuint32_t)HP, 1};
-        SUNB_TRY(sunb_encode_tensor_map(&tmX, x, 4, dims, strides, box));
-        const int per_pair_t = max(1, min(sms_t / 4, B));
-        gconv3x3_tma_kernel<<<4 * per_pair_t, T_THREADS, T_SMEM_BYTES, stream>>>(tmX, wg, y, ldy, y2, ldy2, aux, ldaux, B, act, dact);
-        SUNB_CHECK_CUDA(cudaGetLastError());
-        return SUNB_OK;
-    }
-    static bool configured = false;
-    static int sms = 148, swap = 0;
-    if (!configured) {
-        const char* e = getenv("SUNB_GCONV_DBG");   // timing experiments only: 1 one tap, 2 no epilogue, 4 no loads
-        swap = e ? atoi(e) : 0;
-        SUNB_CHECK_CUDA(cudaFuncSetAttribute(gconv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        int dev = 0;
-        SUNB_CHECK_CUDA(cudaGetDevice(&dev));
-        SUNB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        configured = true;
-    }
-    const int per_pair = max(1, min(sms / 4, B));        // CTAs per group pair; 148 SMs = 4 pairs x 37
-    gconv3x3_tc_kernel<<<4 * per_pair, THREADS, SMEM_BYTES, stream>>>(x, ldx, wg, y, ldy, y2, ldy2, aux, ldaux, B, act, dact, swap);
+    SUNB_TRY(sunb_opt_in_smem(reinterpret_cast<const void*>(&gconv3x3_tc_kernel), SMEM_BYTES));
+    const int per_pair = max(1, min(sunb_num_sms() / 4, B));        // CTAs per group pair; 148 SMs = 4 pairs x 37
+    gconv3x3_tc_kernel<<<4 * per_pair, THREADS, SMEM_BYTES, stream>>>(x, ldx, wg, y, ldy, y2, ldy2, aux, ldaux, B, act, dact);
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
 }
+
+extern "C" {
+
+int sunb_gconv3x3(const void* x, int ldx, const void* wg, void* y, int ldy, void* y2, int ldy2, const void* aux, int ldaux,
+                  int B, int act, int dact, void* stream) {
+    SUNB_REQUIRE(x && wg && y && B > 0, "gconv3x3: bad arguments");
+    return sunb_launch_gconv_tc(reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<const bf16*>(wg), reinterpret_cast<bf16*>(y),
+                                ldy, reinterpret_cast<bf16*>(y2), ldy2, reinterpret_cast<const bf16*>(aux), ldaux, B, act, dact,
+                                reinterpret_cast<cudaStream_t>(stream));
+}
+
+int sunb_gconv_pack(const float* w, void* dst, int transpose_flip, void* stream) {
+    SUNB_REQUIRE(w && dst, "gconv_pack: bad arguments");
+    gconv_pack_kernel<<<72, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(w, reinterpret_cast<bf16*>(dst), transpose_flip);
+    SUNB_CHECK_CUDA(cudaGetLastError());
+    return SUNB_OK;
+}
+
+}  // extern "C"

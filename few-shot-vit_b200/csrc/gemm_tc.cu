@@ -11,14 +11,11 @@
 #include "common.cuh"
 
 #include <mutex>
-#include <stdlib.h>
 
 namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;                      // 64 bf16 = one 128-byte swizzle row
-constexpr int NUM_EPI_WARPS = 8;
-constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;   // TMA warp, MMA warp, 8 epilogue warps (2-CTA variant)
 #ifndef SUNB_EPI_WARPS1
 #define SUNB_EPI_WARPS1 16
 #endif
@@ -149,22 +146,21 @@ struct SmemLayout {
 // Persistent kernel: CTA b processes tiles b, b + gridDim.x, ...  (tile id = (m_tile * groups + g) * n_tiles + n_tile).
 // The smem ring runs continuously across tiles; two TMEM accumulators let the epilogue of tile i overlap the
 // MMAs of tile i + 1.
-// BSTAT (weight-stationary): a CTA keeps one (n-tile, group) for its whole life, loads that tile's complete weight
-// operand (all taps x K blocks) into shared memory once, and streams only activation tiles through the ring.
-template <int BN, bool BSTAT>
+// (A weight-stationary schedule and a cta_group::2 variant were measured neutral / slower in round 1 and removed.)
+template <int BN>
 __global__ void __launch_bounds__(THREADS1, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                  const __grid_constant__ CUtensorMap tmB,
                                                                  const GemmParams p, const int n_tiles,
-                                                                 const int total_tiles, const int a_stages) {
+                                                                 const int total_tiles) {
     using L = SmemLayout<BN>;
     constexpr int MAXR = L::MAX_RING;
-    const int STAGES = BSTAT ? a_stages : L::STAGES;
+    constexpr int STAGES = L::STAGES;
     constexpr uint32_t TMEM_COLS = 2 * BN;           // two accumulators; 128 / 256 / 512 columns
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-    const uint32_t bars = smem_base + L::TILE_BYTES;    // full[MAXR], empty[MAXR], acc_full[2], acc_empty[2], b_full
+    const uint32_t bars = smem_base + L::TILE_BYTES;    // full[MAXR], empty[MAXR], acc_full[2], acc_empty[2]
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + L::TILE_BYTES + 8 * (2 * MAXR + 5));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -175,14 +171,9 @@ __global__ void __launch_bounds__(THREADS1, 1) gemm_tc_kernel(const __grid_const
     auto empty_bar = [&](int s) { return bars + 8u * (MAXR + s); };
     auto acc_full = [&](int a) { return bars + 8u * (2 * MAXR + a); };
     auto acc_empty = [&](int a) { return bars + 8u * (2 * MAXR + 2 + a); };
-    const uint32_t b_full = bars + 8u * (2 * MAXR + 4);
-    // smem map: generic mode = ring of (A|B) stages; stationary mode = [nk B blocks][ring of A stages]
-    const uint32_t ring_base = BSTAT ? smem_base + nk * L::B_BYTES : smem_base;
-    constexpr uint32_t RING_STRIDE = BSTAT ? L::A_BYTES : L::STAGE_BYTES;
-    // tile schedule
-    const int slots = n_tiles * p.groups;
-    const int tile0 = BSTAT ? (blockIdx.x / slots) * slots + (blockIdx.x % slots) : blockIdx.x;
-    const int tstep = gridDim.x;                         // stationary mode: gridDim.x is a multiple of slots
+    const uint32_t ring_base = smem_base;               // ring of (A|B) stages
+    constexpr uint32_t RING_STRIDE = L::STAGE_BYTES;
+    const int tile0 = blockIdx.x, tstep = gridDim.x;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -193,7 +184,6 @@ __global__ void __launch_bounds__(THREADS1, 1) gemm_tc_kernel(const __grid_const
             mbar_init(acc_full(a), 1);
             mbar_init(acc_empty(a), EPI_WARPS1);
         }
-        mbar_init(b_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {   // whole warp allocates TMEM, base address lands in shared memory
@@ -218,17 +208,6 @@ __global__ void __launch_bounds__(THREADS1, 1) gemm_tc_kernel(const __grid_const
             const int tiles_x = p.a_mode ? p.W / p.bw : 1;
             const int spi = p.a_mode ? tiles_x * (p.H / p.bh) : 1;
             uint32_t it = 0;
-            if (BSTAT && tile0 < total_tiles) {          // the whole weight operand of this CTA's (n-tile, group), once
-                const int n0 = (tile0 % n_tiles) * BN;
-                const int g = (tile0 / n_tiles) % p.groups;
-                if (elect_one()) {
-                    mbar_expect_tx(b_full, nk * L::B_BYTES);
-                    for (int kb = 0; kb < nk; ++kb)
-                        tma_load_2d(smem_base + kb * L::B_BYTES, &tmB, b_full, (kb % kpt) * BK,
-                                    (g * p.taps + kb / kpt) * p.N + n0);
-                }
-                __syncwarp();
-            }
             for (int tile = tile0; tile < total_tiles; tile += tstep) {
                 const int n0 = (tile % n_tiles) * BN;
                 const int g = (tile / n_tiles) % p.groups;
@@ -241,7 +220,7 @@ __global__ void __launch_bounds__(THREADS1, 1) gemm_tc_kernel(const __grid_const
                     const uint32_t b_dst = a_dst + L::A_BYTES;
                     const int tap = kb / kpt, kc = kb % kpt;
                     if (elect_one()) {
-                        mbar_expect_tx(full_bar(s), BSTAT ? L::A_BYTES : L::STAGE_BYTES);
+                        mbar_expect_tx(full_bar(s), L::STAGE_BYTES);
                         if (p.a_mode == 0) {
                             tma_load_2d(a_dst, &tmA, full_bar(s), g * p.a_goff + kc * BK, m_tile * BM);
                         } else {
@@ -251,7 +230,7 @@ __global__ void __launch_bounds__(THREADS1, 1) gemm_tc_kernel(const __grid_const
                             tma_load_4d(a_dst, &tmA, full_bar(s), g * p.a_goff + kc * BK, (blk % tiles_x) * p.bw + dx,
                                         (blk / tiles_x) * p.bh + dy, img0);
                         }
-                        if (!BSTAT) tma_load_2d(b_dst, &tmB, full_bar(s), kc * BK, (g * p.taps + tap) * p.N + n0);
+                        tma_load_2d(b_dst, &tmB, full_bar(s), kc * BK, (g * p.taps + tap) * p.N + n0);
                     }
                     __syncwarp();
                 }
@@ -261,7 +240,6 @@ __global__ void __launch_bounds__(THREADS1, 1) gemm_tc_kernel(const __grid_const
         {
             constexpr uint32_t idesc = make_idesc(BM, BN);
             uint32_t it = 0, lt = 0;
-            if (BSTAT && tile0 < total_tiles) mbar_wait(b_full, 0);
             for (int tile = tile0; tile < total_tiles; tile += tstep, ++lt) {
                 const uint32_t acc = lt & 1, aph = (lt >> 1) & 1;
                 mbar_wait(acc_empty(acc), aph ^ 1);       // epilogue has drained this accumulator
@@ -274,7 +252,7 @@ __global__ void __launch_bounds__(THREADS1, 1) gemm_tc_kernel(const __grid_const
                     tc_fence_after();
                     const uint32_t a_addr = ring_base + s * RING_STRIDE;
                     const uint64_t a_desc = make_sw128_desc(a_addr);
-                    const uint64_t b_desc = make_sw128_desc(BSTAT ? smem_base + kb * L::B_BYTES : a_addr + L::A_BYTES);
+                    const uint64_t b_desc = make_sw128_desc(a_addr + L::A_BYTES);
                     if (elect_one()) {
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k)   // advance 32 bytes (2 x 16-byte units) per UMMA_K = 16
@@ -323,203 +301,6 @@ __global__ void __launch_bounds__(THREADS1, 1) gemm_tc_kernel(const __grid_const
 }
 
 
-// ------------------------------------------------------------------------------------------------------------------
-// 2-CTA variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x BN tile pair.  Each CTA loads its own
-// 128 activation rows but only HALF of the weight tile (BN/2 rows); the leader CTA issues tcgen05.mma.cta_group::2 (M = 256),
-// which reads A from both CTAs' shared memory and stitches the two weight halves together, and writes each CTA's 128 rows
-// of accumulator into that CTA's TMEM.  Per SM the L2 -> SMEM traffic per K block drops from 16 KB + BN*128 B to
-// 16 KB + BN*64 B -- the fill rate, not the tensor pipe, bounds these GEMMs.
-// Barriers: full[s] lives in the leader (both CTAs' TMA loads complete_tx on it), empty[s] / acc_full[a] are signalled in
-// both CTAs by multicast tcgen05.commit, acc_empty[a] lives in the leader and collects the epilogue warps of both CTAs.
-// ------------------------------------------------------------------------------------------------------------------
-constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;     // clears the CTA-rank bit of a shared::cluster address -> leader's copy
-
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {     // every thread of both CTAs
-    __syncwarp();
-    asm volatile("barrier.cluster.arrive.release;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
-}
-__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar & PEER_MASK), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                             int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar & PEER_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                           uint32_t accumulate) {
-    const uint32_t z = 0;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(z) : "memory");
-}
-__device__ __forceinline__ void umma2_commit_both(uint32_t bar) {     // arrive on `bar` in both CTAs of the pair
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"((uint16_t)3) : "memory");
-}
-
-template <int BN>
-struct SmemLayout2 {
-    static constexpr int A_BYTES = BM * BK * 2;             // this CTA's 128 rows
-    static constexpr int B_BYTES = (BN / 2) * BK * 2;       // this CTA's half of the weight tile
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;      // 6 (BN 256) / 8 (BN 128)
-    static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;
-    static constexpr int TOTAL = TILE_BYTES + 256 + 1024;
-};
-
-template <int BN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p,
-                const int n_tiles, const int m_tiles, const int total_pairs) {
-    using L = SmemLayout2<BN>;
-    constexpr int STAGES = L::STAGES;
-    constexpr uint32_t TMEM_COLS = 2 * BN;
-
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-    const uint32_t bars = smem_base + L::TILE_BYTES;    // full[S], empty[S], acc_full[2], acc_empty[2]
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + L::TILE_BYTES + 8 * (2 * STAGES + 4));
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
-    const int kpt = (p.K + BK - 1) / BK;
-    const int nk = p.taps * kpt;
-    const int pair0 = blockIdx.x >> 1, pstep = gridDim.x >> 1;
-
-    auto full_bar = [&](int s) { return bars + 8u * s; };
-    auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
-    auto acc_full = [&](int a) { return bars + 8u * (2 * STAGES + a); };
-    auto acc_empty = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), 1);
-        }
-        for (int a = 0; a < 2; ++a) {
-            mbar_init(acc_full(a), 1);
-            mbar_init(acc_empty(a), 2 * NUM_EPI_WARPS);      // epilogue warps of both CTAs
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {   // the same warp of both CTAs allocates the pair's TMEM columns
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
-                     ::"r"(smem_u32((const void*)tmem_slot)), "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    cluster_sync_all();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-            const int nimg = p.a_mode ? BM / (p.bw * p.bh) : 1;
-            const int tiles_x = p.a_mode ? p.W / p.bw : 1;
-            const int spi = p.a_mode ? tiles_x * (p.H / p.bh) : 1;
-            uint32_t it = 0;
-            for (int t = pair0; t < total_pairs; t += pstep) {
-                const int n0 = (t % n_tiles) * BN;
-                const int g = (t / n_tiles) % p.groups;
-                const int m_tile = 2 * (t / (n_tiles * p.groups)) + (int)rank;
-                for (int kb = 0; kb < nk; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(empty_bar(s), ph ^ 1);
-                    const uint32_t a_dst = smem_base + s * L::STAGE_BYTES;
-                    const uint32_t b_dst = a_dst + L::A_BYTES;
-                    if (rank == 0) mbar_expect_tx(full_bar(s), 2 * L::STAGE_BYTES);     // bytes of both CTAs
-                    const int tap = kb / kpt, kc = kb % kpt;
-                    if (p.a_mode == 0) {
-                        tma2_load_2d(a_dst, &tmA, full_bar(s), g * p.a_goff + kc * BK, m_tile * BM);
-                    } else {
-                        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-                        const int blk = m_tile % spi, img0 = (m_tile / spi) * nimg;
-                        tma2_load_4d(a_dst, &tmA, full_bar(s), g * p.a_goff + kc * BK, (blk % tiles_x) * p.bw + dx,
-                                     (blk / tiles_x) * p.bh + dy, img0);
-                    }
-                    tma2_load_2d(b_dst, &tmB, full_bar(s), kc * BK, (g * p.taps + tap) * p.N + n0 + (int)rank * (BN / 2));
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
-            constexpr uint32_t idesc = make_idesc(2 * BM, BN);
-            uint32_t it = 0, lt = 0;
-            for (int t = pair0; t < total_pairs; t += pstep, ++lt) {
-                const uint32_t acc = lt & 1, aph = (lt >> 1) & 1;
-                mbar_wait(acc_empty(acc), aph ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < nk; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(full_bar(s), ph);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_base + s * L::STAGE_BYTES;
-                    const uint64_t a_desc = make_sw128_desc(a_addr);
-                    const uint64_t b_desc = make_sw128_desc(a_addr + L::A_BYTES);
-#pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)
-                        umma2_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) ? 1u : 0u);
-                    umma2_commit_both(empty_bar(s));
-                }
-                umma2_commit_both(acc_full(acc));
-            }
-        }
-    } else {
-        const int q = warp & 3;
-        const int half = (warp - 2) >> 2;
-        const int r = q * 32 + lane;
-        uint32_t lt = 0;
-        for (int t = pair0; t < total_pairs; t += pstep, ++lt) {
-            const int n0 = (t % n_tiles) * BN;
-            const int g = (t / n_tiles) % p.groups;
-            const int m_tile = 2 * (t / (n_tiles * p.groups)) + (int)rank;
-            const uint32_t acc = lt & 1, aph = (lt >> 1) & 1;
-            mbar_wait(acc_full(acc), aph);
-            tc_fence_after();
-            int mm = p.a_mode ? conv_tile_row_to_pixel(p, m_tile, r) : m_tile * BM + r;
-            if (m_tile >= m_tiles) mm = p.M;               // odd tile count: the last pair's second half is empty
-#pragma unroll 1
-            for (int c = half; c < BN / 32; c += 2) {
-                if (n0 + c * 32 >= p.N) break;
-                float v[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
-                epilogue_row<32>(p, g, mm, n0 + c * 32, v);
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(acc_empty(acc) & PEER_MASK);      // the leader's barrier
-        }
-    }
-
-    tc_fence_before();
-    cluster_sync_all();        // nobody leaves (or frees TMEM) while the partner may still read its smem / signal its barriers
-    if (warp == 1) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
-    }
-}
-
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -557,26 +338,10 @@ int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* d
     return SUNB_OK;
 }
 
-int num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
-}
-
 template <int BN>
 int launch_bn(const GemmParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB, cudaStream_t stream) {
     using L = SmemLayout<BN>;
-    static bool configured = false;
-    if (!configured) {
-        SUNB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-        SUNB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-        configured = true;
-    }
+    SUNB_TRY(sunb_opt_in_smem(reinterpret_cast<const void*>(&gemm_tc_kernel<BN>), L::TOTAL));
     const int n_tiles = (p.N + BN - 1) / BN;
     int m_tiles = (p.M + BM - 1) / BM;
     if (p.a_mode) {       // spatial blocks x groups of 128/(bw*bh) images
@@ -585,47 +350,9 @@ int launch_bn(const GemmParams& p, const CUtensorMap& tmA, const CUtensorMap& tm
     }
     const long total = (long)n_tiles * m_tiles * p.groups;
     SUNB_REQUIRE(total < (1L << 31), "gemm_tc: too many tiles");
-    const int sms = num_sms();
-    static int use_2cta = -1;
-    if (use_2cta < 0) { const char* e = getenv("SUNB_GEMM_2CTA"); use_2cta = (e && e[0] == '1') ? 1 : 0; }
-    if (use_2cta && BN >= 128 && m_tiles >= 2) {
-        using L2 = SmemLayout2<BN>;
-        static bool configured2 = false;
-        if (!configured2) {
-            SUNB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L2::TOTAL));
-            configured2 = true;
-        }
-        CUtensorMap tmB2;      // weight boxes of BN/2 rows: each CTA of the pair fetches one half
-        {
-            cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.groups * p.taps * p.N};
-            cuuint64_t strides[1] = {(cuuint64_t)p.ldw * 2};
-            cuuint32_t box[2] = {BK, (cuuint32_t)(BN / 2)};
-            SUNB_TRY(encode_map(&tmB2, p.Wt, 2, dims, strides, box));
-        }
-        const long pairs = (long)n_tiles * ((m_tiles + 1) / 2) * p.groups;
-        const int cl = sms / 2;
-        const int grid = 2 * (int)(pairs < cl ? pairs : cl);
-        gemm_tc2_kernel<BN><<<grid, NUM_THREADS, L2::TOTAL, stream>>>(tmA, tmB2, p, n_tiles, m_tiles, (int)pairs);
-        SUNB_CHECK_CUDA(cudaGetLastError());
-        return SUNB_OK;
-    }
-    // weight-stationary schedule when the (n-tile, group) weight operand fits beside >= 3 activation stages and every
-    // CTA gets enough m-tiles to amortise loading it
-    const int nk = p.taps * ((p.K + BK - 1) / BK);
-    const long b_bytes = (long)nk * L::B_BYTES;
-    const int slots = n_tiles * p.groups;
-    static int allow_bstat = -1;
-    // weight-stationary schedule is opt-in (SUNB_GEMM_BSTAT=1): measured neutral on B200 once conv tiles became single TMA boxes
-    if (allow_bstat < 0) { const char* e = getenv("SUNB_GEMM_BSTAT"); allow_bstat = (e && e[0] == '1') ? 1 : 0; }
-    if (allow_bstat && b_bytes <= L::TILE_BYTES - 3 * L::A_BYTES && slots <= sms && m_tiles >= 4 * (sms / slots)) {
-        int a_stages = (int)((L::TILE_BYTES - b_bytes) / L::A_BYTES);
-        if (a_stages > 10) a_stages = 10;
-        const int grid = (sms / slots) * slots;
-        gemm_tc_kernel<BN, true><<<grid, THREADS1, L::TOTAL, stream>>>(tmA, tmB, p, n_tiles, (int)total, a_stages);
-    } else {
-        const int grid = (int)(total < sms ? total : sms);     // persistent: one CTA per SM
-        gemm_tc_kernel<BN, false><<<grid, THREADS1, L::TOTAL, stream>>>(tmA, tmB, p, n_tiles, (int)total, L::STAGES);
-    }
+    const int sms = sunb_num_sms();
+    const int grid = (int)(total < sms ? total : sms);     // persistent: one CTA per SM
+    gemm_tc_kernel<BN><<<grid, THREADS1, L::TOTAL, stream>>>(tmA, tmB, p, n_tiles, (int)total);
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
 }

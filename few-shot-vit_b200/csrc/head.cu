@@ -143,11 +143,7 @@ int sunb_launch_episode_logits(const float* feat_shot, const float* feat_query, 
     SUNB_REQUIRE(metric >= 0 && metric <= 2, "episode_logits: metric must be 0 (dot), 1 (cos) or 2 (sqr)");
     const size_t smem = (size_t)way * D * sizeof(float);
     SUNB_REQUIRE(smem <= 200 * 1024, "episode_logits: way*D too large for shared memory");
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        SUNB_CHECK_CUDA(cudaFuncSetAttribute(episode_logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    if (smem > 48 * 1024) SUNB_TRY(sunb_opt_in_smem(reinterpret_cast<const void*>(&episode_logits_kernel), (int)smem));
     int qs = E >= 64 ? 1 : (Q + 7) / 8;           // few episodes: split the queries of an episode over several blocks
     if (qs > 16) qs = 16;
     episode_logits_kernel<<<dim3(E, qs), 256, smem, stream>>>(feat_shot, feat_query, logits, way, shot, Q, D, metric, temp_dev,
@@ -304,11 +300,9 @@ int sunb_launch_episode_logits_bwd(const float* feat_shot, const float* feat_que
     SUNB_REQUIRE(E > 0 && way > 0 && shot > 0 && Q > 0 && D > 0 && metric >= 0 && metric <= 2, "episode_logits_bwd: bad shape");
     const size_t smem = (size_t)(2 * way * D + 8 * D) * sizeof(float);
     SUNB_REQUIRE(smem <= 200 * 1024, "episode_logits_bwd: way*D too large for shared memory");
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        SUNB_CHECK_CUDA(cudaFuncSetAttribute(episode_logits_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SUNB_CHECK_CUDA(cudaFuncSetAttribute(episode_logits_bwd_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+    if (smem > 48 * 1024) {
+        SUNB_TRY(sunb_opt_in_smem(reinterpret_cast<const void*>(&episode_logits_bwd_kernel), (int)smem));
+        SUNB_TRY(sunb_opt_in_smem(reinterpret_cast<const void*>(&episode_logits_bwd_finish_kernel), (int)smem));
     }
     // an episode is split over QS blocks (8 queries per block and pass) so that a few episodes still fill the GPU
     int qs = (Q + 7) / 8;

@@ -242,11 +242,7 @@ int sunb_launch_stem_in_tc(const float* x, const float* w1, const float* b1, con
     SUNB_REQUIRE(B > 0, "stem_in: B must be positive");
     SUNB_REQUIRE((((size_t)b1) & 15) == 0 && (((size_t)bd) & 15) == 0, "stem_in: biases must be 16-byte aligned");
     SUNB_REQUIRE((((size_t)a1) & 31) == 0 && (((size_t)idn) & 31) == 0, "stem_in: outputs must be 32-byte aligned");
-    static bool configured = false;
-    if (!configured) {
-        SUNB_CHECK_CUDA(cudaFuncSetAttribute(stem_in_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        configured = true;
-    }
+    SUNB_TRY(sunb_opt_in_smem(reinterpret_cast<const void*>(&stem_in_tc_kernel), SMEM_BYTES));
     const int n_tiles = (B * NPIX + 127) / 128;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);

@@ -7,7 +7,7 @@
 
 namespace {
 
-constexpr int MAX_CPL = 4;       // classes per lane -> n_cls <= 128
+constexpr int MAX_CPL = 16;      // classes per lane -> n_cls <= 512 (miniImageNet 64, tieredImageNet 351 base classes)
 constexpr int MAX_HW = 64;
 
 __device__ __forceinline__ float warp_max(float v) {
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(256) hard_ce_bwd_kernel(const float* __restric
 
 int sunb_launch_softlabel(const float* logits, long sb, long sc, long sp, int B, int n_cls, int hw, int k, int bp,
                           double smoothing, float* out, cudaStream_t stream) {
-    SUNB_REQUIRE(B > 0 && n_cls > 0 && n_cls <= 32 * MAX_CPL, "softlabel: n_cls must be in [1,128], got %d", n_cls);
+    SUNB_REQUIRE(B > 0 && n_cls > 0 && n_cls <= 32 * MAX_CPL, "softlabel: n_cls must be in [1,512], got %d", n_cls);
     SUNB_REQUIRE(hw > 0 && hw <= MAX_HW && bp >= 0 && bp <= hw && k > 0 && k <= n_cls,
                  "softlabel: bad hw=%d bp=%d k=%d", hw, bp, k);
     const double off = smoothing / (double)n_cls;

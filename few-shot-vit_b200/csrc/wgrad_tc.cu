@@ -312,11 +312,7 @@ int make_map(CUtensorMap* map, const bf16* base, int C, int ld, const WgradParam
 template <int BN>
 int launch_w(const WgradParams& p, const CUtensorMap& tmY, const CUtensorMap& tmX, cudaStream_t stream) {
     using L = WLayout<BN>;
-    static bool configured = false;
-    if (!configured) {
-        SUNB_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-        configured = true;
-    }
+    SUNB_TRY(sunb_opt_in_smem(reinterpret_cast<const void*>(&wgrad_tc_kernel<BN>), L::TOTAL));
     const int n_tiles = (p.Nb + BN - 1) / BN, m_tiles = (p.Ma + BM - 1) / BM;
     dim3 grid(n_tiles * m_tiles, p.taps * p.groups, p.ksplit);
     wgrad_tc_kernel<BN><<<grid, NUM_THREADS, L::TOTAL, stream>>>(tmY, tmX, p, n_tiles);
@@ -345,8 +341,7 @@ int sunb_launch_wgrad_tc(WgradParams p, cudaStream_t stream) {
                              : (p.P + BKP - 1) / BKP;
     if (p.ksplit <= 0) {       // ~1.5 waves of CTAs (fewer split-K atomics than 2 waves), at least 4 K blocks per CTA
         const int tiles = n_tiles * m_tiles * p.taps * p.groups;
-        static int waves_x2 = -1;                        // CTA waves x 2 (SUNB_WGRAD_WAVES_X2).  Measured on the train step: 2 -> 11.4 ms, 3 -> 11.15, 4 -> 11.4, 6 -> 11.5
-        if (waves_x2 < 0) { const char* e = getenv("SUNB_WGRAD_WAVES_X2"); waves_x2 = e ? atoi(e) : 3; if (waves_x2 < 1) waves_x2 = 3; }
+        constexpr int waves_x2 = 3;                      // CTA waves x 2.  Measured on the train step: 2 -> 11.4 ms, 3 -> 11.15, 4 -> 11.4, 6 -> 11.5
         int ks = (waves_x2 * 74 + tiles - 1) / tiles;
         ks = ks < 1 ? 1 : ks;
         const int max_ks = kblocks / 4 > 0 ? kblocks / 4 : 1;

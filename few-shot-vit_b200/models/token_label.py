@@ -21,8 +21,21 @@ class TokenLabelOffline(nn.Module):
         self.classifier_local = models.make(classifier, **local)
 
     def forward(self, x, is_teacher=False):
+        head = self.classifier if is_teacher else self.classifier_local
+        if hasattr(self.encoder, "features"):                   # native encoder: fp32 + bf16 copies of the final features
+            f = self.encoder.features(x)
+            tokens, pooled = f["dense"], f["pooled"]            # dense is NHWC-contiguous [B,5,5,512]
+            y_token = _apply_head(head, tokens, f["dense_bf16"]).permute(0, 3, 1, 2)
+            return y_token, _apply_head(self.classifier, pooled, f["pooled_bf16"]), pooled
         dense, pooled = self.encoder(x)
         tokens = dense.permute(0, 2, 3, 1)                      # NHWC, contiguous
-        head = self.classifier if is_teacher else self.classifier_local
         y_token = head(tokens).permute(0, 3, 1, 2)
         return y_token, self.classifier(pooled), pooled
+
+
+def _apply_head(head, x, x_bf16):
+    """LinearClassifier heads take the bf16 copy the encoder's last kernel already wrote (no re-cast of the activations)."""
+    lin = getattr(head, "linear", None)
+    if isinstance(lin, nn.Linear):
+        return utils.linear(x, lin.weight, lin.bias, x_bf16=x_bf16)
+    return head(x)

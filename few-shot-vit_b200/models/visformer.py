@@ -5,8 +5,9 @@ Reference: test_phase/models/visformer.py:291-462 (class), :482-487 (factory 'vi
 output variants: pooled only (test_phase :462), (dense, pooled) (sun_meta_training/models/visformer.py:464),
 dense only (meta_tuning_sun_d/Models/models/visformer.py:461).
 
-The sub-modules below are parameter containers (they keep `.train()/.eval()`, `freeze_bn`, optimizers,
-`state_dict()/load_state_dict()` and DataParallel replication working); they never execute a torch forward.
+The sub-modules below are parameter containers (they keep `.train()/.eval()`, `freeze_bn`, optimizers and
+`state_dict()/load_state_dict()` working); they never execute a torch forward.  Multi-GPU runs are one process per GPU
+(`sunb200.dist`); wrapping the module in nn.DataParallel raises a clear error on the first replica forward.
 """
 import math
 
@@ -169,22 +170,59 @@ class Visformer(nn.Module):
                                       .div_(keep).view(batch) for _ in range(n)]
         return rs
 
-    def forward(self, x, taps=None, drop_path_scales=None):
+    # ------------------------------------------------------------------ packed-weight cache plumbing
+    def _apply(self, fn, *args, **kwargs):
+        # .cuda() / .to() / .float() replace the buffer tensors: drop the cached tensor list and the packed weights
+        self._state_list = None
+        self._engine.invalidate()
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self._state_list = None
+        self._engine.invalidate()
+        return super().load_state_dict(*args, **kwargs)
+
+    def invalidate_packed_weights(self):
+        """Force a re-pack of the eval-mode weights on the next eval forward.  Needed only when parameters or BatchNorm
+        statistics were changed by something torch's version counters do not see (CUDA-graph replays of a training step);
+        the native train path and load_state_dict/.to() call it themselves."""
+        self._engine.invalidate()
+
+    def _state_tensors(self):
+        """[(name, tensor)] of the 148 state entries; cached (tensor objects only change in _apply)."""
+        if getattr(self, "_state_list", None) is None:
+            self._state_list = list(self.state_dict(keep_vars=True).items())
+        return self._state_list
+
+    def _check_not_replica(self):
+        if getattr(self, "_is_replica", False):
+            raise RuntimeError(
+                "sunb200: nn.DataParallel replicas are not supported (the native engines hold per-device packed weights and "
+                "workspaces).  Run one process per GPU (torchrun) and shard episodes with sunb200.dist.shard_episodes; for "
+                "meta-tuning call model.encoder.enable_data_parallel() (INTEGRATION.md section 4).")
+
+    def features(self, x, taps=None, drop_path_scales=None):
+        """dict(pooled [B,512] fp32, dense NHWC [B,5,5,512] fp32 | None, pooled_bf16, dense_bf16): both precisions of the
+        final features as the last kernel emits them (the linear heads consume the bf16 copies directly)."""
+        self._check_not_replica()
         bn_eval = self._bn_in_eval()
+        want_dense = self.output != "pooled"
         if not self.training or (bn_eval and not torch.is_grad_enabled()):
             if not bn_eval:
                 raise NotImplementedError("sunb200: eval-mode module with BatchNorm layers switched to train() is not supported")
-            state = dict(self.state_dict(keep_vars=True))
-            out = self._engine.forward(state, x, want_dense=self.output != "pooled", taps=taps)
-            pooled, dense = out["pooled"], out["dense"]
-        else:
-            # BatchNorm layers put in eval() by utils.freeze_bn use their running statistics inside the training step
-            self._train_engine.frozen_bn = frozenset(n for n, m in self.named_modules()
-                                                     if isinstance(m, nn.BatchNorm2d) and not m.training)
-            rs = drop_path_scales if drop_path_scales is not None else self._drop_path_scales(x.shape[0], x.device)
-            names = [n for n, _ in self.named_parameters()]
-            params = [p for _, p in self.named_parameters()]
-            pooled, dense = _EncoderTrainFn.apply(self, x, rs, names, *params)
+            return self._engine.forward(self._state_tensors(), x, want_dense=want_dense, want_bf16=want_dense, taps=taps)
+        # BatchNorm layers put in eval() by utils.freeze_bn use their running statistics inside the training step
+        self._train_engine.frozen_bn = frozenset(n for n, m in self.named_modules()
+                                                 if isinstance(m, nn.BatchNorm2d) and not m.training)
+        rs = drop_path_scales if drop_path_scales is not None else self._drop_path_scales(x.shape[0], x.device)
+        names = [n for n, _ in self.named_parameters()]
+        params = [p for _, p in self.named_parameters()]
+        pooled, dense, pooled16, dense16 = _EncoderTrainFn.apply(self, x, rs, names, *params)
+        return {"pooled": pooled, "dense": dense, "pooled_bf16": pooled16, "dense_bf16": dense16}
+
+    def forward(self, x, taps=None, drop_path_scales=None):
+        out = self.features(x, taps=taps, drop_path_scales=drop_path_scales)
+        pooled, dense = out["pooled"], out["dense"]
         if self.output == "pooled":
             return pooled
         dense = dense.permute(0, 3, 1, 2)              # NCHW view of NHWC memory (token_label.py:50 permutes it back)
@@ -202,12 +240,16 @@ class _EncoderTrainFn(torch.autograd.Function):
         P = {n: p.detach() for n, p in zip(names, params)}
         Bf = {n: b for n, b in module.named_buffers()}
         eng = module._train_engine
-        pooled, dense, c = eng.forward(P, Bf, x.detach().contiguous().float(), rs)
+        # the native train path updates BatchNorm running statistics (and the caller's optimizer the weights) without
+        # bumping torch's version counters in every case: the eval-mode packed weights are stale from here on
+        module._engine.invalidate()
+        pooled, dense, pooled16, dense16, c = eng.forward(P, Bf, x.detach().contiguous().float(), rs)
         ctx.eng, ctx.c, ctx.P, ctx.names = eng, c, P, names
-        return pooled, dense
+        ctx.mark_non_differentiable(pooled16, dense16)
+        return pooled, dense, pooled16, dense16
 
     @staticmethod
-    def backward(ctx, dpooled, ddense):
+    def backward(ctx, dpooled, ddense, _dp16=None, _dd16=None):
         dp = dpooled.contiguous().float() if dpooled is not None else None
         dd = ddense.contiguous().float() if ddense is not None else None
         if dp is None and dd is None:

@@ -65,6 +65,20 @@ def broadcast_module_state(module: torch.nn.Module, src: int = 0, group=None):
         dist.broadcast(t.data, src=src, group=group)
 
 
+def sync_bn_buffers(module: torch.nn.Module, src: int = 0, group=None):
+    """Re-broadcast rank `src`'s BatchNorm buffers (running_mean / running_var / num_batches_tracked).  During multi-process
+    meta-tuning every rank updates its own running statistics (un-synchronised BN, as each DataParallel replica does);
+    DataParallel then keeps replica 0's.  Call this at epoch end, before a rank-sharded evaluation and before saving a
+    checkpoint, so that every rank evaluates / stores rank 0's statistics."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    for b in module.buffers():
+        dist.broadcast(b.data, src=src, group=group)
+    for m in module.modules():
+        if hasattr(m, "invalidate_packed_weights"):
+            m.invalidate_packed_weights()
+
+
 class GradComm:
     """Overlapped data-parallel gradient reduction for the native backward pass (sunb200/train.py): every ready slice of
     the flat gradient buffer is all-reduced (sum) on a dedicated stream while the compute stream keeps running the

@@ -33,14 +33,20 @@ class EncoderEngine:
 
     @staticmethod
     def _state_key(tensors):
-        return tuple((t.data_ptr(), t._version, str(t.device)) for t in tensors)
+        return tuple((t.data_ptr(), t._version) for t in tensors)
 
-    def pack(self, state: Dict[str, torch.Tensor]) -> None:
-        key = self._state_key(state.values())
+    def invalidate(self) -> None:
+        """Drop the packed weights: the next eval forward re-folds BatchNorm from the module's current state."""
+        self._key = None
+
+    def pack(self, state) -> None:
+        """state: dict or [(name, tensor)] of the encoder state entries (reference names)."""
+        items = list(state.items()) if isinstance(state, dict) else state
+        key = self._state_key([t for _, t in items])
         if key == self._key:
             return
         with torch.no_grad():
-            self._packed = packing.pack_encoder(state)
+            self._packed = packing.pack_encoder(dict(items))
         self._struct = packing.to_struct(self._packed)
         self._key = key
 

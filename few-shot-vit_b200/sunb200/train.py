@@ -193,7 +193,7 @@ class TrainEngine:
     def forward(self, P, Bf, x, rs: Dict[str, List[Optional[torch.Tensor]]], update_running=True):
         """P: encoder parameters (fp32 CUDA, reference names without the 'encoder.' prefix); Bf: BN buffers;
         x fp32 [B,3,80,80]; rs[block] = per-branch DropPath scales (fp32 [B]) or None.
-        Returns (pooled fp32 [B,512], dense fp32 NHWC [B,5,5,512], ctx)."""
+        Returns (pooled fp32 [B,512], dense fp32 NHWC [B,5,5,512], pooled bf16, dense bf16, ctx)."""
         self.dev = x.device
         B = x.shape[0]
         lib = self.lib
@@ -280,10 +280,12 @@ class TrainEngine:
         bnf = self.bn_forward(cur, "norm.bn", 512, Mf, P, Bf, update_running)
         pooled = self.empty(B, 512, dtype=torch.float32)
         dense = self.empty(B, 5, 5, 512, dtype=torch.float32)
-        N.check(lib.sunb_final_norm_pool(cur.data_ptr(), bnf.row(2).data_ptr(), bnf.row(3).data_ptr(), dense.data_ptr(), None,
-                                         pooled.data_ptr(), None, B, 25, 512, _st()), "sunb_final_norm_pool")
+        pooled16, dense16 = self.empty(B, 512), self.empty(B, 5, 5, 512)        # bf16 copies for the linear heads
+        N.check(lib.sunb_final_norm_pool(cur.data_ptr(), bnf.row(2).data_ptr(), bnf.row(3).data_ptr(), dense.data_ptr(),
+                                         dense16.data_ptr(), pooled.data_ptr(), pooled16.data_ptr(), B, 25, 512, _st()),
+                "sunb_final_norm_pool")
         ctx["final"] = dict(x=cur, bn=bnf)
-        return pooled, dense, ctx
+        return pooled, dense, pooled16, dense16, ctx
 
     # ------------------------------------------------------------------ backward
     # parameter groups in the order their gradients become final during the backward pass

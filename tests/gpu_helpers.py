@@ -4,7 +4,34 @@ import ctypes as C
 import torch
 import torch.nn.functional as F
 
+import os
+
 from sunb200 import native as N
+
+_CHECK = None
+
+
+def check_lib():
+    """tests/native/libsunb200_check.so: SIMT GEMM, CUDA-core stem and warp-MMA grouped conv cross-check kernels (built by
+    `make -C few-shot-vit_b200/csrc`; test-only, never linked into the product library)."""
+    global _CHECK
+    if _CHECK is None:
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "native", "libsunb200_check.so")
+        l = C.CDLL(path)
+        l.sunb_check_last_error.restype = C.c_char_p
+        l.sunb_check_gemm.restype, l.sunb_check_gemm.argtypes = C.c_int, [C.POINTER(N.GemmDesc), C.c_void_p]
+        vp = C.c_void_p
+        l.sunb_check_stem_in.restype = C.c_int
+        l.sunb_check_stem_in.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp]
+        l.sunb_check_gconv3x3.restype = C.c_int
+        l.sunb_check_gconv3x3.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+        _CHECK = l
+    return _CHECK
+
+
+def check_call(status, what):
+    if status != 0:
+        raise RuntimeError(f"{what} failed: {check_lib().sunb_check_last_error().decode()}")
 
 
 def run_gemm(A, Wt, M, Nn, K, impl=0, taps=1, groups=1, a_goff=0, c_goff=0, conv=None, bias=None, bias_mod=1,
@@ -31,7 +58,10 @@ def run_gemm(A, Wt, M, Nn, K, impl=0, taps=1, groups=1, a_goff=0, c_goff=0, conv
     else:
         d.out, d.ldc = out.data_ptr(), out.shape[-1]
     d.out_map, d.oH, d.oW = out_map, oHW[0], oHW[1]
-    N.check(N.lib().sunb_gemm(C.byref(d), impl, N.current_stream()), "sunb_gemm")
+    if impl == 1:          # SIMT cross-check kernel of the test-only library
+        check_call(check_lib().sunb_check_gemm(C.byref(d), N.current_stream()), "sunb_check_gemm")
+    else:
+        N.check(N.lib().sunb_gemm(C.byref(d), 0, N.current_stream()), "sunb_gemm")
     torch.cuda.synchronize()
     return out
 

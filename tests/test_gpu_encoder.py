@@ -102,6 +102,62 @@ def test_full_episode_argmax_w1(golden_dir):
     assert agree / total >= 0.999
 
 
+@pytest.mark.parametrize("tag,shot,seed0", [("1shot", 1, 1000), ("5shot", 5, 2000)])
+def test_argmax_gate_1500_queries(golden_dir, tag, shot, seed0):
+    """north_star gate: per-query argmax agrees with the fp32 reference on >= 99.9 % of queries, asserted on 20 episodes =
+    1500 queries per setting (reference logits in tests/golden/episodes_argmax_w1.npz, written by the real reference).
+    Margin-conditioned agreement is reported as well."""
+    g = np.load(os.path.join(golden_dir, "episodes_argmax_w1.npz"))
+    ref = torch.as_tensor(g["logits_" + tag])                      # [20, 75, 5]
+    sd = O.calibrate_bn(O.init_meta_baseline_state_dict(12345))
+    m = make_model(sd)
+    data = torch.cat([O.make_episode_images(seed0 + ep, 5, shot + 15) for ep in range(20)]).cuda()
+    xs, xq = fs.split_shot_query(data, 5, shot, 15, ep_per_batch=20)
+    with torch.no_grad():
+        logits = m(xs, xq).cpu()
+    assert logits.shape == ref.shape
+    top2 = ref.topk(2, dim=-1).values
+    margin = (top2[..., 0] - top2[..., 1]).flatten()
+    same = (logits.argmax(-1) == ref.argmax(-1)).flatten()
+    worst = max_err(logits, ref)
+    wide = margin > 0.3
+    print(f"[{tag}] argmax agreement {int(same.sum())}/{same.numel()}, max |dlogit| {worst:.4f}, min reference margin "
+          f"{margin.min():.3f}; agreement where margin > 0.3: {int(same[wide].sum())}/{int(wide.sum())}")
+    assert same.numel() == 1500
+    assert worst < 0.25
+    assert same.float().mean().item() >= 0.999
+    assert bool(same[wide].all())
+
+
+def test_eval_train_eval_repacks_weights():
+    """the train path updates BatchNorm running statistics from raw kernels (no torch version bump); the eval
+    engine must not reuse its stale BN fold afterwards."""
+    sd = O.calibrate_bn(O.init_meta_baseline_state_dict(12345))
+    m = make_model(sd)
+    x = O.make_episode_images(11, 4, 4).cuda()
+    with torch.no_grad():
+        f0 = m.encoder(x).clone()
+        m.train()
+        for _ in range(3):
+            m.encoder(x * 1.5 + 0.3)                 # train-mode forward under no_grad: running statistics move
+        m.eval()
+        f1 = m.encoder(x).clone()
+    sd_after = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    assert not torch.equal(sd_after["encoder.stem.bn1.running_mean"], sd["encoder.stem.bn1.running_mean"])
+    with torch.no_grad():
+        _, ref = O.encoder_forward(sd_after, x.cpu(), "encoder.")
+    assert rel_err(f1.cpu(), ref) < 3e-2, "eval after train must use the updated running statistics"
+    assert rel_err(f0.cpu(), ref) > 3 * rel_err(f1.cpu(), ref)
+
+
+def test_data_parallel_replica_raises():
+    sd = O.calibrate_bn(O.init_meta_baseline_state_dict(12345))
+    m = make_model(sd)
+    rep = m.encoder._replicate_for_data_parallel()
+    with pytest.raises(RuntimeError, match="one process per GPU"):
+        rep(torch.zeros(1, 3, 80, 80, device="cuda"))
+
+
 def test_batched_episodes_match_single(golden_dir):
     """E episodes in one call == the same episodes one by one (episodes are independent in eval mode)."""
     sd = O.calibrate_bn(O.init_meta_baseline_state_dict(12345))

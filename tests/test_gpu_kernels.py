@@ -178,6 +178,39 @@ def test_softlabel_bit_exact(golden_dir):
         assert torch.equal(engine.generate_softlabel(t_logits, k=k, bp=bp).cpu(), ref), (k, bp)
 
 
+def test_softlabel_many_classes():
+    """tieredImageNet has 351 base classes: class chunks per lane cover n_cls <= 512."""
+    gl = torch.Generator().manual_seed(12)
+    t_logits = torch.randn(3, 5, 5, 351, generator=gl).to(DEV).permute(0, 3, 1, 2)
+    ref = O.generate_softlabel(t_logits.cpu(), k=5, bp=10)
+    assert torch.equal(engine.generate_softlabel(t_logits, k=5, bp=10).cpu(), ref)
+
+
+@pytest.mark.parametrize("lead,K,n", [((96,), 512, 64), ((8, 5, 5), 512, 65), ((33,), 256, 10)])
+def test_linear_forward_backward(lead, K, n):
+    """utils.linear: native forward, dgrad (sunb_gemm), wgrad (sunb_wgrad) and bias gradient vs F.linear on the same
+    bf16-rounded operands (reference heads: sun_meta_training/models/classifier.py:27-35, token_label.py:48-60)."""
+    import utils
+    x = rnd(*lead, K, seed=60).bfloat16().float().requires_grad_(True)
+    w = (rnd(n, K, seed=61) * K ** -0.5).bfloat16().float().requires_grad_(True)
+    b = rnd(n, seed=62).requires_grad_(True)
+    dy = rnd(*lead, n, seed=63).bfloat16().float()
+    y = utils.linear(x, w, b)
+    assert y.grad_fn is not None and y.shape == (*lead, n)
+    y.backward(dy)
+    torch.cuda.synchronize()
+    xr, wr, br = x.detach().clone().requires_grad_(True), w.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    yr = F.linear(xr, wr, br)
+    yr.backward(dy)
+    assert rel_err(y, yr) < 2e-3
+    assert rel_err(x.grad, xr.grad) < 1e-2            # dY and W are rounded to bf16 for the tensor-core dgrad
+    assert rel_err(w.grad, wr.grad) < 1e-2
+    assert rel_err(b.grad, br.grad) < 1e-2
+    # a bf16 copy of the activations can be handed in (what the encoder's last kernel emits)
+    y2 = utils.linear(x.detach(), w.detach(), b.detach(), x_bf16=x.detach().bfloat16())
+    assert torch.equal(y2, y.detach())
+
+
 def test_soft_ce_forward_backward(golden_dir):
     import numpy as np, os
     g = np.load(os.path.join(golden_dir, "sun_head.npz"))

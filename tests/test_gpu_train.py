@@ -279,3 +279,96 @@ def test_meta_tuning_step_vs_reference(golden_dir, tag, rate):
     assert abs(model.temp.item() - float(g["after_sgd.temp"])) < 1e-3
     got = model.encoder.stage3[2].attn.proj.weight.detach().flatten()[::128].cpu()
     assert rel_err(got, torch.as_tensor(g["after_sgd.encoder.stage3.2.attn.proj.weight.samp"])) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# SUN-M-shaped shards (BASELINE.json configs[2]: 10-way x (1 shot + 5 query) = 60 images per GPU at N = 8, drop_path 0.5,
+# non-trivial loss) against tests/golden/train_step_sunm.npz, written by the real reference (oracle/make_golden.py).
+# ------------------------------------------------------------------------------------------------------------------
+ZERO_GRAD = {"encoder.patch_embed2.proj.bias", "encoder.patch_embed2.norm.bn.bias",
+             "encoder.patch_embed3.proj.bias", "encoder.patch_embed3.norm.bn.bias"}
+
+
+def compare_grads(grads, g, prefix, tag, rel_tol=0.25, cos_tol=0.97):
+    """grads: {name: tensor}.  Same stated tolerance as the 18-image fixture: per-tensor rel-L2 <= 0.25, cosine >= 0.97;
+    the four analytically-zero gradients are compared absolutely."""
+    report, bad = [], []
+    for name, gr in grads.items():
+        gr = gr.detach().cpu().float()
+        ref_norm = float(g[prefix + "gnorm." + name])
+        if name in ZERO_GRAD:
+            if gr.abs().max().item() > 2e-2 * max(1.0, ref_norm):
+                bad.append((name, "nonzero", gr.abs().max().item()))
+            continue
+        if prefix + "grad." + name in g.files:
+            ref = torch.as_tensor(g[prefix + "grad." + name])
+            a = gr
+        else:
+            ref = torch.as_tensor(g[prefix + "gsamp." + name])
+            a = gr.flatten()[:: max(1, gr.numel() // 2048)]
+        rel = ((a - ref).norm() / (ref.norm() + 1e-12)).item()
+        cos = F.cosine_similarity(a.flatten(), ref.flatten(), dim=0).item()
+        report.append((rel, cos, name))
+        if not (rel <= rel_tol and cos >= cos_tol):
+            bad.append((name, rel, cos))
+    report.sort(reverse=True)
+    rels = sorted(r for r, _, _ in report)
+    print(f"[{tag}] gradient rel-L2 over {len(rels)} tensors: median {rels[len(rels) // 2]:.4f}, worst {report[0][0]:.4f} ({report[0][2]})")
+    for r, c, n in report[:5]:
+        print(f"    {n:50s} rel {r:.4f} cos {c:.5f}")
+    assert not bad, bad[:10]
+    return rels[len(rels) // 2], report[0][0]
+
+
+def sunm_shard_grads(shard, device="cuda"):
+    """One replica's step on SUN-M shard `shard`: fresh model from the calibrated weights, the reference's DropPath draws
+    replayed (CPU RNG stream under seed 77 + shard).  Returns (model, logits, loss)."""
+    import models
+    import utils.few_shot as fs
+    way, shot, query = 10, 1, 5
+    sd = O.calibrate_bn(O.init_meta_baseline_state_dict(12345))
+    model = models.make("meta-baseline", encoder="visformer_micro_80", encoder_args={"drop_path_rate": 0.5})
+    model.load_state_dict(sd)
+    model = model.to(device).train()
+    data = O.make_episode_images(600 + shard, way, shot + query, noise=1.0).to(device)
+    xs, xq = fs.split_shot_query(data, way, shot, query, ep_per_batch=1)
+    label = fs.make_nk_label(way, query, 1).to(device)
+    masks, rates, names = _draw_dp_masks(77 + shard, 0.5, data.shape[0])
+    scales = {n: [(m.view(-1) / (1 - rates[names.index(n)])).to(device) for m in ms] for n, ms in masks.items()}
+    model.encoder._drop_path_scales = lambda batch, dev: scales
+    logits = model(xs, xq).view(-1, way)
+    loss = F.cross_entropy(logits, label)
+    model.zero_grad()
+    return model, logits, loss
+
+
+def test_sunm_shard_step_vs_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "train_step_sunm.npz"))
+    model, logits, loss = sunm_shard_grads(0)
+    loss.backward()
+    torch.cuda.synchronize()
+    print(f"[sunm s0] loss {loss.item():.4f} vs reference {float(g['s0.loss']):.4f}; "
+          f"max |dlogit| {max_err(logits.detach().cpu(), torch.as_tensor(g['s0.logits'])):.4f}")
+    assert abs(loss.item() - float(g["s0.loss"])) <= 0.05 * float(g["s0.loss"])
+    assert max_err(logits.detach().cpu(), torch.as_tensor(g["s0.logits"])) < 0.35
+    compare_grads({n: p.grad for n, p in model.named_parameters()}, g, "s0.", "sunm shard 0")
+    for k in g.files:
+        if k.startswith("s0.bn."):
+            name = k[6:]
+            got, ref = model.state_dict()[name].cpu(), torch.as_tensor(g[k])
+            assert ((got - ref).norm() / (ref.norm() + 1e-12)).item() < 5e-2, name
+
+
+def test_sunm_two_shards_sequential_average_vs_reference(golden_dir):
+    """Data-parallel semantics on ONE GPU: the two shards run one after the other as two replicas would, their gradients
+    are averaged, and the average is compared with the reference's 2-shard average (what N = 2 ranks must produce)."""
+    g = np.load(os.path.join(golden_dir, "train_step_sunm.npz"))
+    acc = None
+    for s in range(2):
+        model, logits, loss = sunm_shard_grads(s)
+        loss.backward()
+        torch.cuda.synchronize()
+        assert abs(loss.item() - float(g[f"s{s}.loss"])) <= 0.05 * float(g[f"s{s}.loss"])
+        grads = {n: p.grad.detach().clone() for n, p in model.named_parameters()}
+        acc = grads if acc is None else {n: (acc[n] + grads[n]) / 2 for n in acc}
+    compare_grads(acc, g, "avg.", "sunm 2-shard average")

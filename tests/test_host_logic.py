@@ -8,6 +8,7 @@ import torch
 
 import sun_oracle as O
 from sunb200 import native as N, packing
+import emulate
 
 
 def test_packing_folds_match_oracle():
@@ -18,7 +19,7 @@ def test_packing_folds_match_oracle():
     with torch.no_grad():
         dense, pooled = O.encoder_forward(sd, x, "encoder.", taps=taps_o)
         P = packing.pack_encoder(sd, "encoder.", wdtype=torch.float32)
-        d2, p2 = packing.emulate_forward(P, x, taps_e)
+        d2, p2 = emulate.emulate_forward(P, x, taps_e)
     for k, ref in taps_o.items():
         ref = ref.permute(0, 2, 3, 1)
         err = (taps_e[k] - ref).abs().max().item() / (ref.abs().max().item() + 1e-12)

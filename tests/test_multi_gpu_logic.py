@@ -63,6 +63,14 @@ def _worker(rank, world, port, out_path):
         lin.weight.fill_(float(rank + 1))
     broadcast_module_state(lin)
     assert float(lin.weight[0, 0]) == 1.0
+    # rank 0's BatchNorm statistics are authoritative after sync_bn_buffers (parameters stay untouched)
+    from sunb200.dist import sync_bn_buffers
+    bn = torch.nn.BatchNorm2d(3)
+    with torch.no_grad():
+        bn.running_mean.fill_(float(rank + 1))
+        bn.weight.fill_(float(rank + 5))
+    sync_bn_buffers(bn)
+    assert float(bn.running_mean[0]) == 1.0 and float(bn.weight[0]) == float(rank + 5)
     if rank == 0:
         torch.save({"names": names, "avg": [h.grad.clone() for h in holders], "loss": loss}, out_path)
     dist.barrier()
