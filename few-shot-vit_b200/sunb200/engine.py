@@ -150,6 +150,33 @@ def ce_and_acc(logits: torch.Tensor, label: torch.Tensor) -> torch.Tensor:
     return out
 
 
+class _CrossEntropy(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, label):
+        l, y = logits.detach().contiguous().float(), label.contiguous().long()
+        out = torch.empty(2, dtype=torch.float32, device=l.device)
+        N.check(N.lib().sunb_logits_ce_acc(l.data_ptr(), y.data_ptr(), l.shape[0], l.shape[1], out.data_ptr(),
+                                           N.current_stream()), "sunb_logits_ce_acc")
+        ctx.save_for_backward(l, y)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        l, y = ctx.saved_tensors
+        dl = torch.empty_like(l)
+        gg = g.contiguous().float().reshape(1)
+        N.check(N.lib().sunb_hard_ce_backward(l.data_ptr(), y.data_ptr(), l.shape[0], l.shape[1], gg.data_ptr(), 1.0,
+                                              dl.data_ptr(), N.current_stream()), "sunb_hard_ce_backward")
+        return dl, None
+
+
+def cross_entropy(logits: torch.Tensor, label: torch.Tensor) -> torch.Tensor:
+    """F.cross_entropy (mean reduction) of [R,W] fp32 logits with a native forward and backward
+    (reference: train_meta.py:169, offline.py:270)."""
+    N.require_cuda(logits, label)
+    return _CrossEntropy.apply(logits, label)
+
+
 def generate_softlabel(logits: torch.Tensor, smoothing: float = 0.1, k: int = 3, bp: int = 10) -> torch.Tensor:
     """Teacher patch logits [B,n_cls,h,w] (any strides with a uniform pixel stride, e.g. the NHWC-backed view the
     token-label model returns) -> soft labels [B*h*w, n_cls+1] (sun_meta_training/offline.py:57-76)."""

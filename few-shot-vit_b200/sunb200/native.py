@@ -49,6 +49,10 @@ class WgradDesc(C.Structure):
     ]
 
 
+class OptTensor(C.Structure):
+    _fields_ = [("p", vp), ("g", vp), ("m", vp), ("v", vp), ("n", C.c_int64)]
+
+
 class ConvMlpW(C.Structure):
     _fields_ = [("w1", vp), ("b1", fp), ("w2", vp), ("w3", vp)]
 
@@ -119,10 +123,14 @@ SIGNATURES = {
     "sunb_attention_backward": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "sunb_episode_logits_backward": (C.c_int, [fp, fp, fp, fp, fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                C.c_int, fp, C.c_float, vp]),
+    # fused multi-tensor optimizers
+    "sunb_opt_chunk_elems": (C.c_int, []),
+    "sunb_fused_sgd": (C.c_int, [vp, vp, C.c_int, C.c_int64, fp, vp]),
+    "sunb_fused_adamw": (C.c_int, [vp, vp, C.c_int, C.c_int64, fp, vp]),
 }
 
 _lib = None
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 def lib() -> C.CDLL:

@@ -6,12 +6,13 @@ import shutil
 import time
 
 import torch
-from torch.optim import SGD, Adam
+from torch.optim import Adam
 from torch.optim.lr_scheduler import MultiStepLR
 
 from . import few_shot  # noqa: F401
 from sunb200 import engine as _engine
 from sunb200 import native as _N
+from sunb200.optim import FusedSGD, FusedAdamW, CosineLRScheduler, MultiStepLRScheduler  # noqa: F401
 
 _log_path = None
 
@@ -176,12 +177,15 @@ def compute_n_params(model, return_str=True):
 
 
 def make_optimizer(params, name, lr, weight_decay=None, milestones=None, gamma=0.1):
-    """SGD(momentum 0.9) / Adam + optional MultiStepLR (reference: utils/__init__.py:128-139)."""
+    """SGD(momentum 0.9) / Adam + optional MultiStepLR (reference: utils/__init__.py:128-139).  'adamw' (used by
+    sun_meta_training/offline.py:229 directly) is accepted too."""
     wd = 0.0 if weight_decay is None else weight_decay
     if name == "sgd":
-        opt = SGD(params, lr, momentum=0.9, weight_decay=wd)
+        opt = FusedSGD(params, lr, momentum=0.9, weight_decay=wd)      # one native launch over all 86 tensors
     elif name == "adam":
         opt = Adam(params, lr, weight_decay=wd)
+    elif name == "adamw":
+        opt = FusedAdamW(params, lr, weight_decay=wd)
     else:
         raise ValueError(name)
     sched = MultiStepLR(opt, milestones, gamma=gamma) if milestones else None

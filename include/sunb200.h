@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SUNB_ABI_VERSION 3
+#define SUNB_ABI_VERSION 4
 
 int sunb_abi_version(void);
 const char* sunb_last_error(void);
@@ -241,6 +241,29 @@ int sunb_attention_backward(const void* qkv, const void* dout, void* dqkv, int B
 int sunb_episode_logits_backward(const float* feat_shot, const float* feat_query, const float* dlogits, float* dshot,
                                  float* dquery, float* dtemp, int E, int way, int shot, int Q, int D, int metric,
                                  const float* temp_dev, float temp_host, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Fused multi-tensor optimizers: one launch updates every parameter tensor (all fp32).
+ *   sunb_fused_sgd   : torch.optim.SGD(momentum, weight_decay) as utils.make_optimizer builds it
+ *                      (meta_tuning_sun_m/utils/__init__.py:128-139; train_meta_warmup.py:140).  m = momentum buffer.
+ *   sunb_fused_adamw : AdamW(betas, eps, decoupled weight decay) (sun_meta_training/offline.py:229).  m, v = moments.
+ * tensors_dev: device array of n_tensors entries; g == NULL skips the tensor.  chunk_prefix_dev: device int64
+ * [n_tensors + 1], prefix sums of ceil(n / sunb_opt_chunk_elems()).  hp_dev: device fp32 [8]:
+ *   [0] lr  [1] momentum (SGD) | beta1 (AdamW)  [2] weight_decay  [3] beta2  [4] eps  [5] step counter (AdamW: incremented
+ *   on the device by every call, so a captured CUDA graph replays correctly).
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct SunbOptTensor {
+    void* p;            /* fp32 parameter */
+    const void* g;      /* fp32 gradient (nullable) */
+    void* m;            /* fp32 momentum / first moment */
+    void* v;            /* fp32 second moment (AdamW; NULL for SGD) */
+    int64_t n;          /* elements */
+} SunbOptTensor;
+int sunb_opt_chunk_elems(void);
+int sunb_fused_sgd(const SunbOptTensor* tensors_dev, const int64_t* chunk_prefix_dev, int n_tensors, int64_t total_chunks,
+                   float* hp_dev, void* stream);
+int sunb_fused_adamw(const SunbOptTensor* tensors_dev, const int64_t* chunk_prefix_dev, int n_tensors, int64_t total_chunks,
+                     float* hp_dev, void* stream);
 
 #ifdef __cplusplus
 }

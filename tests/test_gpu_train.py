@@ -372,3 +372,82 @@ def test_sunm_two_shards_sequential_average_vs_reference(golden_dir):
         grads = {n: p.grad.detach().clone() for n, p in model.named_parameters()}
         acc = grads if acc is None else {n: (acc[n] + grads[n]) / 2 for n in acc}
     compare_grads(acc, g, "avg.", "sunm 2-shard average")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# fused optimizers and the SUN meta-training step (sun_meta_training/offline.py:263-303)
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["sgd", "adamw"])
+def test_fused_optimizers_match_torch(kind):
+    from sunb200.optim import FusedSGD, FusedAdamW
+    shapes = [(64, 3, 3, 3), (128,), (), (1530, 512, 1, 1), (65, 512), (7,), (4097,)]
+    ps = [torch.nn.Parameter(rnd(*s, seed=100 + i) if len(s) else rnd(1, seed=100 + i)[0].clone()) for i, s in enumerate(shapes)]
+    qs = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    if kind == "sgd":
+        a, b = FusedSGD(ps, lr=1e-2, momentum=0.9, weight_decay=5e-4), torch.optim.SGD(qs, lr=1e-2, momentum=0.9, weight_decay=5e-4)
+    else:
+        a = FusedAdamW(ps, lr=3e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.05)
+        b = torch.optim.AdamW(qs, lr=3e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.05)
+    for it in range(4):
+        for i, (p, q) in enumerate(zip(ps, qs)):
+            gr = rnd(*p.shape, seed=1000 * it + i) if p.dim() else rnd(1, seed=1000 * it + i)[0].clone()
+            p.grad, q.grad = gr.clone(), gr.clone()
+        if it == 2:                                   # scheduler changes the learning rate between steps
+            for o in (a, b):
+                o.param_groups[0]["lr"] *= 0.5
+        a.step()
+        b.step()
+    torch.cuda.synchronize()
+    for p, q, s in zip(ps, qs, shapes):
+        assert (p - q).abs().max().item() <= 2e-6 * max(1.0, q.abs().max().item()), s
+
+
+def test_sun_meta_training_step_vs_reference(golden_dir):
+    """One SUN meta-training step (offline.py:263-303, batch scaled 512 -> 16): losses, gradients of all 90 tensors and the
+    AdamW update against the reference's own outputs (tests/golden/sun_meta_step.npz)."""
+    import models
+    from sunb200 import sun_meta
+    g = np.load(os.path.join(golden_dir, "sun_meta_step.npz"))
+    margs = dict(encoder="visformer_micro_80", encoder_args={"drop_path_rate": 0.5}, classifier="linear-classifier",
+                 classifier_args={"n_classes": 64})
+    student, teacher = models.make("token-label", **margs), models.make("token-label", **margs)
+    student.load_state_dict(O.calibrate_bn(O.init_token_label_state_dict(4321)))
+    teacher.load_state_dict(O.calibrate_bn(O.init_token_label_state_dict(12345)))
+    student, teacher = student.cuda().train(), teacher.cuda().eval()
+    strong = O.make_episode_images(800, 8, 2, noise=1.0).cuda()
+    weak = O.make_episode_images(800, 8, 2, noise=0.5).cuda()
+    label = torch.as_tensor(g["label"]).cuda()
+    masks, rates, names = _draw_dp_masks(123, 0.5, 16)
+    scales = {n: [(m.view(-1) / (1 - rates[names.index(n)])).cuda() for m in ms] for n, ms in masks.items()}
+    student.encoder._drop_path_scales = lambda batch, dev: scales
+    # (1) end to end: our bf16 teacher's pseudo labels vs the fp32 reference's (reported statistic, SURVEY.md 7.3-8b)
+    with torch.no_grad():
+        yt_t, _, _ = teacher(weak, True)
+        soft = engine.generate_softlabel(yt_t, k=5, bp=10)
+    ref_soft = torch.as_tensor(g["soft_label"]).cuda()
+    same_rows = (soft == ref_soft).all(dim=1).float().mean().item()
+    print(f"[sun step] teacher patch logits rel-L2 {rel_err(yt_t.cpu(), torch.as_tensor(g['teacher_logits_token'])):.4f}; "
+          f"soft-label rows identical to the fp32 reference: {100 * same_rows:.1f} %")
+    assert rel_err(yt_t.cpu(), torch.as_tensor(g["teacher_logits_token"])) < 5e-2
+    assert same_rows > 0.7
+    # (2) the step itself with the reference's soft labels injected (identical targets -> comparable gradients)
+    before = {k: p.detach().clone() for k, p in student.named_parameters()}
+    opt, _ = sun_meta.build_optimizer(student, batch_size=16)
+    assert abs(opt.param_groups[0]["lr"] - 1e-6) < 1e-12           # warm-up start of the cosine schedule
+    opt.param_groups[0]["lr"] = float(g["lr"])
+    out = sun_meta.sun_meta_training_step(student, teacher, strong, weak, label, opt, 5, 10, soft_label=ref_soft)
+    torch.cuda.synchronize()
+    print(f"[sun step] loss {out['loss'].item():.4f} / cls {out['cls_loss'].item():.4f} / token {out['token_loss'].item():.4f}"
+          f" vs reference {float(g['loss']):.4f} / {float(g['cls_loss']):.4f} / {float(g['token_loss']):.4f}")
+    for k in ("loss", "cls_loss", "token_loss"):
+        assert abs(out[k].item() - float(g[k])) <= 0.05 * float(g[k]), k
+    compare_grads({n: p.grad for n, p in student.named_parameters()}, g, "", "sun meta step")
+    # AdamW's first step moves every element by ~lr * sign(g): compare the update direction and size
+    for k in g.files:
+        if k.startswith("adamw_delta."):
+            name = k[len("adamw_delta."):]
+            p = dict(student.named_parameters())[name]
+            d = (p.detach() - before[name]).flatten()[:: max(1, p.numel() // 1024)].cpu()
+            ref = torch.as_tensor(g[k])
+            agree = (torch.sign(d) == torch.sign(ref)).float().mean().item()
+            assert agree > 0.9 and abs(d.abs().mean().item() / ref.abs().mean().item() - 1) < 0.1, (name, agree)
