@@ -3,8 +3,10 @@
 //                                     (reference meta_tuning_sun_m/utils/__init__.py:128-139; train_meta_warmup.py:140)
 //   AdamW (decoupled weight decay)  : torch / timm AdamW semantics (reference sun_meta_training/offline.py:229)
 // HBM-bound: 16 B (SGD: p, g, m read + p, m written = 20 B) / 28 B per parameter element, float4 accesses.
-// The tensor table (pointers + sizes) and the hyper-parameters live in device memory, so a captured CUDA graph of the
-// training step keeps working when the learning rate changes or the step counter advances.
+// The tensor table (pointers + sizes) travels BY VALUE in the kernel arguments (<= 96 tensors per launch, 4.6 KB), so no
+// host-to-device copy happens at step time and a CUDA-graph capture of the training step records the table in its kernel
+// node.  The hyper-parameters and the AdamW step counter live in device memory: a captured graph keeps working when the
+// scheduler changes the learning rate or the step counter advances.
 #include "common.cuh"
 #include "../../include/sunb200.h"
 
@@ -23,10 +25,18 @@ __device__ __forceinline__ int find_tensor(const long long* __restrict__ chunk_p
     return lo;
 }
 
+constexpr int MAX_T = 96;                    // tensors per launch
+struct OptArgs {
+    SunbOptTensor t[MAX_T];
+    long long prefix[MAX_T + 1];             // prefix sums of the per-tensor chunk counts
+    int n;
+};
+
 template <bool ADAMW>
-__global__ void __launch_bounds__(THREADS) fused_opt_kernel(const SunbOptTensor* __restrict__ tensors,
-                                                           const long long* __restrict__ chunk_prefix, int n_tensors,
-                                                           const float* __restrict__ hp) {
+__global__ void __launch_bounds__(THREADS) fused_opt_kernel(const __grid_constant__ OptArgs args, const float* __restrict__ hp) {
+    const SunbOptTensor* tensors = args.t;
+    const long long* chunk_prefix = args.prefix;
+    const int n_tensors = args.n;
     const long long total = chunk_prefix[n_tensors];
     const float lr = hp[0], wd = hp[2];
     float mu = 0.f, b1 = 0.f, b2 = 0.f, eps = 0.f, step_size = 0.f, inv_sqrt_bc2 = 0.f;
@@ -104,32 +114,39 @@ __global__ void __launch_bounds__(THREADS) fused_opt_kernel(const SunbOptTensor*
 
 __global__ void opt_step_inc_kernel(float* hp) { hp[5] += 1.f; }
 
+template <bool ADAMW>
+int launch_opt(const SunbOptTensor* tensors, int n_tensors, float* hp_dev, cudaStream_t st) {
+    for (int t0 = 0; t0 < n_tensors; t0 += MAX_T) {
+        OptArgs a;
+        a.n = n_tensors - t0 < MAX_T ? n_tensors - t0 : MAX_T;
+        a.prefix[0] = 0;
+        for (int i = 0; i < a.n; ++i) {
+            a.t[i] = tensors[t0 + i];
+            SUNB_REQUIRE(a.t[i].p && a.t[i].m && a.t[i].n > 0 && (!ADAMW || a.t[i].v), "fused optimizer: bad tensor entry %d", t0 + i);
+            a.prefix[i + 1] = a.prefix[i] + (a.t[i].n + CHUNK - 1) / CHUNK;
+        }
+        const long long total = a.prefix[a.n];
+        const int grid = (int)(total < 148 * 8 ? total : 148 * 8);
+        fused_opt_kernel<ADAMW><<<grid, THREADS, 0, st>>>(a, hp_dev);
+        SUNB_CHECK_CUDA(cudaGetLastError());
+    }
+    return SUNB_OK;
+}
+
 }  // namespace
 
 extern "C" {
 
-int sunb_opt_chunk_elems(void) { return CHUNK; }
-
-int sunb_fused_sgd(const SunbOptTensor* tensors_dev, const int64_t* chunk_prefix_dev, int n_tensors, int64_t total_chunks,
-                   float* hp_dev, void* stream) {
-    SUNB_REQUIRE(tensors_dev && chunk_prefix_dev && hp_dev && n_tensors > 0 && total_chunks > 0, "fused_sgd: bad arguments");
-    const int grid = (int)(total_chunks < 148 * 8 ? total_chunks : 148 * 8);
-    fused_opt_kernel<false><<<grid, THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        tensors_dev, reinterpret_cast<const long long*>(chunk_prefix_dev), n_tensors, hp_dev);
-    SUNB_CHECK_CUDA(cudaGetLastError());
-    return SUNB_OK;
+int sunb_fused_sgd(const SunbOptTensor* tensors, int n_tensors, float* hp_dev, void* stream) {
+    SUNB_REQUIRE(tensors && hp_dev && n_tensors > 0, "fused_sgd: bad arguments");
+    return launch_opt<false>(tensors, n_tensors, hp_dev, reinterpret_cast<cudaStream_t>(stream));
 }
 
-int sunb_fused_adamw(const SunbOptTensor* tensors_dev, const int64_t* chunk_prefix_dev, int n_tensors, int64_t total_chunks,
-                     float* hp_dev, void* stream) {
-    SUNB_REQUIRE(tensors_dev && chunk_prefix_dev && hp_dev && n_tensors > 0 && total_chunks > 0, "fused_adamw: bad arguments");
+int sunb_fused_adamw(const SunbOptTensor* tensors, int n_tensors, float* hp_dev, void* stream) {
+    SUNB_REQUIRE(tensors && hp_dev && n_tensors > 0, "fused_adamw: bad arguments");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     opt_step_inc_kernel<<<1, 1, 0, st>>>(hp_dev);                  // the step counter lives on the device (graph replays)
-    const int grid = (int)(total_chunks < 148 * 8 ? total_chunks : 148 * 8);
-    fused_opt_kernel<true><<<grid, THREADS, 0, st>>>(tensors_dev, reinterpret_cast<const long long*>(chunk_prefix_dev),
-                                                      n_tensors, hp_dev);
-    SUNB_CHECK_CUDA(cudaGetLastError());
-    return SUNB_OK;
+    return launch_opt<true>(tensors, n_tensors, hp_dev, st);
 }
 
 }  // extern "C"

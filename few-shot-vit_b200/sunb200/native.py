@@ -124,9 +124,8 @@ SIGNATURES = {
     "sunb_episode_logits_backward": (C.c_int, [fp, fp, fp, fp, fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                C.c_int, fp, C.c_float, vp]),
     # fused multi-tensor optimizers
-    "sunb_opt_chunk_elems": (C.c_int, []),
-    "sunb_fused_sgd": (C.c_int, [vp, vp, C.c_int, C.c_int64, fp, vp]),
-    "sunb_fused_adamw": (C.c_int, [vp, vp, C.c_int, C.c_int64, fp, vp]),
+    "sunb_fused_sgd": (C.c_int, [C.POINTER(OptTensor), C.c_int, fp, vp]),
+    "sunb_fused_adamw": (C.c_int, [C.POINTER(OptTensor), C.c_int, fp, vp]),
 }
 
 _lib = None

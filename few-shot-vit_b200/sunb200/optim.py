@@ -5,8 +5,8 @@ keep working) whose step() is ONE native launch over every parameter tensor (csr
   * FusedSGD   = torch.optim.SGD(lr, momentum, weight_decay) as utils.make_optimizer builds it
                  (reference meta_tuning_sun_m/utils/__init__.py:128-139, train_meta_warmup.py:140)
   * FusedAdamW = AdamW(betas, eps, decoupled weight decay) (reference sun_meta_training/offline.py:229)
-All hyper-parameters and the AdamW step counter live in a small device tensor, so a CUDA graph that captured step()
-stays valid when the scheduler changes the learning rate.
+The tensor table is passed to the kernel by value (no copy at step time); the hyper-parameters and the AdamW step counter
+live in a small device tensor, so a CUDA graph that captured step() stays valid when the scheduler changes the learning rate.
 
 CosineLRScheduler / MultiStepLRScheduler restate the timm schedulers the reference imports (offline.py:231,
 train_meta_warmup.py:141).  timm is not installed in this image: parity with timm is unpinned, the formulas are timm's
@@ -29,32 +29,18 @@ class _FusedBase(torch.optim.Optimizer):
     _adamw = False
 
     def _init_tables(self):
-        self._tables = None            # (ptr signature, tensors_dev, prefix_dev, n, total_chunks, keep-alive list)
         self._hp = None
         self._hp_host = None
 
-    def _ensure(self, group, params, grads, bufs1, bufs2):
-        sig = tuple((p.data_ptr(), 0 if g is None else g.data_ptr()) for p, g in zip(params, grads))
-        if self._tables is not None and self._tables[0] == sig:
-            return self._tables
-        chunk = N.lib().sunb_opt_chunk_elems()
+    @staticmethod
+    def _table(params, grads, bufs1, bufs2):
+        """Host-side tensor table; the native launcher passes it to the kernel by value (nothing is copied at step time)."""
         arr = (N.OptTensor * len(params))()
-        prefix = [0]
         for i, (p, g, m, v) in enumerate(zip(params, grads, bufs1, bufs2)):
-            arr[i].p, arr[i].g, arr[i].m = p.data_ptr(), (None if g is None else g.data_ptr()), m.data_ptr()
+            arr[i].p, arr[i].g, arr[i].m = p.data_ptr(), g.data_ptr(), m.data_ptr()
             arr[i].v = None if v is None else v.data_ptr()
             arr[i].n = p.numel()
-            prefix.append(prefix[-1] + (p.numel() + chunk - 1) // chunk)
-        dev = params[0].device
-        # pinned staging + async copies: legal inside a CUDA-graph capture (the pinned buffers are kept alive with the table)
-        raw_h = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).pin_memory()
-        pre_h = torch.tensor(prefix, dtype=torch.int64).pin_memory()
-        raw = torch.empty_like(raw_h, device=dev)
-        pre = torch.empty_like(pre_h, device=dev)
-        raw.copy_(raw_h, non_blocking=True)
-        pre.copy_(pre_h, non_blocking=True)
-        self._tables = (sig, raw, pre, len(params), prefix[-1], raw_h, pre_h)
-        return self._tables
+        return arr
 
     def _hyper(self, dev, values):
         """Device hyper-parameter block; re-uploaded only when a value (e.g. the learning rate) changed.  Slot 5 (the
@@ -93,10 +79,9 @@ class FusedSGD(_FusedBase):
                 st["momentum_buffer"] = torch.zeros_like(p)      # zero start == torch's "first step: buf = grad"
             grads.append(p.grad)
             bufs.append(st["momentum_buffer"])
-        _, raw, pre, n, total = self._ensure(grp, params, grads, bufs, [None] * len(params))[:5]
+        arr = self._table(params, grads, bufs, [None] * len(params))
         hp = self._hyper(params[0].device, [float(grp["lr"]), float(grp["momentum"]), float(grp["weight_decay"]), 0.0, 0.0])
-        N.check(N.lib().sunb_fused_sgd(raw.data_ptr(), pre.data_ptr(), n, total, hp.data_ptr(), N.current_stream()),
-                "sunb_fused_sgd")
+        N.check(N.lib().sunb_fused_sgd(arr, len(params), hp.data_ptr(), N.current_stream()), "sunb_fused_sgd")
         return loss
 
 
@@ -125,11 +110,10 @@ class FusedAdamW(_FusedBase):
             grads.append(p.grad)
             m1.append(st["exp_avg"])
             m2.append(st["exp_avg_sq"])
-        _, raw, pre, n, total = self._ensure(grp, params, grads, m1, m2)[:5]
+        arr = self._table(params, grads, m1, m2)
         b1, b2 = grp["betas"]
         hp = self._hyper(params[0].device, [float(grp["lr"]), float(b1), float(grp["weight_decay"]), float(b2), float(grp["eps"])])
-        N.check(N.lib().sunb_fused_adamw(raw.data_ptr(), pre.data_ptr(), n, total, hp.data_ptr(), N.current_stream()),
-                "sunb_fused_adamw")
+        N.check(N.lib().sunb_fused_adamw(arr, len(params), hp.data_ptr(), N.current_stream()), "sunb_fused_adamw")
         return loss
 
 

@@ -247,8 +247,8 @@ int sunb_episode_logits_backward(const float* feat_shot, const float* feat_query
  *   sunb_fused_sgd   : torch.optim.SGD(momentum, weight_decay) as utils.make_optimizer builds it
  *                      (meta_tuning_sun_m/utils/__init__.py:128-139; train_meta_warmup.py:140).  m = momentum buffer.
  *   sunb_fused_adamw : AdamW(betas, eps, decoupled weight decay) (sun_meta_training/offline.py:229).  m, v = moments.
- * tensors_dev: device array of n_tensors entries; g == NULL skips the tensor.  chunk_prefix_dev: device int64
- * [n_tensors + 1], prefix sums of ceil(n / sunb_opt_chunk_elems()).  hp_dev: device fp32 [8]:
+ * tensors: HOST array of n_tensors entries (device pointers inside); it is passed to the kernel by value, so nothing is
+ * copied at step time and a CUDA-graph capture records it.  g == NULL skips the tensor.  hp_dev: device fp32 [8]:
  *   [0] lr  [1] momentum (SGD) | beta1 (AdamW)  [2] weight_decay  [3] beta2  [4] eps  [5] step counter (AdamW: incremented
  *   on the device by every call, so a captured CUDA graph replays correctly).
  * ------------------------------------------------------------------------------------------------- */
@@ -259,11 +259,8 @@ typedef struct SunbOptTensor {
     void* v;            /* fp32 second moment (AdamW; NULL for SGD) */
     int64_t n;          /* elements */
 } SunbOptTensor;
-int sunb_opt_chunk_elems(void);
-int sunb_fused_sgd(const SunbOptTensor* tensors_dev, const int64_t* chunk_prefix_dev, int n_tensors, int64_t total_chunks,
-                   float* hp_dev, void* stream);
-int sunb_fused_adamw(const SunbOptTensor* tensors_dev, const int64_t* chunk_prefix_dev, int n_tensors, int64_t total_chunks,
-                     float* hp_dev, void* stream);
+int sunb_fused_sgd(const SunbOptTensor* tensors, int n_tensors, float* hp_dev, void* stream);
+int sunb_fused_adamw(const SunbOptTensor* tensors, int n_tensors, float* hp_dev, void* stream);
 
 #ifdef __cplusplus
 }
