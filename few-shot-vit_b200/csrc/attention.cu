@@ -9,8 +9,8 @@
 // shared memory (zero-padded to MMA shapes: S -> 112 / 32 keys, d 42 -> 48, 85 -> 96); each warp owns 16 query rows,
 // computes the full score row block with mma.sync.m16n8k16 (bf16 in, fp32 accumulate), does the softmax on the
 // accumulator registers (row max / sum via quad shuffles, exp2 with the scale folded in) and feeds the probabilities
-// straight back as the A operand of the P.V MMAs.  QK^T + PV are 1.2 % of the encoder FLOPs; the problems are far
-// too small (100x100x42) for a 128-row tcgen05 tile, so this stays on the legacy warp MMA path by design.
+// straight back as the A operand of the P.V MMAs.  This kernel serves the TRAINING path's packed head layout (ds == d);
+// the eval engine's padded layout runs on the tcgen05 kernel in attention_tc.cu.
 #include "common.cuh"
 
 #ifndef SUNB_ATT_CTAS
@@ -244,10 +244,18 @@ int launch_cfg(const bf16* qkv, bf16* out, int n_pairs, int S, int d, int ds, in
 
 }  // namespace
 
+int sunb_attention_tc_supported(const bf16* qkv, const bf16* out, int S, int d, int ds, int ld_qkv, int ld_out);   // attention_tc.cu
+int sunb_launch_attention_tc(const bf16* qkv, bf16* out, int B, int S, int d, int ds, int heads, int ld_qkv, int ld_out,
+                             cudaStream_t stream);
+
 int sunb_launch_attention(const bf16* qkv, bf16* out, int B, int S, int d, int ds, int heads, int ld_qkv, int ld_out,
                           cudaStream_t stream) {
     SUNB_REQUIRE(B > 0 && heads > 0, "attention: empty problem");
     SUNB_REQUIRE(ds >= d && ld_qkv >= 3 * heads * ds && ld_out >= heads * ds, "attention: head stride %d / row strides too small", ds);
+    // the eval engine's padded head layouts (ds = 48 / 96) run on tcgen05 (attention_tc.cu); the packed layout of the training
+    // path (ds == d = 42 / 85: head segments are not 16-byte aligned, no TMA box) stays on the warp-MMA kernel below
+    if (sunb_attention_tc_supported(qkv, out, S, d, ds, ld_qkv, ld_out))
+        return sunb_launch_attention_tc(qkv, out, B, S, d, ds, heads, ld_qkv, ld_out, stream);
     const float scale = 1.0f / sqrtf((float)d);
     const int n_pairs = B * heads;
     if (S <= 32 && d <= 96 && d > 48) return launch_cfg<32, 96, 4>(qkv, out, n_pairs, S, d, ds, heads, ld_qkv, ld_out, scale, stream);

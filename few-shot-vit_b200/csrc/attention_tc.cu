@@ -1,0 +1,310 @@
+// Multi-head self-attention core on tcgen05 / TMEM / TMA (reference: test_phase/models/visformer.py:183-190) for the eval
+// engine's padded head layout (head stride ds = 48 for d = 42, ds = 96 for d = 85; pad channels are exact zeros).
+//   qkv : bf16 [B*S, ld_qkv], channel c = x*(heads*ds) + y*ds + z   (x in {q,k,v}, y head, z < ds)
+//   out : bf16 [B*S, ld_out], channel y*ds + z          P = softmax(q k^T * d^-0.5), O = P v
+//
+// One 128-row tile per work item:
+//   stage 2 (S = 100): one (image, head) problem per tile -- 100 query rows, keys padded to 112;
+//   stage 3 (S = 25) : FIVE images of one head per tile -- 125 query rows, 128 key rows, block-diagonal mask (a query only
+//                      attends to the 25 keys of its own image); the off-diagonal 80 % of the score tile is computed and
+//                      masked, which is cheaper than five 32-row problems on a 128-lane tensor core.
+// Persistent, warp-specialised CTA (one per SM, 320 threads):
+//   warp 0      TMA producer: Q, K, V boxes (64 channels x rows, SWIZZLE_128B) of the tile into a 2-stage ring;
+//   warp 1      MMA issuer: S = Q K^T (K-major operands, N = keys) into TMEM, later O = P V with P read from shared memory
+//               (K-major, no swizzle) and V used in place as an MN-major operand (no transposed copy); software-pipelined so
+//               QK^T of tile i+1 is issued before P V of tile i;
+//   warps 2-9   two softmax groups (even / odd tiles) of four warps, one query row per thread: tcgen05.ld of the score row,
+//               running max and sum kept in registers (pass 1: max over the valid keys; pass 2: exp2 with the scale folded
+//               in, sum, bf16 probabilities to shared memory), then the O epilogue (1/sum, bf16, 32-byte global stores).
+// Accumulators: S double-buffered (2 x 128 TMEM columns), O double-buffered (2 x 128).
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace tc;
+
+template <int S_, int IPT_, int NPAD_, int KA_>
+struct ACfg {
+    static constexpr int S = S_, IPT = IPT_, NPAD = NPAD_, KA = KA_;
+    static constexpr int DP = KA_ == 1 ? 48 : 96;             // padded head width
+    static constexpr int ROWS = S_ * IPT_;                    // valid query rows per tile (<= 128)
+    static constexpr int Q_ATOM = 128 * 128;                  // 128 rows x 64 channels
+    static constexpr int KV_ATOM = NPAD_ * 128;
+    static constexpr int STAGE = KA_ * (Q_ATOM + 2 * KV_ATOM);
+    static constexpr int P_BYTES = (NPAD_ / 8) * 2048;        // [key chunk of 8][128 rows][16 B]
+    static constexpr int PBUFS = (2 * STAGE + 2 * P_BYTES + 2048 <= 232448) ? 2 : 1;
+    static constexpr int SMEM = 1024 + 2 * STAGE + PBUFS * P_BYTES + 256;
+    static constexpr int THREADS = 320;
+    static constexpr int NCHUNK = (NPAD_ + 31) / 32;          // 32-column chunks of the score row (the last one may be 16 wide)
+};
+
+template <typename C>
+__global__ void __launch_bounds__(C::THREADS, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, bf16* __restrict__ out,
+                    int B, int heads, int ld_out, float scale_log2e) {
+    constexpr int S = C::S, IPT = C::IPT, NPAD = C::NPAD, KA = C::KA, DP = C::DP;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t pbase = base + 2 * C::STAGE;
+    const uint32_t bars = pbase + C::PBUFS * C::P_BYTES;
+    // barriers (8 B each): stage_full[2] stage_empty[2] s_full[2] s_empty[2] p_full[2] p_empty[2] o_full[2] o_empty[2] | tmem slot
+    auto BAR = [&](int kind, int i) { return bars + 8u * (kind * 2 + i); };
+    enum { STAGE_FULL, STAGE_EMPTY, S_FULL, S_EMPTY, P_FULL, P_EMPTY, O_FULL, O_EMPTY };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + 2 * C::STAGE + C::PBUFS * C::P_BYTES + 8 * 16);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int img_tiles = (B + IPT - 1) / IPT;
+    const int n_tiles = img_tiles * heads;
+    const int n_local = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int inner = heads * DP;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(BAR(STAGE_FULL, i), 1);
+            mbar_init(BAR(STAGE_EMPTY, i), 1);
+            mbar_init(BAR(S_FULL, i), 1);
+            mbar_init(BAR(S_EMPTY, i), 4);
+            mbar_init(BAR(P_FULL, i), 4);
+            mbar_init(BAR(P_EMPTY, i), 1);
+            mbar_init(BAR(O_FULL, i), 1);
+            mbar_init(BAR(O_EMPTY, i), 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_slot), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================================================ TMA producer
+        if (elect_one()) {
+            prefetch_tensormap(&tmQ);
+            prefetch_tensormap(&tmKV);
+        }
+        __syncwarp();
+        for (int i = 0; i < n_local; ++i) {
+            const int t = blockIdx.x + i * gridDim.x;
+            const int head = t % heads, row0 = (t / heads) * IPT * S;
+            const int s = i & 1, ph = (i >> 1) & 1;
+            mbar_wait(BAR(STAGE_EMPTY, s), ph ^ 1);
+            if (elect_one()) {
+                const uint32_t st = base + s * C::STAGE;
+                mbar_expect_tx(BAR(STAGE_FULL, s), C::STAGE);
+#pragma unroll
+                for (int a = 0; a < KA; ++a) {
+                    tma_load_2d(st + a * C::Q_ATOM, &tmQ, BAR(STAGE_FULL, s), head * DP + a * 64, row0);
+                    tma_load_2d(st + KA * C::Q_ATOM + a * C::KV_ATOM, &tmKV, BAR(STAGE_FULL, s), inner + head * DP + a * 64, row0);
+                    tma_load_2d(st + KA * (C::Q_ATOM + C::KV_ATOM) + a * C::KV_ATOM, &tmKV, BAR(STAGE_FULL, s),
+                                2 * inner + head * DP + a * 64, row0);
+                }
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // ================================================================ MMA issuer
+        constexpr uint32_t idesc_qk = make_idesc(128, NPAD);
+        constexpr uint32_t idesc_pv = make_idesc(128, KA * 64, false, true);       // B = V, MN-major
+        for (int i = 0; i <= n_local; ++i) {
+            if (i < n_local) {
+                const int s = i & 1, ph = (i >> 1) & 1;
+                mbar_wait(BAR(STAGE_FULL, s), ph);
+                mbar_wait(BAR(S_EMPTY, s), ph ^ 1);
+                tc_fence_after();
+                const uint32_t q_sm = base + s * C::STAGE, k_sm = q_sm + KA * C::Q_ATOM;
+                const uint32_t d_s = tmem_base + s * 128;
+                if (elect_one()) {
+#pragma unroll
+                    for (int a = 0; a < KA; ++a) {
+                        const int ksteps = (DP - a * 64) >= 64 ? 4 : (DP - a * 64) / 16;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (k < ksteps)
+                                umma_bf16(d_s, desc_k_sw128(q_sm + a * C::Q_ATOM + k * 32), desc_k_sw128(k_sm + a * C::KV_ATOM + k * 32),
+                                          idesc_qk, (a | k) ? 1u : 0u);
+                    }
+                    umma_commit(BAR(S_FULL, s));
+                }
+                __syncwarp();
+            }
+            if (i >= 1) {
+                const int j = i - 1, s = j & 1, ph = (j >> 1) & 1;
+                const int pb = j % C::PBUFS, pph = (j / C::PBUFS) & 1;
+                mbar_wait(BAR(P_FULL, pb), pph);
+                mbar_wait(BAR(O_EMPTY, s), ph ^ 1);
+                tc_fence_after();
+                const uint32_t v_sm = base + s * C::STAGE + KA * (C::Q_ATOM + C::KV_ATOM);
+                const uint32_t p_sm = pbase + pb * C::P_BYTES;
+                const uint32_t d_o = tmem_base + 256 + s * 128;
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < NPAD / 16; ++k)
+                        umma_bf16(d_o, desc_k_noswz(p_sm + 2 * k * 2048, 2048, 128), desc_mn_sw128(v_sm + k * 2048, C::KV_ATOM),
+                                  idesc_pv, k ? 1u : 0u);
+                    umma_commit(BAR(O_FULL, s));
+                    umma_commit(BAR(STAGE_EMPTY, s));
+                    umma_commit(BAR(P_EMPTY, pb));
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ================================================================ softmax + output: group g owns tiles g, g+2, ...
+        const int g = (warp - 2) >> 2, q = warp & 3;
+        const int r = q * 32 + lane;                                   // query row of this thread = TMEM lane
+        const int blk = r < C::ROWS ? r / S : 0;
+        const int lo = blk * S, hi = lo + S;                           // valid key columns of this row
+        // 32-column chunks any row of this warp needs (warp-uniform)
+        const int wlo = min(q * 32, C::ROWS - 1) / S * S, whi = min(q * 32 + 31, C::ROWS - 1) / S * S + S;
+        const int c_lo = wlo / 32, c_hi = (whi - 1) / 32;
+        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+        for (int i = g; i < n_local; i += 2) {
+            const int t = blockIdx.x + i * gridDim.x;
+            const int head = t % heads, img0 = (t / heads) * IPT;
+            const int rows_valid = min(IPT, B - img0) * S;
+            const int ph = (i >> 1) & 1, pb = i % C::PBUFS, pph = (i / C::PBUFS) & 1;
+            const uint32_t t_s = tmem_base + lane_sel + g * 128;
+            mbar_wait(BAR(S_FULL, g), ph);
+            tc_fence_after();
+            // ---- pass 1: row max over the valid keys
+            float mx = -INFINITY;
+#pragma unroll 1
+            for (int c = c_lo; c <= c_hi; ++c) {
+                float v[32];
+                if (NPAD - c * 32 >= 32) {
+                    tmem_ld32(t_s + c * 32, v);
+                } else {
+                    tmem_ld16(t_s + c * 32, v);
+#pragma unroll
+                    for (int jj = 16; jj < 32; ++jj) v[jj] = -INFINITY;
+                }
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) {
+                    const int col = c * 32 + jj;
+                    if (col >= lo && col < hi) mx = fmaxf(mx, v[jj]);
+                }
+            }
+            const float mxs = mx * scale_log2e;
+            // ---- pass 2: probabilities (un-normalised, <= 1) -> shared memory as the K-major A operand of P V
+            mbar_wait(BAR(P_EMPTY, pb), pph ^ 1);
+            uint8_t* prow = base_ptr + 2 * C::STAGE + pb * C::P_BYTES + r * 16;
+            float sum = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < C::NCHUNK; ++c) {
+                const int width = (NPAD - c * 32 >= 32) ? 32 : 16;
+                if (c < c_lo || c > c_hi) {                            // no row of this warp attends to these keys
+                    for (int jj = 0; jj < width / 8; ++jj)
+                        *reinterpret_cast<uint4*>(prow + (c * 4 + jj) * 2048) = make_uint4(0, 0, 0, 0);
+                    continue;
+                }
+                float v[32];
+                if (width == 32) {
+                    tmem_ld32(t_s + c * 32, v);
+                } else {
+                    tmem_ld16(t_s + c * 32, v);
+                }
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) {
+                    const int col = c * 32 + jj;
+                    const float e = (col >= lo && col < hi && jj < width) ? ex2_approx(fmaf(v[jj], scale_log2e, -mxs)) : 0.f;
+                    v[jj] = e;
+                    sum += e;
+                }
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    if (jj * 8 < width) {
+                        uint4 u;
+                        u.x = pack_bf16x2(v[jj * 8 + 0], v[jj * 8 + 1]);
+                        u.y = pack_bf16x2(v[jj * 8 + 2], v[jj * 8 + 3]);
+                        u.z = pack_bf16x2(v[jj * 8 + 4], v[jj * 8 + 5]);
+                        u.w = pack_bf16x2(v[jj * 8 + 6], v[jj * 8 + 7]);
+                        *reinterpret_cast<uint4*>(prow + (c * 4 + jj) * 2048) = u;
+                    }
+                }
+            }
+            // scores consumed -> S buffer back to the MMA warp; probabilities written -> visible to the tensor core
+            tc_fence_before();
+            fence_async_proxy();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(BAR(S_EMPTY, g));
+                mbar_arrive(BAR(P_FULL, pb));
+            }
+            const float inv = 1.f / sum;
+            // ---- output: O / sum -> bf16, DP channels of this head
+            mbar_wait(BAR(O_FULL, g), ph);
+            tc_fence_after();
+            const uint32_t t_o = tmem_base + lane_sel + 256 + g * 128;
+            bf16* orow = out + ((size_t)img0 * S + r) * ld_out + head * DP;
+#pragma unroll
+            for (int c = 0; c < DP / 32; ++c) {
+                float v[32];
+                tmem_ld32(t_o + c * 32, v);
+                if (r < rows_valid) {
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) v[jj] *= inv;
+                    store16_bf16(orow + c * 32, v);
+                    store16_bf16(orow + c * 32 + 16, v + 16);
+                }
+            }
+            if (DP % 32) {
+                float v[16];
+                tmem_ld16(t_o + (DP / 32) * 32, v);
+                if (r < rows_valid) {
+#pragma unroll
+                    for (int jj = 0; jj < 16; ++jj) v[jj] *= inv;
+                    store16_bf16(orow + (DP / 32) * 32, v);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(O_EMPTY, g));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_free(tmem_base, 512);
+    }
+}
+
+template <typename C>
+int launch_tc(const bf16* qkv, bf16* out, int B, int heads, int ld_qkv, int ld_out, float scale, cudaStream_t stream) {
+    CUtensorMap tmQ, tmKV;
+    cuuint64_t dims[2] = {(cuuint64_t)(3 * heads * C::DP), (cuuint64_t)B * C::S};
+    cuuint64_t strides[1] = {(cuuint64_t)ld_qkv * 2};
+    cuuint32_t boxq[2] = {64, 128}, boxkv[2] = {64, (cuuint32_t)C::NPAD};
+    SUNB_TRY(sunb_encode_tensor_map(&tmQ, qkv, 2, dims, strides, boxq));
+    SUNB_TRY(sunb_encode_tensor_map(&tmKV, qkv, 2, dims, strides, boxkv));
+    SUNB_TRY(sunb_opt_in_smem(reinterpret_cast<const void*>(&attention_tc_kernel<C>), C::SMEM));
+    const int n_tiles = ((B + C::IPT - 1) / C::IPT) * heads;
+    const int sms = sunb_num_sms();
+    const int grid = n_tiles < sms ? n_tiles : sms;
+    attention_tc_kernel<C><<<grid, C::THREADS, C::SMEM, stream>>>(tmQ, tmKV, out, B, heads, ld_out, scale * 1.4426950408889634f);
+    SUNB_CHECK_CUDA(cudaGetLastError());
+    return SUNB_OK;
+}
+
+}  // namespace
+
+// 1 when the tcgen05 kernel covers this problem (the eval engine's padded head layouts), else the caller keeps the warp-MMA
+// kernel of attention.cu (the training path's packed layout).
+int sunb_attention_tc_supported(const bf16* qkv, const bf16* out, int S, int d, int ds, int ld_qkv, int ld_out) {
+    if ((((size_t)qkv) & 15) || (((size_t)out) & 31) || (ld_qkv % 8) || (ld_out % 16)) return 0;
+    if (S == 100 && ds == 48 && d <= 48) return 1;
+    if (S == 25 && ds == 96 && d <= 96 && d > 48) return 1;
+    return 0;
+}
+
+int sunb_launch_attention_tc(const bf16* qkv, bf16* out, int B, int S, int d, int ds, int heads, int ld_qkv, int ld_out,
+                             cudaStream_t stream) {
+    const float scale = 1.0f / sqrtf((float)d);
+    if (S == 100 && ds == 48) return launch_tc<ACfg<100, 1, 112, 1>>(qkv, out, B, heads, ld_qkv, ld_out, scale, stream);
+    if (S == 25 && ds == 96) return launch_tc<ACfg<25, 5, 128, 2>>(qkv, out, B, heads, ld_qkv, ld_out, scale, stream);
+    sunb_set_error("attention_tc: unsupported shape S=%d ds=%d", S, ds);
+    return SUNB_ERR_ARG;
+}

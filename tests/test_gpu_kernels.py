@@ -127,10 +127,12 @@ def test_attention(S, d, C):
     assert (out[:, inner:] == 0).all()
 
 
+@pytest.mark.parametrize("B", [7, 301])
 @pytest.mark.parametrize("S,d,dp", [(100, 42, 48), (25, 85, 96)])
-def test_attention_padded_heads(S, d, dp):
-    """Eval-engine layout: heads padded to dp channels (zeros in, zeros out), 16-byte staged fast path."""
-    B, heads = 7, 6
+def test_attention_padded_heads(S, d, dp, B):
+    """Eval-engine layout: heads padded to dp channels (zeros in, zeros out): the tcgen05 kernel (attention_tc.cu).
+    B = 7 exercises a partial 5-image tile (S = 25), B = 301 the multi-tile software pipeline of every persistent CTA."""
+    heads = 6
     real = rnd(B * S, 3, heads, d, seed=21).bfloat16()
     qkv = torch.zeros(B * S, 3, heads, dp, device=DEV, dtype=torch.bfloat16)
     qkv[..., :d] = real
