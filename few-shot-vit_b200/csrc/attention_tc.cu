@@ -9,13 +9,15 @@
 //                      attends to the 25 keys of its own image); the off-diagonal 80 % of the score tile is computed and
 //                      masked, which is cheaper than five 32-row problems on a 128-lane tensor core.
 // Persistent, warp-specialised CTA (one per SM, 320 threads):
-//   warp 0      TMA producer: Q, K, V boxes (64 channels x rows, SWIZZLE_128B) of the tile into a 2-stage ring;
+//   warp 0      TMA producer: Q, K, V boxes (64 channels x rows, SWIZZLE_128B) of the tile; (Q, K) and V travel through
+//               separate rings -- (Q, K) is released as soon as QK^T has been issued, V lives until P V -- so the loads run
+//               several tiles ahead of the softmax (the kernel is bound by HBM latency x bytes in flight otherwise);
 //   warp 1      MMA issuer: S = Q K^T (K-major operands, N = keys) into TMEM, later O = P V with P read from shared memory
 //               (K-major, no swizzle) and V used in place as an MN-major operand (no transposed copy); software-pipelined so
 //               QK^T of tile i+1 is issued before P V of tile i;
-//   warps 2-9   two softmax groups (even / odd tiles) of four warps, one query row per thread: tcgen05.ld of the score row,
-//               running max and sum kept in registers (pass 1: max over the valid keys; pass 2: exp2 with the scale folded
-//               in, sum, bf16 probabilities to shared memory), then the O epilogue (1/sum, bf16, 32-byte global stores).
+//   warps 2-9   two softmax groups (even / odd tiles) of four warps, one query row per thread: tcgen05.ld of the whole score
+//               row into registers (the S buffer is handed back at once), max and sum in registers, exp2 with the scale
+//               folded in, bf16 probabilities to shared memory, then the O epilogue (1/sum, bf16, 32-byte global stores).
 // Accumulators: S double-buffered (2 x 128 TMEM columns), O double-buffered (2 x 128).
 #include "tc_common.cuh"
 
@@ -23,17 +25,22 @@ namespace {
 
 using namespace tc;
 
-template <int S_, int IPT_, int NPAD_, int KA_>
+template <int S_, int IPT_, int NPAD_, int KA_, int NQK_, int NV_, int PBUFS_>
 struct ACfg {
     static constexpr int S = S_, IPT = IPT_, NPAD = NPAD_, KA = KA_;
+    static constexpr int NQK = NQK_, NV = NV_, PBUFS = PBUFS_;      // ring depths: (Q, K) stages, V stages, P buffers
     static constexpr int DP = KA_ == 1 ? 48 : 96;             // padded head width
     static constexpr int ROWS = S_ * IPT_;                    // valid query rows per tile (<= 128)
     static constexpr int Q_ATOM = 128 * 128;                  // 128 rows x 64 channels
     static constexpr int KV_ATOM = NPAD_ * 128;
-    static constexpr int STAGE = KA_ * (Q_ATOM + 2 * KV_ATOM);
+    static constexpr int QK_STAGE = KA_ * (Q_ATOM + KV_ATOM);
+    static constexpr int V_STAGE = KA_ * KV_ATOM;
     static constexpr int P_BYTES = (NPAD_ / 8) * 2048;        // [key chunk of 8][128 rows][16 B]
-    static constexpr int PBUFS = (2 * STAGE + 2 * P_BYTES + 2048 <= 232448) ? 2 : 1;
-    static constexpr int SMEM = 1024 + 2 * STAGE + PBUFS * P_BYTES + 256;
+    static constexpr int V_OFF = NQK_ * QK_STAGE;
+    static constexpr int P_OFF = V_OFF + NV_ * V_STAGE;
+    static constexpr int BAR_OFF = P_OFF + PBUFS_ * P_BYTES;
+    static constexpr int SMEM = 1024 + BAR_OFF + 512;
+    static_assert(SMEM <= 232448, "attention_tc: shared memory budget");
     static constexpr int THREADS = 320;
     static constexpr int NCHUNK = (NPAD_ + 31) / 32;          // 32-column chunks of the score row (the last one may be 16 wide)
 };
@@ -46,12 +53,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t pbase = base + 2 * C::STAGE;
-    const uint32_t bars = pbase + C::PBUFS * C::P_BYTES;
-    // barriers (8 B each): stage_full[2] stage_empty[2] s_full[2] s_empty[2] p_full[2] p_empty[2] o_full[2] o_empty[2] | tmem slot
-    auto BAR = [&](int kind, int i) { return bars + 8u * (kind * 2 + i); };
-    enum { STAGE_FULL, STAGE_EMPTY, S_FULL, S_EMPTY, P_FULL, P_EMPTY, O_FULL, O_EMPTY };
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + 2 * C::STAGE + C::PBUFS * C::P_BYTES + 8 * 16);
+    const uint32_t vbase = base + C::V_OFF, pbase = base + C::P_OFF, bars = base + C::BAR_OFF;
+    // barriers (8 B each)
+    auto QK_FULL = [&](int i) { return bars + 8u * i; };
+    auto QK_EMPTY = [&](int i) { return bars + 8u * (8 + i); };
+    auto V_FULL = [&](int i) { return bars + 8u * (16 + i); };
+    auto V_EMPTY = [&](int i) { return bars + 8u * (24 + i); };
+    auto S_FULL = [&](int i) { return bars + 8u * (32 + i); };
+    auto S_EMPTY = [&](int i) { return bars + 8u * (34 + i); };
+    auto P_FULL = [&](int i) { return bars + 8u * (36 + i); };
+    auto P_EMPTY = [&](int i) { return bars + 8u * (38 + i); };
+    auto O_FULL = [&](int i) { return bars + 8u * (40 + i); };
+    auto O_EMPTY = [&](int i) { return bars + 8u * (42 + i); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + C::BAR_OFF + 8 * 44);
+    static_assert(C::NQK <= 8 && C::NV <= 8 && C::PBUFS <= 2, "barrier map");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int img_tiles = (B + IPT - 1) / IPT;
@@ -60,15 +75,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int inner = heads * DP;
 
     if (threadIdx.x == 0) {
+        for (int i = 0; i < C::NQK; ++i) { mbar_init(QK_FULL(i), 1); mbar_init(QK_EMPTY(i), 1); }
+        for (int i = 0; i < C::NV; ++i) { mbar_init(V_FULL(i), 1); mbar_init(V_EMPTY(i), 1); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(BAR(STAGE_FULL, i), 1);
-            mbar_init(BAR(STAGE_EMPTY, i), 1);
-            mbar_init(BAR(S_FULL, i), 1);
-            mbar_init(BAR(S_EMPTY, i), 4);
-            mbar_init(BAR(P_FULL, i), 4);
-            mbar_init(BAR(P_EMPTY, i), 1);
-            mbar_init(BAR(O_FULL, i), 1);
-            mbar_init(BAR(O_EMPTY, i), 4);
+            mbar_init(S_FULL(i), 1);
+            mbar_init(S_EMPTY(i), 4);
+            mbar_init(P_FULL(i), 4);
+            mbar_init(P_EMPTY(i), 1);
+            mbar_init(O_FULL(i), 1);
+            mbar_init(O_EMPTY(i), 4);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -85,23 +100,38 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             prefetch_tensormap(&tmKV);
         }
         __syncwarp();
-        for (int i = 0; i < n_local; ++i) {
-            const int t = blockIdx.x + i * gridDim.x;
-            const int head = t % heads, row0 = (t / heads) * IPT * S;
-            const int s = i & 1, ph = (i >> 1) & 1;
-            mbar_wait(BAR(STAGE_EMPTY, s), ph ^ 1);
-            if (elect_one()) {
-                const uint32_t st = base + s * C::STAGE;
-                mbar_expect_tx(BAR(STAGE_FULL, s), C::STAGE);
+        // Q / K loads run one tile ahead of the V loads: a full V ring (V lives until P V) must not hold back the next Q K^T
+        for (int i = 0; i <= n_local; ++i) {
+            if (i < n_local) {
+                const int t = blockIdx.x + i * gridDim.x;
+                const int head = t % heads, row0 = (t / heads) * IPT * S;
+                const int sq = i % C::NQK;
+                mbar_wait(QK_EMPTY(sq), ((i / C::NQK) & 1) ^ 1);
+                if (elect_one()) {
+                    const uint32_t st = base + sq * C::QK_STAGE;
+                    mbar_expect_tx(QK_FULL(sq), C::QK_STAGE);
 #pragma unroll
-                for (int a = 0; a < KA; ++a) {
-                    tma_load_2d(st + a * C::Q_ATOM, &tmQ, BAR(STAGE_FULL, s), head * DP + a * 64, row0);
-                    tma_load_2d(st + KA * C::Q_ATOM + a * C::KV_ATOM, &tmKV, BAR(STAGE_FULL, s), inner + head * DP + a * 64, row0);
-                    tma_load_2d(st + KA * (C::Q_ATOM + C::KV_ATOM) + a * C::KV_ATOM, &tmKV, BAR(STAGE_FULL, s),
-                                2 * inner + head * DP + a * 64, row0);
+                    for (int a = 0; a < KA; ++a) {
+                        tma_load_2d(st + a * C::Q_ATOM, &tmQ, QK_FULL(sq), head * DP + a * 64, row0);
+                        tma_load_2d(st + KA * C::Q_ATOM + a * C::KV_ATOM, &tmKV, QK_FULL(sq), inner + head * DP + a * 64, row0);
+                    }
                 }
+                __syncwarp();
             }
-            __syncwarp();
+            if (i >= 1) {
+                const int j = i - 1;
+                const int t = blockIdx.x + j * gridDim.x;
+                const int head = t % heads, row0 = (t / heads) * IPT * S;
+                const int sv = j % C::NV;
+                mbar_wait(V_EMPTY(sv), ((j / C::NV) & 1) ^ 1);
+                if (elect_one()) {
+                    mbar_expect_tx(V_FULL(sv), C::V_STAGE);
+#pragma unroll
+                    for (int a = 0; a < KA; ++a)
+                        tma_load_2d(vbase + sv * C::V_STAGE + a * C::KV_ATOM, &tmKV, V_FULL(sv), 2 * inner + head * DP + a * 64, row0);
+                }
+                __syncwarp();
+            }
         }
     } else if (warp == 1) {
         // ================================================================ MMA issuer
@@ -109,11 +139,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         constexpr uint32_t idesc_pv = make_idesc(128, KA * 64, false, true);       // B = V, MN-major
         for (int i = 0; i <= n_local; ++i) {
             if (i < n_local) {
-                const int s = i & 1, ph = (i >> 1) & 1;
-                mbar_wait(BAR(STAGE_FULL, s), ph);
-                mbar_wait(BAR(S_EMPTY, s), ph ^ 1);
+                const int s = i & 1, ph = (i >> 1) & 1, sq = i % C::NQK;
+                mbar_wait(QK_FULL(sq), (i / C::NQK) & 1);
+                mbar_wait(S_EMPTY(s), ph ^ 1);
                 tc_fence_after();
-                const uint32_t q_sm = base + s * C::STAGE, k_sm = q_sm + KA * C::Q_ATOM;
+                const uint32_t q_sm = base + sq * C::QK_STAGE, k_sm = q_sm + KA * C::Q_ATOM;
                 const uint32_t d_s = tmem_base + s * 128;
                 if (elect_one()) {
 #pragma unroll
@@ -125,17 +155,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                                 umma_bf16(d_s, desc_k_sw128(q_sm + a * C::Q_ATOM + k * 32), desc_k_sw128(k_sm + a * C::KV_ATOM + k * 32),
                                           idesc_qk, (a | k) ? 1u : 0u);
                     }
-                    umma_commit(BAR(S_FULL, s));
+                    umma_commit(S_FULL(s));
+                    umma_commit(QK_EMPTY(sq));          // Q and K are dead once QK^T has run: refill while the softmax works
                 }
                 __syncwarp();
             }
             if (i >= 1) {
-                const int j = i - 1, s = j & 1, ph = (j >> 1) & 1;
+                const int j = i - 1, s = j & 1, ph = (j >> 1) & 1, sv = j % C::NV;
                 const int pb = j % C::PBUFS, pph = (j / C::PBUFS) & 1;
-                mbar_wait(BAR(P_FULL, pb), pph);
-                mbar_wait(BAR(O_EMPTY, s), ph ^ 1);
+                mbar_wait(V_FULL(sv), (j / C::NV) & 1);
+                mbar_wait(P_FULL(pb), pph);
+                mbar_wait(O_EMPTY(s), ph ^ 1);
                 tc_fence_after();
-                const uint32_t v_sm = base + s * C::STAGE + KA * (C::Q_ATOM + C::KV_ATOM);
+                const uint32_t v_sm = vbase + sv * C::V_STAGE;
                 const uint32_t p_sm = pbase + pb * C::P_BYTES;
                 const uint32_t d_o = tmem_base + 256 + s * 128;
                 if (elect_one()) {
@@ -143,9 +175,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     for (int k = 0; k < NPAD / 16; ++k)
                         umma_bf16(d_o, desc_k_noswz(p_sm + 2 * k * 2048, 2048, 128), desc_mn_sw128(v_sm + k * 2048, C::KV_ATOM),
                                   idesc_pv, k ? 1u : 0u);
-                    umma_commit(BAR(O_FULL, s));
-                    umma_commit(BAR(STAGE_EMPTY, s));
-                    umma_commit(BAR(P_EMPTY, pb));
+                    umma_commit(O_FULL(s));
+                    umma_commit(V_EMPTY(sv));
+                    umma_commit(P_EMPTY(pb));
                 }
                 __syncwarp();
             }
@@ -158,7 +190,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const int lo = blk * S, hi = lo + S;                           // valid key columns of this row
         // 32-column chunks any row of this warp needs (warp-uniform)
         const int wlo = min(q * 32, C::ROWS - 1) / S * S, whi = min(q * 32 + 31, C::ROWS - 1) / S * S + S;
-        const int c_lo = wlo / 32, c_hi = (whi - 1) / 32;
+        const int c_lo = IPT == 1 ? 0 : wlo / 32, c_hi = IPT == 1 ? (S - 1) / 32 : (whi - 1) / 32;
         const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
         for (int i = g; i < n_local; i += 2) {
             const int t = blockIdx.x + i * gridDim.x;
@@ -166,75 +198,84 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             const int rows_valid = min(IPT, B - img0) * S;
             const int ph = (i >> 1) & 1, pb = i % C::PBUFS, pph = (i / C::PBUFS) & 1;
             const uint32_t t_s = tmem_base + lane_sel + g * 128;
-            mbar_wait(BAR(S_FULL, g), ph);
+            mbar_wait(S_FULL(g), ph);
             tc_fence_after();
-            // ---- pass 1: row max over the valid keys
-            float mx = -INFINITY;
-#pragma unroll 1
-            for (int c = c_lo; c <= c_hi; ++c) {
-                float v[32];
-                if (NPAD - c * 32 >= 32) {
-                    tmem_ld32(t_s + c * 32, v);
-                } else {
-                    tmem_ld16(t_s + c * 32, v);
+            // ---- the score row in registers (only the 32-column chunks a row of this warp attends to: all of them for one
+            //      image per tile, at most NL = 3 of 4 with five images per tile); the S buffer goes straight back to the MMA warp
+            constexpr int NL = (IPT == 1) ? C::NCHUNK : 3;
+            float v[NL][32];
 #pragma unroll
-                    for (int jj = 16; jj < 32; ++jj) v[jj] = -INFINITY;
-                }
+            for (int k = 0; k < NL; ++k) {
+                const int c = c_lo + k;
+                if (c > c_hi) continue;                                // warp-uniform
+                if (IPT == 1 && NPAD - k * 32 < 32) tmem_ld16(t_s + c * 32, v[k]);
+                else tmem_ld32(t_s + c * 32, v[k]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(S_EMPTY(g));
+            // ---- row max over the valid keys, then exp2 with the scale folded in, sum, bf16 probabilities (packed in place)
+            float mx = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < NL; ++k) {
+                const int c = c_lo + k;
+                if (c > c_hi) continue;
 #pragma unroll
                 for (int jj = 0; jj < 32; ++jj) {
                     const int col = c * 32 + jj;
-                    if (col >= lo && col < hi) mx = fmaxf(mx, v[jj]);
+                    if (IPT == 1 && k * 32 + jj >= NPAD) continue;
+                    const bool ok = (IPT == 1) ? (k * 32 + jj < S) : (col >= lo && col < hi);
+                    if (ok) mx = fmaxf(mx, v[k][jj]);
                 }
             }
             const float mxs = mx * scale_log2e;
-            // ---- pass 2: probabilities (un-normalised, <= 1) -> shared memory as the K-major A operand of P V
-            mbar_wait(BAR(P_EMPTY, pb), pph ^ 1);
-            uint8_t* prow = base_ptr + 2 * C::STAGE + pb * C::P_BYTES + r * 16;
             float sum = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < C::NCHUNK; ++c) {
-                const int width = (NPAD - c * 32 >= 32) ? 32 : 16;
-                if (c < c_lo || c > c_hi) {                            // no row of this warp attends to these keys
-                    for (int jj = 0; jj < width / 8; ++jj)
-                        *reinterpret_cast<uint4*>(prow + (c * 4 + jj) * 2048) = make_uint4(0, 0, 0, 0);
-                    continue;
-                }
-                float v[32];
-                if (width == 32) {
-                    tmem_ld32(t_s + c * 32, v);
-                } else {
-                    tmem_ld16(t_s + c * 32, v);
-                }
+            uint32_t pk[NL][16];                                       // bf16 pairs of this row's probabilities
+#pragma unroll
+            for (int k = 0; k < NL; ++k) {
+                const int c = c_lo + k;
+                if (c > c_hi) continue;
 #pragma unroll
                 for (int jj = 0; jj < 32; ++jj) {
                     const int col = c * 32 + jj;
-                    const float e = (col >= lo && col < hi && jj < width) ? ex2_approx(fmaf(v[jj], scale_log2e, -mxs)) : 0.f;
-                    v[jj] = e;
+                    const bool in = !(IPT == 1 && k * 32 + jj >= NPAD);
+                    const bool ok = in && ((IPT == 1) ? (k * 32 + jj < S) : (col >= lo && col < hi));
+                    const float e = ok ? ex2_approx(fmaf(v[k][jj], scale_log2e, -mxs)) : 0.f;
+                    v[k][jj] = e;
                     sum += e;
                 }
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                    if (jj * 8 < width) {
-                        uint4 u;
-                        u.x = pack_bf16x2(v[jj * 8 + 0], v[jj * 8 + 1]);
-                        u.y = pack_bf16x2(v[jj * 8 + 2], v[jj * 8 + 3]);
-                        u.z = pack_bf16x2(v[jj * 8 + 4], v[jj * 8 + 5]);
-                        u.w = pack_bf16x2(v[jj * 8 + 6], v[jj * 8 + 7]);
-                        *reinterpret_cast<uint4*>(prow + (c * 4 + jj) * 2048) = u;
+                for (int jj = 0; jj < 16; ++jj) pk[k][jj] = pack_bf16x2(v[k][2 * jj], v[k][2 * jj + 1]);
+            }
+            // the P buffer is free once P V of the tile that used it has completed; only the stores sit behind that wait
+            mbar_wait(P_EMPTY(pb), pph ^ 1);
+            uint8_t* prow = base_ptr + C::P_OFF + pb * C::P_BYTES + r * 16;
+            if (IPT != 1) {                                            // key chunks no row of this warp attends to: zeros
+#pragma unroll
+                for (int c = 0; c < C::NCHUNK; ++c)
+                    if (c < c_lo || c > c_hi) {
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) *reinterpret_cast<uint4*>(prow + (c * 4 + jj) * 2048) = make_uint4(0, 0, 0, 0);
                     }
+            }
+#pragma unroll
+            for (int k = 0; k < NL; ++k) {
+                const int c = c_lo + k;
+                if (c > c_hi) continue;
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    if (IPT == 1 && k * 32 + jj * 8 >= NPAD) continue;
+                    *reinterpret_cast<uint4*>(prow + (c * 4 + jj) * 2048) =
+                        make_uint4(pk[k][jj * 4], pk[k][jj * 4 + 1], pk[k][jj * 4 + 2], pk[k][jj * 4 + 3]);
                 }
             }
-            // scores consumed -> S buffer back to the MMA warp; probabilities written -> visible to the tensor core
-            tc_fence_before();
+            // probabilities written -> visible to the tensor core (async proxy)
             fence_async_proxy();
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(BAR(S_EMPTY, g));
-                mbar_arrive(BAR(P_FULL, pb));
-            }
+            if (lane == 0) mbar_arrive(P_FULL(pb));
             const float inv = 1.f / sum;
             // ---- output: O / sum -> bf16, DP channels of this head
-            mbar_wait(BAR(O_FULL, g), ph);
+            mbar_wait(O_FULL(g), ph);
             tc_fence_after();
             const uint32_t t_o = tmem_base + lane_sel + 256 + g * 128;
             bf16* orow = out + ((size_t)img0 * S + r) * ld_out + head * DP;
@@ -260,7 +301,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(O_EMPTY, g));
+            if (lane == 0) mbar_arrive(O_EMPTY(g));
         }
     }
 
@@ -303,8 +344,8 @@ int sunb_attention_tc_supported(const bf16* qkv, const bf16* out, int S, int d, 
 int sunb_launch_attention_tc(const bf16* qkv, bf16* out, int B, int S, int d, int ds, int heads, int ld_qkv, int ld_out,
                              cudaStream_t stream) {
     const float scale = 1.0f / sqrtf((float)d);
-    if (S == 100 && ds == 48) return launch_tc<ACfg<100, 1, 112, 1>>(qkv, out, B, heads, ld_qkv, ld_out, scale, stream);
-    if (S == 25 && ds == 96) return launch_tc<ACfg<25, 5, 128, 2>>(qkv, out, B, heads, ld_qkv, ld_out, scale, stream);
+    if (S == 100 && ds == 48) return launch_tc<ACfg<100, 1, 112, 1, 3, 5, 2>>(qkv, out, B, heads, ld_qkv, ld_out, scale, stream);
+    if (S == 25 && ds == 96) return launch_tc<ACfg<25, 5, 128, 2, 2, 2, 1>>(qkv, out, B, heads, ld_qkv, ld_out, scale, stream);
     sunb_set_error("attention_tc: unsupported shape S=%d ds=%d", S, ds);
     return SUNB_ERR_ARG;
 }
