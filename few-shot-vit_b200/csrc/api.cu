@@ -38,6 +38,7 @@ int sunb_launch_wgrad_tc(WgradParams p, cudaStream_t stream);
 int sunb_launch_layernorm_rows(const float* x, const float* gamma, const float* beta, float* y, long M, int C, float eps,
                                cudaStream_t stream);
 
+extern "C" int sunb_convmlp_tail(const void* h1, const void* wblob, const void* resid, void* out, int B, int s2d, void* stream);
 extern "C" int sunb_gconv3x3(const void* x, int ldx, const void* wg, void* y, int ldy, void* y2, int ldy2, const void* aux,
                              int ldaux, int B, int act, int dact, void* stream);
 
@@ -83,7 +84,7 @@ namespace {
 constexpr int HEADS = 6;
 
 struct Workspace {
-    bf16 *a1, *idn, *a2, *c3, *s1, *h1, *h2, *s1d, *t2, *qkv2, *ao2, *hid2, *t2d, *t3, *qkv3, *ao3, *hid3;
+    bf16 *a1, *idn, *a2, *c3, *s1, *h1, *s1b, *s1d, *t2, *qkv2, *ao2, *hid2, *t2d, *t3, *qkv3, *ao3, *hid3;
     size_t bytes;
 };
 
@@ -102,7 +103,7 @@ Workspace carve(void* base, int B) {
     w.c3 = take(b * 1600 * 128);
     w.s1 = take(b * 400 * 128);
     w.h1 = take(b * 400 * 256);
-    w.h2 = take(b * 400 * 256);
+    w.s1b = take(b * 400 * 128);       // stage-1 residual stream ping-pong (the fused block tail cannot run in place)
     w.s1d = take(b * 400 * 128);
     w.t2 = take(b * 100 * 256);
     w.qkv2 = take(b * 100 * 864);      // 3 x 6 heads x 48 (d = 42 padded)
@@ -215,26 +216,25 @@ int sunb_encoder_forward(const SunbEncoderWeights* w, const float* x, int B, voi
     SUNB_TRY(tap_copy(tp.stem, ws.s1, (size_t)B * 400 * 128, st));
 
     // ---- stage 1: x + conv3(gelu(gconv3x3(gelu(conv1(bn(x))))))  (visformer.py:152-163, 259-263)
+    //      conv1 + GELU as a tcgen05 GEMM, then ONE fused kernel for grouped 3x3 + GELU + conv3 + residual (convmlp_tc.cu)
+    bf16* cur = ws.s1;
+    bf16* nxt = ws.s1b;
     for (int i = 0; i < 4; ++i) {
         const SunbConvMlpW& bw = w->s1[i];
         const bool last = (i == 3);
-        GemmParams p = base_gemm(B * 400, 256, 128, ws.s1, 128, bw.w1, 128, ws.h1, 256);
+        GemmParams p = base_gemm(B * 400, 256, 128, cur, 128, bw.w1, 128, ws.h1, 256);
         p.bias = bw.b1; p.act = ACT_GELU;
         SUNB_TRY(sunb_launch_gemm(p, st));
-        SUNB_TRY(sunb_gconv3x3(ws.h1, 256, bw.w2, ws.h2, 256, nullptr, 0, nullptr, 0, B, ACT_GELU, ACT_NONE, stream));
-        p = base_gemm(B * 400, 128, 256, ws.h2, 256, bw.w3, 256, last ? ws.s1d : ws.s1, 128);
-        p.resid = ws.s1; p.ldr = 128;
-        if (last) { p.out_map = MAP_S2D; p.oH = 20; p.oW = 20; }
-        SUNB_TRY(sunb_launch_gemm(p, st));
+        // the last block stores its output 2x2 space-to-depth for the PatchEmbed GEMM
+        SUNB_TRY(sunb_convmlp_tail(ws.h1, bw.w23, cur, last ? ws.s1d : nxt, B, last ? 1 : 0, stream));
         if (tp.stage1[i]) {
             if (last) {   // the raster copy only exists for the test tap
-                GemmParams q = p;
-                q.out = reinterpret_cast<bf16*>(tp.stage1[i]); q.out_map = MAP_IDENT;
-                SUNB_TRY(sunb_launch_gemm(q, st));
+                SUNB_TRY(sunb_convmlp_tail(ws.h1, bw.w23, cur, tp.stage1[i], B, 0, stream));
             } else {
-                SUNB_TRY(tap_copy(tp.stage1[i], ws.s1, (size_t)B * 400 * 128, st));
+                SUNB_TRY(tap_copy(tp.stage1[i], nxt, (size_t)B * 400 * 128, st));
             }
         }
+        bf16* t = cur; cur = nxt; nxt = t;
     }
 
     // ---- patch_embed2 + pos_embed2 (visformer.py:438-441): GEMM over the space-to-depth view [B*100, 512]

@@ -54,7 +54,7 @@ class OptTensor(C.Structure):
 
 
 class ConvMlpW(C.Structure):
-    _fields_ = [("w1", vp), ("b1", fp), ("w2", vp), ("w3", vp)]
+    _fields_ = [("w1", vp), ("b1", fp), ("w2", vp), ("w3", vp), ("w23", vp)]
 
 
 class AttnBlockW(C.Structure):
@@ -119,17 +119,19 @@ SIGNATURES = {
     "sunb_grouped_wgrad_extract": (C.c_int, [fp, fp, vp]),
     "sunb_gconv3x3": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "sunb_gconv_pack": (C.c_int, [fp, vp, C.c_int, vp]),
+    "sunb_convmlp_tail": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, vp]),
     "sunb_layernorm_rows": (C.c_int, [fp, fp, fp, fp, C.c_long, C.c_int, C.c_float, vp]),
     "sunb_attention_backward": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "sunb_episode_logits_backward": (C.c_int, [fp, fp, fp, fp, fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                C.c_int, fp, C.c_float, vp]),
+    "sunb_preprocess_u8": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, fp, fp, vp]),
     # fused multi-tensor optimizers
     "sunb_fused_sgd": (C.c_int, [C.POINTER(OptTensor), C.c_int, fp, vp]),
     "sunb_fused_adamw": (C.c_int, [C.POINTER(OptTensor), C.c_int, fp, vp]),
 }
 
 _lib = None
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 def lib() -> C.CDLL:

@@ -52,6 +52,18 @@ def _grouped_taps(w: torch.Tensor, groups: int = 8) -> torch.Tensor:
     return w.reshape(groups, opg, cpg, 9).permute(0, 3, 1, 2).contiguous()
 
 
+def _convmlp_tail_blob(w2: torch.Tensor, w3: torch.Tensor, groups: int = 8) -> torch.Tensor:
+    """Operand blob of sunb_convmlp_tail: per group g [grouped taps: 9 x 4 k-chunks x 32 n x 8 k | conv3 slice: 4 k-chunks x
+    128 n x 8 k] -- both no-swizzle K-major UMMA operands (core matrix = 8 rows x 16 bytes), 26,624 bytes per group.
+    w2 [256, 32, 3, 3] grouped 3x3 weight, w3 [128, 256] (conv3 as a matrix); returns a flat tensor of w2's dtype."""
+    n_out, cpg = w2.shape[0], w2.shape[1]
+    opg = n_out // groups
+    taps = w2.reshape(groups, opg, cpg, 9).permute(0, 3, 1, 2)                      # [g][tap][n][k]
+    a = taps.reshape(groups, 9, opg, cpg // 8, 8).permute(0, 1, 3, 2, 4)            # [g][tap][c][n][8]
+    b = w3.reshape(w3.shape[0], groups, cpg // 8, 8).permute(1, 2, 0, 3)            # [g][c][n][8]
+    return torch.cat([a.reshape(groups, -1), b.reshape(groups, -1)], dim=1).contiguous().reshape(-1)
+
+
 def _pad_cols(w: torch.Tensor, mult: int = 8) -> torch.Tensor:
     k = w.shape[1]
     kp = (k + mult - 1) // mult * mult
@@ -101,6 +113,7 @@ def pack_encoder(sd: Dict[str, torch.Tensor], prefix: str = "", wdtype: torch.dt
         P[f"s1.{i}.b1"] = (w1 @ t).contiguous()
         P[f"s1.{i}.w2"] = _grouped_taps(g[b + "mlp.conv2.weight"].float()).to(wdtype)
         P[f"s1.{i}.w3"] = w2d(b + "mlp.conv3.weight").to(wdtype).contiguous()
+        P[f"s1.{i}.w23"] = _convmlp_tail_blob(g[b + "mlp.conv2.weight"].float(), w2d(b + "mlp.conv3.weight")).to(wdtype)
 
     for stage, depth, hw in (("2", DEPTH[1], 100), ("3", DEPTH[2], 25)):
         pe = f"patch_embed{stage}."
@@ -138,7 +151,7 @@ def to_struct(P: Dict[str, torch.Tensor]):
               "pe2_w", "pe2_bias", "pe3_w", "pe3_bias", "final_scale", "final_shift"):
         setattr(w, f, P[f].data_ptr())
     for i in range(4):
-        for f in ("w1", "b1", "w2", "w3"):
+        for f in ("w1", "b1", "w2", "w3", "w23"):
             setattr(w.s1[i], f, P[f"s1.{i}.{f}"].data_ptr())
     for stage, arr, depth in (("2", w.s2, 2), ("3", w.s3, 3)):
         for i in range(depth):

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SUNB_ABI_VERSION 4
+#define SUNB_ABI_VERSION 5
 
 int sunb_abi_version(void);
 const char* sunb_last_error(void);
@@ -77,8 +77,10 @@ int sunb_gemm(const SunbGemmDesc* desc, int impl, void* stream);
  * ------------------------------------------------------------------------------------------------- */
 typedef struct SunbConvMlpW {        /* stage-1 Block: norm2 folded into conv1 */
     const void* w1; const float* b1; /* bf16 [256][128], fp32 [256] */
-    const void* w2;                  /* bf16 grouped 3x3 weights [8 groups][9 taps][32 n][32 k] */
-    const void* w3;                  /* bf16 [128][256] */
+    const void* w2;                  /* bf16 grouped 3x3 weights [8 groups][9 taps][32 n][32 k] (stand-alone sunb_gconv3x3) */
+    const void* w3;                  /* bf16 [128][256] (stand-alone conv3 GEMM) */
+    const void* w23;                 /* operand blob of the fused block tail (sunb_convmlp_tail): per group g 26,624 bytes =
+                                      * grouped taps [9][4 k-chunks][32 n][8 k] then the conv3 slice [4 k-chunks][128 n][8 k] */
 } SunbConvMlpW;
 
 typedef struct SunbAttnBlockW {      /* stage-2/3 Block: norm1 folded into qkv, norm2 into mlp.conv1 */
@@ -235,12 +237,28 @@ int sunb_gconv3x3(const void* x, int ldx, const void* wg, void* y, int ldy, void
                   int B, int act, int dact, void* stream);
 int sunb_gconv_pack(const float* w, void* dst, int transpose_flip, void* stream);
 
+/* Fused tail of the stage-1 conv-MLP block, eval mode (Mlp.conv2 + GELU + conv3 and the Block residual, visformer.py:146-163,
+ * 259-263):  out = resid + conv3(gelu(gconv3x3(h1))).  h1: bf16 [B*400, 256] = gelu(conv1(bn(x))); wblob: SunbConvMlpW.w23;
+ * resid, out: bf16 [B*400, 128] (out != resid); s2d = 1 stores the rows 2x2 space-to-depth (input order of the following
+ * PatchEmbed GEMM).  The 256-channel hidden tensor between the grouped conv and conv3 never leaves the SM. */
+int sunb_convmlp_tail(const void* h1, const void* wblob, const void* resid, void* out, int B, int s2d, void* stream);
+
 /* backward of the attention core and of the episode head */
 int sunb_attention_backward(const void* qkv, const void* dout, void* dqkv, int B, int S, int d, int heads, int ld_qkv,
                             int ld_out, void* stream);
 int sunb_episode_logits_backward(const float* feat_shot, const float* feat_query, const float* dlogits, float* dshot,
                                  float* dquery, float* dtemp, int E, int way, int shot, int Q, int D, int metric,
                                  const float* temp_dev, float temp_host, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * On-device input path (test_phase/datasets/mini_imagenet.py:50-56 default_transform): uint8 HWC images [N, in, in, 3]
+ * resident in HBM -> PIL-exact bilinear Resize -> CenterCrop -> ToTensor -> Normalize -> fp32 NCHW [n, 3, out, out].
+ * idx (nullable): int64 [n] gather index into the image store (the flat batch of a CategoriesSampler).
+ * tab_min int32 [out], tab_k int32 [out][3]: first source index and 22-bit fixed-point weights of every CROPPED output
+ * position (PIL precompute_coeffs / normalize_coeffs_8bpc; built by sunb200/input.py); mean_std fp32 [6].
+ * ------------------------------------------------------------------------------------------------- */
+int sunb_preprocess_u8(const void* data, const int64_t* idx, int n, int in_size, int out_size, const int32_t* tab_min,
+                       const int32_t* tab_k, const float* mean_std, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Fused multi-tensor optimizers: one launch updates every parameter tensor (all fp32).

@@ -469,3 +469,47 @@ def calibrate_bn(sd: SD, prefix: str = "encoder.", seed: int = 0, passes: int = 
             for k, v in st.updates.items():
                 sd[prefix + k] = v
     return sd
+
+
+# --------------------------------------------------------------------------------------
+# Input transform (test_phase/datasets/mini_imagenet.py:50-56): Resize((88,88)) -> CenterCrop(80) -> ToTensor -> Normalize
+# --------------------------------------------------------------------------------------
+def _pil_bilinear_coeffs(in_size: int, out_size: int):
+    """PIL Resample.c precompute_coeffs (bilinear: support 1) + normalize_coeffs_8bpc (22 fractional bits)."""
+    import numpy as np
+    scale = in_size / out_size
+    fscale = max(scale, 1.0)
+    support = 1.0 * fscale
+    ks = []
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        w = np.array([max(0.0, 1.0 - abs((x + xmin - center + 0.5) / fscale)) for x in range(xmax)], dtype=np.float64)
+        w = w / w.sum()
+        kk = np.where(w < 0, (-0.5 + w * (1 << 22)).astype(np.int64), (0.5 + w * (1 << 22)).astype(np.int64))
+        ks.append((xmin, kk))
+    return ks
+
+
+def _pil_resample_axis(a, ks, axis):
+    import numpy as np
+    a = np.moveaxis(a, axis, 0).astype(np.int64)
+    out = np.empty((len(ks),) + a.shape[1:], dtype=np.int64)
+    for i, (xmin, kk) in enumerate(ks):
+        out[i] = np.clip(((1 << 21) + np.tensordot(kk, a[xmin:xmin + len(kk)], axes=(0, 0))) >> 22, 0, 255)
+    return np.moveaxis(out.astype(np.uint8), 0, axis)
+
+
+def default_transform(img_u8, resize: int = 88, crop: int = 80, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)) -> Tensor:
+    """One uint8 HWC image [S, S, 3] -> fp32 [3, crop, crop].  PIL resamples 8-bit images in fixed point, horizontally
+    first, rounding / clipping to uint8 after each pass; CenterCrop offset = round((resize - crop) / 2); ToTensor = /255;
+    Normalize = (x - mean) / std in fp32."""
+    import numpy as np
+    a = np.asarray(img_u8)
+    ks = _pil_bilinear_coeffs(a.shape[0], resize)
+    r = _pil_resample_axis(_pil_resample_axis(a, ks, 1), ks, 0)
+    off = int(round((resize - crop) / 2.0))
+    c = r[off:off + crop, off:off + crop]
+    f = torch.from_numpy(np.ascontiguousarray(c)).permute(2, 0, 1).float().div(255)
+    return (f - torch.tensor(mean).view(3, 1, 1)) / torch.tensor(std).view(3, 1, 1)

@@ -307,3 +307,26 @@ def test_gconv3x3_forward_and_dgrad():
     gprime = 0.5 * (1 + torch.erf(a * 0.70710678118654752)) + a * torch.exp(-0.5 * a * a) * 0.3989422804014327
     ref_dx = xf.grad.permute(0, 2, 3, 1).reshape(-1, 256) * gprime
     assert rel_err(dx, ref_dx) < 1e-2
+
+
+@pytest.mark.parametrize("B,s2d", [(1, 0), (3, 1), (301, 0)])
+def test_convmlp_tail_fused(B, s2d):
+    """sunb_convmlp_tail: out = resid + conv3(gelu(gconv3x3(h1))) in one kernel vs torch (fp32 on the same bf16 operands)."""
+    from sunb200 import packing
+    h1 = rnd(B * 400, 256, seed=70).bfloat16()
+    x = rnd(B * 400, 128, seed=71).bfloat16()
+    w2 = rnd(256, 32, 3, 3, seed=72, scale=(9 * 32) ** -0.5)
+    w3 = rnd(128, 256, seed=73, scale=256 ** -0.5)
+    blob = packing._convmlp_tail_blob(w2, w3).bfloat16().contiguous()
+    out = torch.full((B * 400, 128), float("nan"), device=DEV, dtype=torch.bfloat16)
+    N.check(N.lib().sunb_convmlp_tail(h1.data_ptr(), blob.data_ptr(), x.data_ptr(), out.data_ptr(), B, s2d, N.current_stream()),
+            "sunb_convmlp_tail")
+    torch.cuda.synchronize()
+    hf = h1.float().view(B, 20, 20, 256).permute(0, 3, 1, 2)
+    h2 = act_ref(F.conv2d(hf, w2.bfloat16().float(), padding=1, groups=8), 2).bfloat16().float()     # the kernel rounds h2 to bf16
+    y = F.conv2d(h2, w3.bfloat16().float().view(128, 256, 1, 1)).permute(0, 2, 3, 1).reshape(B, 20, 20, 128) + x.float().view(B, 20, 20, 128)
+    if s2d:
+        y = y.reshape(B, 10, 2, 10, 2, 128).permute(0, 1, 3, 2, 4, 5)
+    ref = y.reshape(B * 400, 128)
+    assert torch.isfinite(out.float()).all()
+    assert rel_err(out, ref) < BF16_OUT

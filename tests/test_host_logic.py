@@ -51,6 +51,21 @@ def test_packed_layouts():
         assert v.is_contiguous(), k
 
 
+def test_convmlp_tail_blob_layout():
+    """Operand blob of the fused stage-1 block tail: no-swizzle K-major core matrices, 26,624 bytes per group."""
+    g = torch.Generator().manual_seed(3)
+    w2 = torch.randn(256, 32, 3, 3, generator=g)
+    w3 = torch.randn(128, 256, generator=g)
+    blob = packing._convmlp_tail_blob(w2, w3).reshape(8, -1)
+    assert blob.shape[1] * 2 == 26624                      # bytes per group in bf16
+    for (grp, tap, n, k) in [(0, 0, 0, 0), (3, 5, 17, 9), (7, 8, 31, 31), (2, 4, 8, 24)]:
+        c, j = k // 8, k % 8
+        assert blob[grp, ((tap * 4 + c) * 32 + n) * 8 + j] == w2[grp * 32 + n, k, tap // 3, tap % 3]
+    for (grp, n, k) in [(0, 0, 0), (5, 100, 13), (7, 127, 31)]:
+        c, j = k // 8, k % 8
+        assert blob[grp, 9 * 4 * 32 * 8 + (c * 128 + n) * 8 + j] == w3[n, grp * 32 + k]
+
+
 def test_registry_and_state_dict_contract():
     import models
     m = models.make("meta-baseline", encoder="visformer_micro_80", encoder_args={"drop_path_rate": 0.5})
@@ -105,5 +120,5 @@ def test_c_abi_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     assert N.lib().sunb_abi_version() == N.ABI_VERSION
     # struct layouts mirror the header (sizes are what the C compiler produces for these field lists)
-    assert ctypes.sizeof(N.ConvMlpW) == 32 and ctypes.sizeof(N.AttnBlockW) == 48
-    assert ctypes.sizeof(N.EncoderWeights) == 9 * 8 + 4 * 32 + 16 + 2 * 48 + 16 + 3 * 48 + 16
+    assert ctypes.sizeof(N.ConvMlpW) == 40 and ctypes.sizeof(N.AttnBlockW) == 48
+    assert ctypes.sizeof(N.EncoderWeights) == 9 * 8 + 4 * 40 + 16 + 2 * 48 + 16 + 3 * 48 + 16
