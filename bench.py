@@ -29,7 +29,7 @@ EPISODES_PER_GPU = 75                             # 600 / 8
 CHUNK = 25                                        # episodes per forward call (2500 images)
 FLOP_PER_IMAGE = 2_030_615_400
 FLOP_PER_EPISODE = IMGS_PER_EPISODE * FLOP_PER_IMAGE + 2 * (WAY * QUERY) * WAY * 512
-LAUNCHES_PER_FORWARD = 45                         # 44 encoder kernels (csrc/api.cu schedule) + 1 episode-head kernel
+LAUNCHES_PER_FORWARD = 41                         # 40 encoder kernels (csrc/api.cu schedule) + 1 episode-head kernel
 METRIC = "5-way 5-shot Visformer episodic eval throughput"
 UNIT = "episodes/s"
 
@@ -261,21 +261,19 @@ def kernel_rooflines(model_state, device, burst_tf, hbm_gbs):
     s1 = torch.randn(B * 400, 128, device=device).bfloat16()
     s1o = torch.empty_like(s1)
     h1 = torch.empty(B * 400, 256, device=device, dtype=torch.bfloat16)
-    h2 = torch.empty_like(h1)
     d1 = gemm_desc(B * 400, 256, 128, s1, 128, P["s1.0.w1"], 128, h1, 256, bias=P["s1.0.b1"], act=2)
-    d3 = gemm_desc(B * 400, 128, 256, h2, 256, P["s1.0.w3"], 256, s1o, 128, resid=s1)
 
     def block():
         N.check(lib.sunb_gemm(C.byref(d1), 0, st), "conv1")
-        N.check(lib.sunb_gconv3x3(h1.data_ptr(), 256, P["s1.0.w2"].data_ptr(), h2.data_ptr(), 256, None, 0, None, 0, B, 2, 0, st), "gconv")
-        N.check(lib.sunb_gemm(C.byref(d3), 0, st), "conv3")
+        N.check(lib.sunb_convmlp_tail(h1.data_ptr(), P["s1.0.w23"].data_ptr(), s1.data_ptr(), s1o.data_ptr(), B, 0, st), "tail")
     ms = _time_launch(block)
-    e = entry("stage-1 conv-MLP block (gemm_tc<256> conv1+GELU, gconv3x3_tc + GELU, gemm_tc<128> conv3+residual)", "tensor", ms,
-              flops=2.0 * B * 400 * (256 * 128 + 256 * 288 + 128 * 256), key="stage1_block")
+    e = entry("stage-1 conv-MLP block (gemm_tc<256> conv1+GELU, then convmlp_tail_kernel: grouped 3x3 + GELU + conv3 + residual "
+              "fused, h2 stays on chip)", "tensor", ms, flops=2.0 * B * 400 * (256 * 128 + 256 * 288 + 128 * 256), key="stage1_block")
     e["algorithmic_bytes_per_launch"] = 2 * B * 400 * 128 * 2
-    e["hbm_frac_if_fused"] = e["algorithmic_bytes_per_launch"] / (ms * 1e-3) / 1e9 / hbm_gbs
+    e["note"] = ("the grouped 3x3 (N = 32 per group) is bound by the tensor core's shared-memory operand fetch: 5 KB per "
+                 "128x32x16 MMA, ~47 cycles against a 16-cycle tensor floor (profiles/r02_ncu_convmlp_tail.md)")
     out.append(e)
-    del s1, s1o, h1, h2
+    del s1, s1o, h1
     # ---- attention cores
     for S, dd, dp, tag in ((100, 42, 48, "stage-2 attention (S=100, d=42)"), (25, 85, 96, "stage-3 attention (S=25, d=85)")):
         qkv = torch.randn(B * S, 18 * dp, device=device).bfloat16()
@@ -566,37 +564,59 @@ def run_product(args):
     stage = [torch.empty_like(dev_chunks[0]) for _ in range(2)]
     host_out = torch.empty(n_chunks, CHUNK, WAY * QUERY, WAY, dtype=torch.float32).pin_memory()
     copy_stream = torch.cuda.Stream(device=device)
-    ready = [torch.cuda.Event() for _ in range(2)]
-    free = [torch.cuda.Event() for _ in range(2)]
 
-    e2e_state = {"g": 0, "prefetched": False}
-    done = torch.cuda.Event()
-
-    def issue_h2d(chunk, slot):
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(free[slot])                           # the slot's previous occupant has been consumed
-            stage[slot].copy_(host_chunks[chunk], non_blocking=True)     # H2D inside the timed region
-            ready[slot].record(copy_stream)
-
-    def step_e2e():
+    class E2E:
         """Public API with HOST inputs: pinned H2D of every chunk, model call, D2H of the logits -- all inside the timed
         region.  Transfers are double-buffered on a copy stream: while chunk g runs, chunk g+1 (of this step, or the first
-        chunk of the next step) is already on its way, so a stream of batches keeps the encoder busy.  The step returns
-        when ITS logits are on the host."""
-        main = torch.cuda.current_stream()
-        for c in range(n_chunks):
-            g = e2e_state["g"]
-            slot = g % 2
-            if not (c == 0 and e2e_state["prefetched"]):
-                issue_h2d(c, slot)
-            main.wait_event(ready[slot])
-            issue_h2d((c + 1) % n_chunks, (g + 1) % 2)                   # next chunk; at c == last: chunk 0 of the next step
-            host_out[c].copy_(model_on_slot(slot), non_blocking=True)    # D2H of the step's result (logits)
-            free[slot].record(main)
-            e2e_state["g"] = g + 1
-        e2e_state["prefetched"] = True
-        done.record(main)
-        done.synchronize()
+        chunk of the next step) is already on its way, so a stream of batches keeps the encoder busy.  A step returns when
+        ITS logits are on the host."""
+
+        def __init__(self, host, slots, forward_slot):
+            self.host, self.slots, self.forward_slot = host, slots, forward_slot
+            self.ready = [torch.cuda.Event() for _ in range(2)]
+            self.free = [torch.cuda.Event() for _ in range(2)]
+            self.done = torch.cuda.Event()
+            self.g, self.prefetched = 0, False
+
+        def issue_h2d(self, chunk, slot):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(self.free[slot])                      # the slot's previous occupant has been consumed
+                self.slots[slot].copy_(self.host[chunk], non_blocking=True)  # H2D inside the timed region
+                self.ready[slot].record(copy_stream)
+
+        def step(self):
+            main = torch.cuda.current_stream()
+            for c in range(n_chunks):
+                slot = self.g % 2
+                if not (c == 0 and self.prefetched):
+                    self.issue_h2d(c, slot)
+                main.wait_event(self.ready[slot])
+                self.issue_h2d((c + 1) % n_chunks, (self.g + 1) % 2)     # next chunk; at c == last: chunk 0 of the next step
+                host_out[c].copy_(self.forward_slot(slot), non_blocking=True)    # D2H of the step's result (logits)
+                self.free[slot].record(main)
+                self.g += 1
+            self.prefetched = True
+            self.done.record(main)
+            self.done.synchronize()
+
+    def forward_fp32_slot(slot):
+        a, b = fs.split_shot_query(stage[slot], WAY, SHOT, QUERY, ep_per_batch=CHUNK)
+        return model(a, b)
+
+    # (1) fp32 host images (what a DataLoader over the reference dataset hands to .cuda()): 576 MB of H2D per step
+    e2e_fp32 = E2E(host_chunks, stage, forward_fp32_slot)
+    # (2) the on-device input path (sunb200/input.py): uint8 84x84 host images, 3.6x fewer H2D bytes; PIL-exact resize to 88,
+    #     centre crop 80 and normalisation run on the device in front of the encoder (datasets/mini_imagenet.py:50-56)
+    from sunb200.input import preprocess_u8
+    gu8 = torch.Generator().manual_seed(31 + rank)
+    host_u8 = [torch.randint(0, 256, (CHUNK * IMGS_PER_EPISODE, 84, 84, 3), generator=gu8, dtype=torch.uint8).pin_memory()
+               for _ in range(n_chunks)]
+    stage_u8 = [torch.empty(CHUNK * IMGS_PER_EPISODE, 84, 84, 3, dtype=torch.uint8, device=device) for _ in range(2)]
+
+    def forward_u8_slot(slot):
+        a, b = fs.split_shot_query(preprocess_u8(stage_u8[slot]), WAY, SHOT, QUERY, ep_per_batch=CHUNK)
+        return model(a, b)
+    e2e_u8 = E2E(host_u8, stage_u8, forward_u8_slot)
 
     def barrier():
         if world > 1:
@@ -674,26 +694,12 @@ def run_product(args):
             if rank == 0:
                 print(json.dumps({"profile_mode": True, "ms_per_chunk": ms_total / args.steps}))
             return
-        # e2e: one captured forward per staging slot (inputs land in the slot by H2D, logits leave by D2H)
-        slot_graphs = [None, None]
-        if use_graph:
-            for sl in range(2):
-                stage[sl].copy_(dev_chunks[0])
-
-                def fwd_slot(sl=sl):
-                    a, b = fs.split_shot_query(stage[sl], WAY, SHOT, QUERY, ep_per_batch=CHUNK)
-                    return model(a, b)
-                slot_graphs[sl] = capture(fwd_slot)
-
-        def model_on_slot(slot):
-            if slot_graphs[slot] is not None:
-                slot_graphs[slot][0].replay()
-                return slot_graphs[slot][1]
-            a, b = fs.split_shot_query(stage[slot], WAY, SHOT, QUERY, ep_per_batch=CHUNK)
-            return model(a, b)
         for _ in range(2):
-            step_e2e()
-        ms_e2e = timed(step_e2e, args.steps)
+            e2e_u8.step()
+        ms_e2e = timed(e2e_u8.step, args.steps)
+        for _ in range(2):
+            e2e_fp32.step()
+        ms_e2e_fp32 = timed(e2e_fp32.step, args.steps)
         # sanity: accuracy of the last step's logits on the class-structured episodes (not part of the timing)
         acc = (outs[0].reshape(-1, WAY).argmax(1) == label).float().mean().item()
 
@@ -767,7 +773,9 @@ def run_product(args):
     episodes = world * EPISODES_PER_GPU * args.steps
     value = episodes / (ms_total * 1e-3)
     e2e_value = episodes / (ms_e2e * 1e-3)
-    h2d = EPISODES_PER_GPU * IMGS_PER_EPISODE * 3 * 80 * 80 * 4
+    e2e_fp32_value = episodes / (ms_e2e_fp32 * 1e-3)
+    h2d = EPISODES_PER_GPU * IMGS_PER_EPISODE * 84 * 84 * 3
+    h2d_fp32 = EPISODES_PER_GPU * IMGS_PER_EPISODE * 3 * 80 * 80 * 4
     d2h = EPISODES_PER_GPU * WAY * QUERY * WAY * 4
 
     if rank == 0:
@@ -785,7 +793,7 @@ def run_product(args):
     # the meta-tuning step is measured last: a refused graph capture must not disturb the measurements above
     train = None
     if os.environ.get("SUNB_BENCH_TRAIN", "1") == "1":
-        for t in (dev_chunks, stage):
+        for t in (dev_chunks, stage, stage_u8):
             t.clear()
         torch.cuda.empty_cache()
         try:
@@ -809,7 +817,12 @@ def run_product(args):
                        "episodes_per_gpu_per_step": EPISODES_PER_GPU, "images_per_episode": IMGS_PER_EPISODE,
                        "l2_policy": "inputs larger than L2 (576 MB of fp32 images per step)", "parallelism": f"episode-sharded x{world}"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps,
+                    "input": "uint8 84x84x3 host images -> pinned H2D -> on-device PIL-exact Resize(88) + CenterCrop(80) + Normalize "
+                             "(sunb200.input.preprocess_u8) -> split_shot_query -> models.make('meta-baseline') forward -> logits D2H"},
+            "e2e_fp32_input": {"value": e2e_fp32_value, "unit": UNIT, "h2d_bytes_per_step": h2d_fp32, "d2h_bytes_per_step": d2h,
+                               "ms_per_step": ms_e2e_fp32 / args.steps,
+                               "input": "fp32 3x80x80 host images (already transformed on the host) -> pinned H2D -> forward -> D2H"},
             "gpu_launches": LAUNCHES_PER_FORWARD * n_chunks * args.steps,
             "clocks": clocks,
             "roofline": roof,

@@ -124,6 +124,7 @@ SIGNATURES = {
     "sunb_attention_backward": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "sunb_episode_logits_backward": (C.c_int, [fp, fp, fp, fp, fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                C.c_int, fp, C.c_float, vp]),
+    "sunb_emd_head": (C.c_int, [fp, fp, fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp]),
     "sunb_preprocess_u8": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, fp, fp, vp]),
     # fused multi-tensor optimizers
     "sunb_fused_sgd": (C.c_int, [C.POINTER(OptTensor), C.c_int, fp, vp]),

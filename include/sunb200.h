@@ -251,6 +251,15 @@ int sunb_episode_logits_backward(const float* feat_shot, const float* feat_query
                                  const float* temp_dev, float temp_host, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * SUN-D head (DeepEMD on Visformer node features), evaluation path: meta_tuning_sun_d/Models/models/Network.py:48-81,
+ * 109-128, 143-175 and emd_utils.py:65-76.  proto fp32 [W, n, D], query fp32 [Q, n, D] (node-major rows, n <= 32 nodes);
+ * logits fp32 [Q, W] = sum_ij sim_ij * flow_ij * temperature / n with flow = the optimal transport plan of the reference's
+ * cv2.EMD call (solved on the device); flows (nullable) fp32 [Q, W, n, n] returns the plans.
+ * ------------------------------------------------------------------------------------------------- */
+int sunb_emd_head(const float* proto, const float* query, float* logits, float* flows, int W, int Q, int n, int D,
+                  float temperature, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * On-device input path (test_phase/datasets/mini_imagenet.py:50-56 default_transform): uint8 HWC images [N, in, in, 3]
  * resident in HBM -> PIL-exact bilinear Resize -> CenterCrop -> ToTensor -> Normalize -> fp32 NCHW [n, 3, out, out].
  * idx (nullable): int64 [n] gather index into the image store (the flat batch of a CategoriesSampler).

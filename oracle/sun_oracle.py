@@ -513,3 +513,44 @@ def default_transform(img_u8, resize: int = 88, crop: int = 80, mean=(0.485, 0.4
     c = r[off:off + crop, off:off + crop]
     f = torch.from_numpy(np.ascontiguousarray(c)).permute(2, 0, 1).float().div(255)
     return (f - torch.tensor(mean).view(3, 1, 1)) / torch.tensor(std).view(3, 1, 1)
+
+
+# --------------------------------------------------------------------------------------
+# SUN-D head (meta_tuning_sun_d/Models/models/Network.py:48-81,109-175; emd_utils.py:65-76), evaluation / OpenCV solver
+# --------------------------------------------------------------------------------------
+def sund_weight_vector(A: Tensor, B: Tensor) -> Tensor:
+    """Network.get_weight_vector: A [M,C,n,1], B [N,C,n,1] -> relu(<A node, mean-node of B>) + 1e-3, [M, N, n]."""
+    Bm = B.mean(dim=(2, 3), keepdim=True)                               # adaptive_avg_pool2d(B, 1)
+    comb = (A.unsqueeze(1) * Bm.unsqueeze(0)).sum(2)                    # [M, N, n, 1]
+    return F.relu(comb.reshape(A.shape[0], B.shape[0], -1)) + 1e-3
+
+
+def sund_similarity_map(proto: Tensor, query: Tensor) -> Tensor:
+    """Network.get_similiarity_map (metric 'cosine') after normalize_feature ('center'): [Q, W, n_q, n_p]."""
+    proto = proto - proto.mean(1).unsqueeze(1)
+    query = query - query.mean(1).unsqueeze(1)
+    p = proto.reshape(proto.shape[0], proto.shape[1], -1).permute(0, 2, 1)      # [W, n, C]
+    q = query.reshape(query.shape[0], query.shape[1], -1).permute(0, 2, 1)      # [Q, n, C]
+    return F.cosine_similarity(p[None, :, None, :, :], q[:, None, :, None, :], dim=-1)
+
+
+def sund_emd_logits(proto: Tensor, query: Tensor, temperature: float = 12.5, return_flows: bool = False):
+    """Network.emd_forward_1shot with solver 'opencv': cv2.EMD (OpenCV's transportation simplex, the third-party code the
+    reference calls) on cost = 1 - similarity with node weights relu(w) + 1e-5 rescaled to sum n (emd_utils.py:65-76)."""
+    import cv2
+    w1 = sund_weight_vector(query, proto)                                # [Q, W, n]
+    w2 = sund_weight_vector(proto, query)                                # [W, Q, n]
+    sim = sund_similarity_map(proto, query)
+    Q, W, n, _ = sim.shape
+    logits = torch.zeros(Q, W)
+    flows = torch.zeros(Q, W, n, n)
+    for i in range(Q):
+        for j in range(W):
+            a = F.relu(w1[i, j]) + 1e-5
+            b = F.relu(w2[j, i]) + 1e-5
+            a = (a * (n / a.sum().item())).view(-1, 1).numpy()
+            b = (b * (n / b.sum().item())).view(-1, 1).numpy()
+            _, _, flow = cv2.EMD(a, b, cv2.DIST_USER, (1 - sim[i, j]).numpy())
+            flows[i, j] = torch.from_numpy(flow)
+            logits[i, j] = (sim[i, j] * flows[i, j]).sum() * (temperature / n)
+    return (logits, flows) if return_flows else logits

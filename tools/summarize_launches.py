@@ -26,8 +26,8 @@ def short(name):
 
 # MFLOP per image per launch
 LAYERS = ([("stem conv1+downsample", 16.59), ("stem conv2", 235.93), ("stem conv3", 471.86), ("maxpool+pos1", 0)]
-          + [x for i in range(4) for x in ((f"stage1.{i} mlp.conv1", 26.21), (f"stage1.{i} mlp.conv2 (grouped 3x3)", 58.98),
-                                           (f"stage1.{i} mlp.conv3", 26.21))]
+          + [x for i in range(4) for x in ((f"stage1.{i} mlp.conv1", 26.21),
+                                           (f"stage1.{i} grouped 3x3 + GELU + conv3 + residual (fused)", 58.98 + 26.21))]
           + [("patch_embed2", 26.21)]
           + [x for i in range(2) for x in ((f"stage2.{i} qkv", 38.71), (f"stage2.{i} attention", 10.08), (f"stage2.{i} proj", 12.90),
                                            (f"stage2.{i} mlp.conv1", 52.43), (f"stage2.{i} mlp.conv3", 52.43))]
