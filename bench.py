@@ -348,6 +348,8 @@ def measure_train_step(args, device, world, rank, sd):
         reducer = GradAllReducer(model.parameters())
     lo, hi = shard_range(TRAIN_EPISODES, rank, world)
     ep = hi - lo
+    if os.environ.get("SUNB_TRAIN_EPISODES"):            # profiling aid: the per-rank shard of an N-GPU run on one GPU (no all-reduce)
+        ep = int(os.environ["SUNB_TRAIN_EPISODES"])
     g = torch.Generator(device=device).manual_seed(77 + rank)
     protos = torch.randn(ep, TRAIN_WAY, 1, 3, 80, 80, generator=g, device=device)
     data = (protos + 0.5 * torch.randn(ep, TRAIN_WAY, TRAIN_SHOT + TRAIN_QUERY, 3, 80, 80, generator=g, device=device))

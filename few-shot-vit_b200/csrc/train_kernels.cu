@@ -14,9 +14,22 @@ namespace {
 // column statistics over rows:  sum[c] += sum_m x[m,c];  sq[c] += sum_m x[m,c]^2  (u == null)  or  x[m,c]*u[m,c]
 // block = 256 threads = (256 / (C/8)) row lanes x (C/8) vectors of 8 channels; requires C % 8 == 0, C/8 <= 256
 // ------------------------------------------------------------------------------------------------
+// Optional fused finalize: the LAST block to finish (atomic ticket) turns the complete column sums into the BatchNorm
+// coefficients, so a BatchNorm statistics pass is one launch instead of two (forward: scale / shift / running statistics;
+// backward: the dx coefficients and dgamma / dbeta).
+struct BnFin {
+    int mode;                       // 0 none, 1 forward (bn_finalize), 2 backward (bn_bwd_finalize)
+    unsigned int* ticket;           // zero before the launch
+    float count;
+    const float* gamma; const float* beta;
+    float* rmean; float* rvar; long long* nbt; float momentum, eps;
+    float* scale; float* shift; float* mean; float* rstd;          // forward: outputs; backward: mean / rstd are inputs
+    int frozen; float* a; float* c1; float* c2; float* dgamma; float* dbeta;
+};
+
 __global__ void __launch_bounds__(256) colstats_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ u,
                                                        int ldu, int M, int C, int rows_per_block,
-                                                       float* __restrict__ sum, float* __restrict__ sq) {
+                                                       float* __restrict__ sum, float* __restrict__ sq, const BnFin fin) {
     extern __shared__ float red[];          // [2][256][8]
     const int nvec = C / 8;
     const int lanes = 256 / nvec;
@@ -67,6 +80,40 @@ __global__ void __launch_bounds__(256) colstats_kernel(const bf16* __restrict__ 
         atomicAdd(sum + c, a);
         atomicAdd(sq + c, b);
     }
+    if (fin.mode == 0) return;
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(fin.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        const float s0 = __ldcg(sum + c), s1 = __ldcg(sq + c);
+        if (fin.mode == 1) {
+            const float mean = s0 / fin.count;
+            const float var = fmaxf(s1 / fin.count - mean * mean, 0.f);
+            const float rstd = rsqrtf(var + fin.eps);
+            const float sc = fin.gamma[c] * rstd;
+            fin.scale[c] = sc;
+            fin.shift[c] = fin.beta[c] - mean * sc;
+            fin.mean[c] = mean;
+            fin.rstd[c] = rstd;
+            if (fin.rmean) {
+                fin.rmean[c] = (1.f - fin.momentum) * fin.rmean[c] + fin.momentum * mean;
+                fin.rvar[c] = (1.f - fin.momentum) * fin.rvar[c] + fin.momentum * var * (fin.count / fmaxf(fin.count - 1.f, 1.f));
+            }
+        } else {
+            const float mean = fin.mean[c], rstd = fin.rstd[c];
+            const float cen = s1 - mean * s0;                    // sum dz*(x-mean)
+            fin.a[c] = fin.gamma[c] * rstd;
+            fin.c1[c] = fin.frozen ? 0.f : s0 / fin.count;
+            fin.c2[c] = fin.frozen ? 0.f : rstd * rstd * cen / fin.count;
+            fin.dgamma[c] += rstd * cen;
+            fin.dbeta[c] += s0;
+        }
+    }
+    if (threadIdx.x == 0 && fin.mode == 1 && fin.nbt) *fin.nbt += 1;
 }
 
 // one thread per channel: batch mean / biased var -> scale, shift; running stats with the unbiased var
@@ -474,10 +521,52 @@ int sunb_colstats(const void* x, int ldx, const void* u, int ldu, long M, int C,
     int rpb = lanes * 16;
     long blocks = (M + rpb - 1) / rpb;
     if (blocks > 148L * 8) { rpb = (int)((M + 148L * 8 - 1) / (148L * 8)); rpb = (rpb + lanes - 1) / lanes * lanes; blocks = (M + rpb - 1) / rpb; }
+    BnFin fin;
+    memset(&fin, 0, sizeof(fin));
     colstats_kernel<<<(int)blocks, 256, 2 * 2048 * sizeof(float), ST(stream)>>>(
-        reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<const bf16*>(u), ldu, (int)M, C, rpb, sum, sq);
+        reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<const bf16*>(u), ldu, (int)M, C, rpb, sum, sq, fin);
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
+}
+
+static int launch_colstats_fin(const void* x, int ldx, const void* u, int ldu, long M, int C, float* sum, float* sq,
+                               const BnFin& fin, void* stream) {
+    SUNB_REQUIRE(C % 8 == 0 && C / 8 <= 256 && ldx % 8 == 0, "bn_stats: C must be a multiple of 8 and <= 2048 (got %d)", C);
+    const int lanes = 256 / (C / 8);
+    int rpb = lanes * 16;
+    long blocks = (M + rpb - 1) / rpb;
+    if (blocks > 148L * 8) { rpb = (int)((M + 148L * 8 - 1) / (148L * 8)); rpb = (rpb + lanes - 1) / lanes * lanes; blocks = (M + rpb - 1) / rpb; }
+    colstats_kernel<<<(int)blocks, 256, 2 * 2048 * sizeof(float), ST(stream)>>>(
+        reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<const bf16*>(u), ldu, (int)M, C, rpb, sum, sq, fin);
+    SUNB_CHECK_CUDA(cudaGetLastError());
+    return SUNB_OK;
+}
+
+// column statistics + bn_finalize in ONE launch.  sum, sq, ticket must be zero on entry.
+int sunb_bn_stats_forward(const void* x, int ldx, long M, int C, float* sum, float* sq, void* ticket, const float* gamma,
+                          const float* beta, float* rmean, float* rvar, int64_t* nbt, float momentum, float eps, float* scale,
+                          float* shift, float* mean, float* rstd, void* stream) {
+    SUNB_REQUIRE(x && sum && sq && ticket && gamma && beta && scale && shift && mean && rstd && M > 0, "bn_stats_forward: bad arguments");
+    BnFin fin;
+    memset(&fin, 0, sizeof(fin));
+    fin.mode = 1; fin.ticket = reinterpret_cast<unsigned int*>(ticket); fin.count = (float)M;
+    fin.gamma = gamma; fin.beta = beta; fin.rmean = rmean; fin.rvar = rvar; fin.nbt = reinterpret_cast<long long*>(nbt);
+    fin.momentum = momentum; fin.eps = eps; fin.scale = scale; fin.shift = shift; fin.mean = mean; fin.rstd = rstd;
+    return launch_colstats_fin(x, ldx, nullptr, 0, M, C, sum, sq, fin, stream);
+}
+
+// sum(dz), sum(dz*x) + bn_bwd_finalize in ONE launch.  sdz, sdzx, ticket must be zero on entry.
+int sunb_bn_stats_backward(const void* dz, int lddz, const void* x, int ldx, long M, int C, float* sdz, float* sdzx, void* ticket,
+                           float count, const float* mean, const float* rstd, const float* gamma, int frozen, float* a, float* c1,
+                           float* c2, float* dgamma, float* dbeta, void* stream) {
+    SUNB_REQUIRE(dz && x && sdz && sdzx && ticket && mean && rstd && gamma && a && c1 && c2 && dgamma && dbeta && M > 0,
+                 "bn_stats_backward: bad arguments");
+    BnFin fin;
+    memset(&fin, 0, sizeof(fin));
+    fin.mode = 2; fin.ticket = reinterpret_cast<unsigned int*>(ticket); fin.count = count;
+    fin.gamma = gamma; fin.mean = const_cast<float*>(mean); fin.rstd = const_cast<float*>(rstd); fin.frozen = frozen;
+    fin.a = a; fin.c1 = c1; fin.c2 = c2; fin.dgamma = dgamma; fin.dbeta = dbeta;
+    return launch_colstats_fin(dz, lddz, x, ldx, M, C, sdz, sdzx, fin, stream);
 }
 
 int sunb_bn_finalize(const float* sum, const float* sq, float count, const float* gamma, const float* beta, float* rmean,

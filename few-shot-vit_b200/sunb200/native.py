@@ -103,6 +103,10 @@ SIGNATURES = {
     "sunb_stem_wgrad": (C.c_int, [fp, vp, vp, fp, fp, C.c_int, vp, vp]),
     "sunb_colstats": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_long, C.c_int, fp, fp, vp]),
     "sunb_bn_finalize": (C.c_int, [fp, fp, C.c_float, fp, fp, fp, fp, vp, C.c_float, C.c_float, C.c_int, fp, fp, fp, fp, vp]),
+    "sunb_bn_stats_forward": (C.c_int, [vp, C.c_int, C.c_long, C.c_int, fp, fp, vp, fp, fp, fp, fp, vp, C.c_float, C.c_float,
+                                        fp, fp, fp, fp, vp]),
+    "sunb_bn_stats_backward": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_long, C.c_int, fp, fp, vp, C.c_float, fp, fp, fp, C.c_int,
+                                         fp, fp, fp, fp, fp, vp]),
     "sunb_bn_apply": (C.c_int, [vp, C.c_int, fp, fp, C.c_int, fp, C.c_int, vp, C.c_int, C.c_long, C.c_int, vp]),
     "sunb_bn_frozen": (C.c_int, [fp, fp, fp, fp, C.c_float, C.c_int, fp, fp, fp, fp, vp]),
     "sunb_bn_bwd_finalize": (C.c_int, [fp, fp, C.c_float, fp, fp, fp, C.c_int, C.c_int, fp, fp, fp, fp, fp, vp]),
@@ -132,7 +136,7 @@ SIGNATURES = {
 }
 
 _lib = None
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 def lib() -> C.CDLL:

@@ -82,18 +82,44 @@ class BNRec:
         return self.buf[i]
 
 
+class _ZeroArena:
+    """One zero-filled fp32 buffer per pass, carved into the small accumulators the kernels need zeroed (BatchNorm sums and
+    tickets, pos-embed / bias / weight-gradient scratch): ONE fill launch instead of ~40 per step."""
+
+    def __init__(self, n_floats, device):
+        self.buf = torch.zeros(n_floats, dtype=torch.float32, device=device)
+        self.off = 0
+
+    def take(self, *shape):
+        n = 1
+        for d in shape:
+            n *= d
+        if self.off + n > self.buf.numel():             # sized generously; fall back to a fresh allocation rather than fail
+            return torch.zeros(*shape, dtype=torch.float32, device=self.buf.device)
+        v = self.buf[self.off:self.off + n].view(*shape)
+        self.off += (n + 63) // 64 * 64                 # keep every slice 256-byte aligned
+        return v
+
+
 class TrainEngine:
     def __init__(self):
         self.lib = N.lib()
         self.frozen_bn = frozenset()       # names of BatchNorm layers currently in eval() (utils.freeze_bn)
+        self.arena = None
 
     # ------------------------------------------------------------------ small wrappers
     def empty(self, *shape, dtype=torch.bfloat16):
         return torch.empty(*shape, dtype=dtype, device=self.dev)
 
+    def zeros(self, *shape):
+        """Zero-filled fp32 scratch from the pass's arena (created on demand for stand-alone kernel tests)."""
+        if self.arena is None:
+            self.arena = _ZeroArena(64 * 1024, self.dev)
+        return self.arena.take(*shape)
+
     def bn_forward(self, x, name, Cc, M, P, Bf, update_running=True) -> BNRec:
         """colstats + finalize for BatchNorm `name` over x [M, C] (bf16).  Running stats updated in place."""
-        buf = torch.zeros(11, Cc, dtype=torch.float32, device=self.dev)
+        buf = self.zeros(11, Cc)
         rec = BNRec(name, Cc, float(M), buf, x, frozen=name in self.frozen_bn)
         if rec.frozen:      # module switched to eval() by utils.freeze_bn: running statistics, no update
             N.check(self.lib.sunb_bn_frozen(P[name + ".weight"].data_ptr(), P[name + ".bias"].data_ptr(),
@@ -101,15 +127,16 @@ class TrainEngine:
                                             Cc, buf[2].data_ptr(), buf[3].data_ptr(), buf[4].data_ptr(), buf[5].data_ptr(),
                                             _st()), "sunb_bn_frozen")
             return rec
-        N.check(self.lib.sunb_colstats(x.data_ptr(), x.shape[-1], None, 0, M, Cc, buf[0].data_ptr(), buf[1].data_ptr(),
-                                       _st()), "sunb_colstats")
         rm, rv, nbt = Bf[name + ".running_mean"], Bf[name + ".running_var"], Bf[name + ".num_batches_tracked"]
-        N.check(self.lib.sunb_bn_finalize(buf[0].data_ptr(), buf[1].data_ptr(), float(M), P[name + ".weight"].data_ptr(),
-                                          P[name + ".bias"].data_ptr(), rm.data_ptr() if update_running else None,
-                                          rv.data_ptr() if update_running else None,
-                                          nbt.data_ptr() if update_running else None, BN_MOMENTUM, BN_EPS, Cc,
-                                          buf[2].data_ptr(), buf[3].data_ptr(), buf[4].data_ptr(), buf[5].data_ptr(), _st()),
-                "sunb_bn_finalize")
+        ticket = self.zeros(64)
+        # column sums + finalize (scale / shift / running statistics) in one launch: the last block finalizes
+        N.check(self.lib.sunb_bn_stats_forward(x.data_ptr(), x.shape[-1], M, Cc, buf[0].data_ptr(), buf[1].data_ptr(),
+                                               ticket.data_ptr(), P[name + ".weight"].data_ptr(), P[name + ".bias"].data_ptr(),
+                                               rm.data_ptr() if update_running else None,
+                                               rv.data_ptr() if update_running else None,
+                                               nbt.data_ptr() if update_running else None, BN_MOMENTUM, BN_EPS,
+                                               buf[2].data_ptr(), buf[3].data_ptr(), buf[4].data_ptr(), buf[5].data_ptr(), _st()),
+                "sunb_bn_stats_forward")
         return rec
 
     def bn_apply(self, x, rec: BNRec, M, act=ACT_NONE, tab=None, tab_mod=1):
@@ -121,12 +148,13 @@ class TrainEngine:
     def bn_backward(self, dz, rec: BNRec, M, P, G, res=None):
         """dz = gradient w.r.t. the BN output [M, C] -> gradient w.r.t. its input (+ res); accumulates dgamma / dbeta."""
         b = rec.buf
-        N.check(self.lib.sunb_colstats(dz.data_ptr(), dz.shape[-1], rec.x.data_ptr(), rec.x.shape[-1], M, rec.C,
-                                       b[6].data_ptr(), b[7].data_ptr(), _st()), "sunb_colstats(bwd)")
-        N.check(self.lib.sunb_bn_bwd_finalize(b[6].data_ptr(), b[7].data_ptr(), rec.count, b[4].data_ptr(), b[5].data_ptr(),
-                                              P[rec.name + ".weight"].data_ptr(), rec.C, int(rec.frozen), b[8].data_ptr(), b[9].data_ptr(),
-                                              b[10].data_ptr(), G[rec.name + ".weight"].data_ptr(),
-                                              G[rec.name + ".bias"].data_ptr(), _st()), "sunb_bn_bwd_finalize")
+        ticket = self.zeros(64)
+        N.check(self.lib.sunb_bn_stats_backward(dz.data_ptr(), dz.shape[-1], rec.x.data_ptr(), rec.x.shape[-1], M, rec.C,
+                                                b[6].data_ptr(), b[7].data_ptr(), ticket.data_ptr(), rec.count, b[4].data_ptr(),
+                                                b[5].data_ptr(), P[rec.name + ".weight"].data_ptr(), int(rec.frozen),
+                                                b[8].data_ptr(), b[9].data_ptr(), b[10].data_ptr(),
+                                                G[rec.name + ".weight"].data_ptr(), G[rec.name + ".bias"].data_ptr(), _st()),
+                "sunb_bn_stats_backward")
         out = self.empty(M, rec.C)
         N.check(self.lib.sunb_bn_bwd_apply(dz.data_ptr(), dz.shape[-1], rec.x.data_ptr(), rec.x.shape[-1], b[8].data_ptr(),
                                            b[9].data_ptr(), b[10].data_ptr(), b[4].data_ptr(), N.ptr(res),
@@ -199,8 +227,9 @@ class TrainEngine:
         lib = self.lib
         W = self.prep_weights(P)
         ctx = {"B": B, "W": W, "x": x, "rs": rs, "blocks": []}
-        z64 = torch.zeros(64, device=self.dev)
-        z128 = torch.zeros(128, device=self.dev)
+        self.arena = _ZeroArena(160 * 1024, self.dev)              # forward: 21 BatchNorm records (11 x C) + tickets
+        z64 = self.zeros(64)
+        z128 = self.zeros(128)
 
         # ---- stem (visformer.py:220-239)
         M0 = B * 1600
@@ -306,6 +335,7 @@ class TrainEngine:
         order = [n for grp in groups for n in grp]
         assert len(order) == len(P), "parameter grouping must cover every encoder parameter"
         flat = torch.zeros(sum(P[n].numel() for n in order), dtype=torch.float32, device=self.dev)
+        self.arena = _ZeroArena(2560 * 1024, self.dev)              # backward: tickets, pos / bias sums, weight-gradient scratch
         G, spans, off = {}, [], 0
         for grp in groups:
             lo = off
@@ -335,14 +365,14 @@ class TrainEngine:
             # PatchEmbed + pos_embed (visformer.py:438-441, 447-450)
             S, M = side * side, B * side * side
             pe = ctx[f"pe{stage}"]
-            gpos = torch.zeros(S * dim, dtype=torch.float32, device=self.dev)
+            gpos = self.zeros(S * dim)
             N.check(lib.sunb_batch_sum(g.data_ptr(), B, S * dim, gpos.data_ptr(), _st()), "sunb_batch_sum")
             G[f"pos_embed{stage}"] += gpos.view(side, side, dim).permute(2, 0, 1).unsqueeze(0)
             dyp = self.bn_backward(g, pe["bn"], M, P, G)
-            sb = torch.zeros(2, dim, dtype=torch.float32, device=self.dev)
+            sb = self.zeros(2, dim)
             N.check(lib.sunb_colstats(dyp.data_ptr(), dim, None, 0, M, dim, sb[0].data_ptr(), sb[1].data_ptr(), _st()), "colstats")
             G[f"patch_embed{stage}.proj.bias"] += sb[0]
-            gw = torch.zeros(dim, 4 * cin, dtype=torch.float32, device=self.dev)
+            gw = self.zeros(dim, 4 * cin)
             wgrad(dyp, pe["xs"], gw, M, dim, 4 * cin)
             G[f"patch_embed{stage}.proj.weight"] += gw.view(dim, 2, 2, cin).permute(0, 3, 1, 2)
             dxs = gemm(dyp, W[f"pe{stage}.d"], M, 4 * cin, dim, out=self.empty(M, 4 * cin))
@@ -394,7 +424,7 @@ class TrainEngine:
         dh1p = self.empty(M, 256)
         N.check(lib.sunb_gconv3x3(dh2p.data_ptr(), 256, W[name + ".mlp.conv2.d"].data_ptr(), dh1p.data_ptr(), 256, None, 0,
                                   b["h1p"].data_ptr(), 256, B, ACT_NONE, ACT_GELU, _st()), "sunb_gconv3x3(dgrad)")
-        scratch = torch.zeros(2 * 9 * 128, 128, dtype=torch.float32, device=self.dev)
+        scratch = self.zeros(2 * 9 * 128, 128)
         wgrad(dh2p, b["h1"], scratch, M, 128, 128, Ca=256, Cb=256, taps=9, groups=2, a_goff=128, b_goff=128,
               conv=(20, 20, 4, 4))
         N.check(lib.sunb_grouped_wgrad_extract(scratch.data_ptr(), G[name + ".mlp.conv2.weight"].data_ptr(), _st()),
@@ -407,7 +437,7 @@ class TrainEngine:
         lib = self.lib
         s = ctx["stem"]
         M0 = B * 1600
-        gpos = torch.zeros(400 * 128, dtype=torch.float32, device=self.dev)
+        gpos = self.zeros(400 * 128)
         N.check(lib.sunb_batch_sum(g.data_ptr(), B, 400 * 128, gpos.data_ptr(), _st()), "sunb_batch_sum")
         G["pos_embed1"] += gpos.view(20, 20, 128).permute(2, 0, 1).unsqueeze(0)
         bn3, bnd, bn2, bn1 = s["bn3"], s["bnd"], s["bn2"], s["bn1"]
@@ -417,13 +447,13 @@ class TrainEngine:
                                             dz.data_ptr(), B, _st()), "sunb_stem_tail_backward")
         dc3r = self.bn_backward(dz, bn3, M0, P, G)
         didr = self.bn_backward(dz, bnd, M0, P, G)
-        gw3 = torch.zeros(9 * 128, 128, dtype=torch.float32, device=self.dev)
+        gw3 = self.zeros(9 * 128, 128)
         wgrad(dc3r, s["a2"], gw3, M0, 128, 128, taps=9, conv=(40, 40, 8, 8))
         G["stem.conv3.weight"] += gw3.view(9, 128, 128).permute(1, 2, 0).reshape(128, 128, 3, 3)
         da2 = gemm(dc3r, W["stem.conv3.d"], M0, 128, 128, out=self.empty(M0, 128), taps=9, conv=(40, 40, 8, 8),
                    dact_aux=s["a2"], dact=ACT_LRELU)
         da2r = self.bn_backward(da2, bn2, M0, P, G)
-        gw2 = torch.zeros(9 * 128, 64, dtype=torch.float32, device=self.dev)
+        gw2 = self.zeros(9 * 128, 64)
         wgrad(da2r, s["a1"], gw2, M0, 128, 64, taps=9, conv=(40, 40, 8, 8))
         G["stem.conv2.weight"] += gw2.view(9, 128, 64).permute(1, 2, 0).reshape(128, 64, 3, 3)
         da1 = gemm(da2r, W["stem.conv2.d"], M0, 64, 128, out=self.empty(M0, 64), taps=9, conv=(40, 40, 8, 8),

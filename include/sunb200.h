@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SUNB_ABI_VERSION 5
+#define SUNB_ABI_VERSION 6
 
 int sunb_abi_version(void);
 const char* sunb_last_error(void);
@@ -193,6 +193,15 @@ int sunb_colstats(const void* x, int ldx, const void* u, int ldu, long M, int C,
 int sunb_bn_finalize(const float* sum, const float* sq, float count, const float* gamma, const float* beta, float* rmean,
                      float* rvar, int64_t* nbt, float momentum, float eps, int C, float* scale, float* shift, float* mean,
                      float* rstd, void* stream);
+/* one-launch variants: column statistics + finalize by the last block (sum / sq / sdz / sdzx and the 4-byte ticket must be
+ * zero on entry).  sunb_bn_stats_forward = sunb_colstats + sunb_bn_finalize; sunb_bn_stats_backward = sunb_colstats(dz, x) +
+ * sunb_bn_bwd_finalize. */
+int sunb_bn_stats_forward(const void* x, int ldx, long M, int C, float* sum, float* sq, void* ticket, const float* gamma,
+                          const float* beta, float* rmean, float* rvar, int64_t* nbt, float momentum, float eps, float* scale,
+                          float* shift, float* mean, float* rstd, void* stream);
+int sunb_bn_stats_backward(const void* dz, int lddz, const void* x, int ldx, long M, int C, float* sdz, float* sdzx, void* ticket,
+                           float count, const float* mean, const float* rstd, const float* gamma, int frozen, float* a, float* c1,
+                           float* c2, float* dgamma, float* dbeta, void* stream);
 int sunb_bn_apply(const void* x, int ldx, const float* scale, const float* shift, int act, const float* tab, int tab_mod,
                   void* out, int ldo, long M, int C, void* stream);
 /* frozen BatchNorm inside a training step (utils.freeze_bn, test_phase/utils/__init__.py:150-153): running statistics */
