@@ -13,7 +13,6 @@
 // launchers defined in the other translation units
 int sunb_launch_stem_in(const float* x, const float* w1, const float* b1, const float* wd, const float* bd, bf16* a1,
                         bf16* idn, int B, int lrelu, cudaStream_t stream);
-int sunb_launch_pool_pos(const bf16* in, const float* pos, bf16* out, int B, int H, int W, int C, cudaStream_t stream);
 int sunb_launch_attention(const bf16* qkv, bf16* out, int B, int S, int d, int ds, int heads, int ld_qkv, int ld_out,
                           cudaStream_t stream);
 int sunb_launch_final_norm_pool(const bf16* x, const float* scale, const float* shift, float* dense, bf16* dense_bf16,
@@ -84,7 +83,7 @@ namespace {
 constexpr int HEADS = 6;
 
 struct Workspace {
-    bf16 *a1, *idn, *a2, *c3, *s1, *h1, *s1b, *s1d, *t2, *qkv2, *ao2, *hid2, *t2d, *t3, *qkv3, *ao3, *hid3;
+    bf16 *a1, *idn, *a2, *s1, *h1, *s1b, *s1d, *t2, *qkv2, *ao2, *hid2, *t2d, *t3, *qkv3, *ao3, *hid3;
     size_t bytes;
 };
 
@@ -100,7 +99,6 @@ Workspace carve(void* base, int B) {
     w.a1 = take(b * 1600 * 64);
     w.idn = take(b * 1600 * 128);
     w.a2 = take(b * 1600 * 128);
-    w.c3 = take(b * 1600 * 128);
     w.s1 = take(b * 400 * 128);
     w.h1 = take(b * 400 * 256);
     w.s1b = take(b * 400 * 128);       // stage-1 residual stream ping-pong (the fused block tail cannot run in place)
@@ -206,13 +204,15 @@ int sunb_encoder_forward(const SunbEncoderWeights* w, const float* x, int B, voi
         p.taps = 9; p.a_mode = 1; p.H = 40; p.W = 40; p.bw = 8; p.bh = 8;
         p.bias = w->stem_b2; p.act = ACT_LRELU;
         SUNB_TRY(sunb_launch_gemm(p, st));
-        p = base_gemm(B * 1600, 128, 128, ws.a2, 128, w->stem_w3, 128, ws.c3, 128);
+        // conv3 + bn3 + shortcut + LeakyReLU with the 2x2 max-pool and pos_embed1 fused into the epilogue (visformer.py:229-237,
+        // 431): the 40x40 map never reaches HBM, only the pooled 20x20 map is written
+        p = base_gemm(B * 1600, 128, 128, ws.a2, 128, w->stem_w3, 128, nullptr, 128);
         p.taps = 9; p.a_mode = 1; p.H = 40; p.W = 40; p.bw = 8; p.bh = 8;
         p.bias = w->stem_b3; p.act = ACT_LRELU;
         p.resid = ws.idn; p.ldr = 128;
+        p.pool_out = ws.s1; p.pool_pos = w->pos1;
         SUNB_TRY(sunb_launch_gemm(p, st));
     }
-    SUNB_TRY(sunb_launch_pool_pos(ws.c3, w->pos1, ws.s1, B, 40, 40, 128, st));
     SUNB_TRY(tap_copy(tp.stem, ws.s1, (size_t)B * 400 * 128, st));
 
     // ---- stage 1: x + conv3(gelu(gconv3x3(gelu(conv1(bn(x))))))  (visformer.py:152-163, 259-263)

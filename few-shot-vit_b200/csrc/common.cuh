@@ -72,6 +72,9 @@ struct GemmParams {
     bf16* out2; int ldc2;                 // pre-activation copy (value before `act`), bf16, nullable
     const bf16* dact_aux; int ld_aux;     // backward: multiply the result by act'(aux[m, col]) of kind `dact`
     int dact;
+    // fused 2x2 max-pool + position table behind the activation (conv_slab.cu only; eval stem tail, visformer.py:237,431):
+    //   pool_out[img, y/2, x/2, col] = max over the 2x2 window of act(...) + pool_pos[(y/2)*(W/2) + x/2, col]
+    bf16* pool_out; const float* pool_pos;
 };
 
 // MUFU approximations (rel. error ~2^-22), one instruction each

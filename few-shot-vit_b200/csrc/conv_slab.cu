@@ -126,7 +126,10 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+constexpr int POOL_PITCH = 80;                  // bytes per staged row: 32 bf16 + 16 B pad (conflict-free 16-byte row stores)
+constexpr int POOL_STAGE = 256 * POOL_PITCH;    // one 32-column chunk of a 256-row tile
 struct SlabGeom {
+    int pool_off;     // byte offset of the pooling stage from the 1024-aligned base (0 = no fused pooling)
     int P;            // raster pitch W + 2
     int RB;           // output image rows per band
     int bands;        // ceil(H / RB)
@@ -301,6 +304,16 @@ conv_slab2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int c0 = (warp - 3) >> 3;              // first 32-column chunk of this warp
         const int r = half * 128 + q * 32 + lane;
         const int yy = r / g.P, xx = r - yy * g.P;
+        // fused 2x2 max-pool + position table (eval stem tail): the 8 warps that drain the same 32-column chunk exchange the
+        // activated tile through a padded shared-memory stage (raster rows r, r+1, r+P, r+P+1 live in different TMEM lane
+        // quarters), then 240 of their 256 threads each pool one (pooled pixel, 8 columns) item
+        const bool pool = g.pool_off != 0;
+        GemmParams pl = p;
+        pl.out = nullptr; pl.out_f32 = nullptr; pl.out2 = nullptr;
+        uint8_t* stage = smem_raw + (base - smem_u32(smem_raw)) + g.pool_off + c0 * POOL_STAGE;
+        const int wtid = ((warp - 3) & 7) * 32 + lane;                  // thread index inside the 8-warp set
+        const int pp = wtid >> 2, cc = wtid & 3;                         // pooled pixel of the band, 8-column group
+        const int pw = p.W >> 1, py = pp / pw, px = pp - py * pw;
         int lt = 0;
         for (int t = pair0; t < pairs; t += pstep, ++lt) {
             const int acc = lt & 1, aph = (lt >> 1) & 1;
@@ -319,7 +332,48 @@ conv_slab2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster(acc_empty(acc) & PEER_MASK);      // the leader's barrier
                 }
-                epilogue_row<32>(p, 0, m, c * 32, v);
+                if (!pool) {
+                    epilogue_row<32>(p, 0, m, c * 32, v);
+                    continue;
+                }
+                epilogue_row<32>(pl, 0, m, c * 32, v);                    // bias, residual, activation -- in registers only
+                if (valid) {
+                    uint4* dst = reinterpret_cast<uint4*>(stage + r * POOL_PITCH);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 u;
+                        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
+                        dst[j] = u;
+                    }
+                }
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + c0), "r"(256) : "memory");
+                if (tile < g.tiles && py < (g.RB >> 1) && y0 + 2 * py + 1 < p.H) {
+                    const int r0 = 2 * py * g.P + 2 * px;
+                    float mx[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) mx[e] = -INFINITY;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int rr = r0 + (k >> 1) * g.P + (k & 1);
+                        const uint4 u = *reinterpret_cast<const uint4*>(stage + rr * POOL_PITCH + cc * 16);
+                        const bf16* hb = reinterpret_cast<const bf16*>(&u);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) mx[e] = fmaxf(mx[e], __bfloat162float(hb[e]));
+                    }
+                    const int prow = (y0 >> 1) + py;
+                    const float* pos = p.pool_pos + (size_t)(prow * pw + px) * p.N + c * 32 + cc * 8;
+                    const float4 q0 = *reinterpret_cast<const float4*>(pos), q1 = *reinterpret_cast<const float4*>(pos + 4);
+                    uint4 o;
+                    __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+                    oh[0] = __floats2bfloat162_rn(mx[0] + q0.x, mx[1] + q0.y);
+                    oh[1] = __floats2bfloat162_rn(mx[2] + q0.z, mx[3] + q0.w);
+                    oh[2] = __floats2bfloat162_rn(mx[4] + q1.x, mx[5] + q1.y);
+                    oh[3] = __floats2bfloat162_rn(mx[6] + q1.z, mx[7] + q1.w);
+                    *reinterpret_cast<uint4*>(p.pool_out + ((size_t)(img * (p.H >> 1) + prow) * pw + px) * p.N + c * 32 + cc * 8) = o;
+                }
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + c0), "r"(256) : "memory");       // stage free for the next chunk
             }
         }
     }
@@ -347,7 +401,7 @@ int launch2(const GemmParams& p, const SlabGeom& g, const CUtensorMap& tmA, cons
 
 // 1 when the problem fits the slab kernel (then sunb_launch_conv_slab runs it), 0 to keep the tap-per-K-block GEMM
 int sunb_conv_slab_supported(const GemmParams& p) {
-    if (p.a_mode != 1 || p.taps != 9 || p.groups != 1 || p.out_map != 0) return 0;
+    if (p.a_mode != 1 || p.taps != 9 || p.groups != 1 || p.out_map != 0) return p.pool_out ? -1 : 0;
     if (!(p.K == 64 || p.K == 128) || !(p.N == 64 || p.N == 128)) return 0;
     if (p.W + 2 > 128 || p.H < 1 || p.M % (p.H * p.W) != 0) return 0;
     return 1;
@@ -373,11 +427,18 @@ int sunb_launch_conv_slab(const GemmParams& p, cudaStream_t stream) {
     const int slab_total = ATOM_SLOTS * g.atom_bytes;
     const bool pair = true;      // cta_group::2 pairs share one weight stream (a lone last tile is padded with an empty partner)
     const int b_block = (pair ? BN / 2 : BN) * 128;
-    int b_stages = (SMEM_LIMIT - 1024 - 512 - slab_total) / b_block;
+    const int pool_bytes = p.pool_out ? CSTEP * POOL_STAGE : 0;
+    if (p.pool_out) {
+        SUNB_REQUIRE(p.pool_pos && EPI_WARPS == 16 && (g.RB % 2) == 0 && (p.H % 2) == 0 && (p.W % 2) == 0 && (p.N % 32) == 0 &&
+                         (g.RB / 2) * (p.W / 2) <= 64 && (((size_t)p.pool_out) & 15) == 0,
+                     "conv_slab: fused pooling needs even band / image sizes and at most 64 pooled pixels per band");
+    }
+    int b_stages = (SMEM_LIMIT - 1024 - 512 - slab_total - pool_bytes) / b_block;
     if (b_stages > (pair ? 16 : 8)) b_stages = pair ? 16 : 8;
     SUNB_REQUIRE(b_stages >= 2, "conv_slab: slab of %d bytes leaves no room for the weight ring", slab_total);
     g.b_stages = b_stages;
-    const int smem = 1024 + slab_total + b_stages * b_block + 512;
+    g.pool_off = p.pool_out ? slab_total + b_stages * b_block + 512 : 0;
+    const int smem = 1024 + slab_total + b_stages * b_block + 512 + pool_bytes;
     SUNB_REQUIRE((256 + 2 * g.P + 2) * 128 <= g.atom_bytes + b_stages * b_block, "conv_slab: over-read guard");
 
     CUtensorMap tmA, tmB;

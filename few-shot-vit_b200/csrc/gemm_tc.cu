@@ -379,7 +379,8 @@ int sunb_launch_gemm_tc(const GemmParams& p, cudaStream_t stream) {
     SUNB_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm_tc: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
     SUNB_REQUIRE((p.lda % 8) == 0 && (p.ldw % 8) == 0, "gemm_tc: lda/ldw must be multiples of 8 elements (16 B)");
     SUNB_REQUIRE((((size_t)p.A) & 15) == 0 && (((size_t)p.Wt) & 15) == 0, "gemm_tc: operands must be 16-byte aligned");
-    if (sunb_conv_slab_supported(p)) return sunb_launch_conv_slab(p, stream);     // dense 3x3: resident haloed slab (conv_slab.cu)
+    if (sunb_conv_slab_supported(p) > 0) return sunb_launch_conv_slab(p, stream);     // dense 3x3: resident haloed slab (conv_slab.cu)
+    SUNB_REQUIRE(p.pool_out == nullptr, "gemm_tc: the fused max-pool epilogue exists in the slab convolution only");
     const int BN = sunb_gemm_tc_pick_bn(p);
     CUtensorMap tmA, tmB;
     if (p.a_mode == 0) {

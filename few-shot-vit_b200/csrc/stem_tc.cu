@@ -252,3 +252,8 @@ int sunb_launch_stem_in_tc(const float* x, const float* w1, const float* b1, con
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
 }
+
+int sunb_launch_stem_in(const float* x, const float* w1, const float* b1, const float* wd, const float* bd, bf16* a1,
+                        bf16* idn, int B, int lrelu, cudaStream_t stream) {
+    return sunb_launch_stem_in_tc(x, w1, b1, wd, bd, a1, idn, B, lrelu, stream);
+}

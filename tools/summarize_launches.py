@@ -25,7 +25,7 @@ def short(name):
 
 
 # MFLOP per image per launch
-LAYERS = ([("stem conv1+downsample", 16.59), ("stem conv2", 235.93), ("stem conv3", 471.86), ("maxpool+pos1", 0)]
+LAYERS = ([("stem conv1+downsample", 16.59), ("stem conv2", 235.93), ("stem conv3 + shortcut + LeakyReLU + maxpool + pos1 (fused epilogue)", 471.86)]
           + [x for i in range(4) for x in ((f"stage1.{i} mlp.conv1", 26.21),
                                            (f"stage1.{i} grouped 3x3 + GELU + conv3 + residual (fused)", 58.98 + 26.21))]
           + [("patch_embed2", 26.21)]
