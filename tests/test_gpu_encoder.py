@@ -158,6 +158,25 @@ def test_data_parallel_replica_raises():
         rep(torch.zeros(1, 3, 80, 80, device="cuda"))
 
 
+@pytest.mark.parametrize("B", [1, 3, 7, 101])
+def test_odd_batch_sizes(B):
+    """Ragged sizes: odd image counts leave a lone last tile in the 2-CTA slab convolution (fused pooling epilogue), an odd
+    number of half-image items in the fused block tail and a partial 5-image tile in the stage-3 attention."""
+    sd = O.calibrate_bn(O.init_meta_baseline_state_dict(12345))
+    m = make_model(sd)
+    x = O.make_episode_images(40 + B, B, 1)
+    with torch.no_grad():
+        n_ref = min(B, 7)
+        _, ref = O.encoder_forward(sd, x[:n_ref], "encoder.")
+        out = m.encoder(x.cuda()).cpu()
+    assert out.shape == (B, 512) and torch.isfinite(out).all()
+    assert rel_err(out[:n_ref], ref) < 3e-2
+    if B > n_ref:                                   # images are independent in eval mode: the tail of a big batch == the same
+        with torch.no_grad():                       # images alone
+            again = m.encoder(x[n_ref:].cuda()).cpu()
+        assert torch.equal(out[n_ref:], again)
+
+
 def test_batched_episodes_match_single(golden_dir):
     """E episodes in one call == the same episodes one by one (episodes are independent in eval mode)."""
     sd = O.calibrate_bn(O.init_meta_baseline_state_dict(12345))
