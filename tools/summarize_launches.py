@@ -1,6 +1,6 @@
 """Turn the ncu launch lists (gpurun_out/launches.csv, launches_train.csv) into profiles/*.md summaries.
 
-usage: python tools/summarize_launches.py <tag>      e.g. r01b
+usage: python tools/summarize_launches.py <tag>      e.g. r02a
 Eval list: per-layer table with algorithmic FLOPs -> effective TFLOP/s (2500 images = 25 five-shot episodes per forward).
 """
 import collections
