@@ -491,28 +491,59 @@ def measure_sun_meta_step(args, device, world, rank):
             reducer.all_reduce_mean()
         opt.step()
         return out["loss"]
-    for _ in range(3):
-        loss = step()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(args.steps):
-        loss = step()
-    e1.record()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = t.item()
+    def timed(fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.steps):
+            out = fn()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item(), out
+
+    # everything on one side stream (see measure_train_step); eager first, then the whole step as one CUDA graph (the DropPath
+    # draws use torch's graph-safe CUDA generator inside the capture)
+    side = torch.cuda.Stream(device=device)
+    side.wait_stream(torch.cuda.current_stream())
+    mode = "eager"
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            loss = step()
+        ms_eager, loss = timed(step)
+        ms = ms_eager
+        if os.environ.get("SUNB_TRAIN_GRAPH", "1") == "1":
+            try:
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=side, capture_error_mode="thread_local"):
+                    static_loss = step()
+
+                def graph_step():
+                    graph.replay()
+                    return static_loss
+                for _ in range(2):
+                    graph_step()
+                ms_graph, gl = timed(graph_step)
+                if ms_graph < ms_eager:
+                    ms, mode, loss = ms_graph, "cuda_graph", gl
+            except Exception as exc:
+                if rank == 0:
+                    print(f"[bench] CUDA-graph capture of the SUN meta-training step failed ({type(exc).__name__}: "
+                          f"{str(exc).splitlines()[0]}); reporting eager launches", file=sys.stderr)
+                torch.cuda.synchronize()
+    torch.cuda.current_stream().wait_stream(side)
     flops = SUN_BATCH * FLOP_PER_IMAGE * 4.0          # student fwd + bwd (3x) + teacher fwd (1x); heads are < 0.1 %
     return {"metric": "SUN meta-training step (student fwd+bwd, teacher fwd, soft labels, CE + 0.5 token CE, AdamW)",
             "ms_per_step": ms, "unit": "ms", "images_per_step": SUN_BATCH, "images_per_gpu": bs, "scaling": "strong",
             "higher_is_better": False, "achieved_tflops_per_gpu": flops / world / (ms * 1e-3) / 1e12,
-            "loss_last": float(loss.item()), "launch_mode": "eager",
+            "loss_last": float(loss.item()), "launch_mode": mode, "ms_per_step_eager": ms_eager,
             "config": "batch 512, 64 base classes (+1 background column), tl_soft_k 5, bg_token_num 10, drop_path 0.5, "
                       "AdamW(lr 5e-4, wd 0.05)"}
 
