@@ -439,9 +439,10 @@ def measure_train_step(args, device, world, rank, sd):
                           f"{str(exc).splitlines()[0]}); reporting eager launches", file=sys.stderr)
     torch.cuda.current_stream().wait_stream(side)
     ms = torch.tensor([ms], device=device)
-    flops = 3.0 * TRAIN_IMAGES * FLOP_PER_IMAGE
+    images = ep * world * TRAIN_WAY * (TRAIN_SHOT + TRAIN_QUERY)          # == TRAIN_IMAGES unless SUNB_TRAIN_EPISODES overrides
+    flops = 3.0 * images * FLOP_PER_IMAGE
     return {"metric": "SUN-M meta-tuning step (fwd+bwd+allreduce+SGD)", "ms_per_step": ms.item(), "unit": "ms",
-            "images_per_step": TRAIN_IMAGES, "episodes_per_gpu": ep, "scaling": "strong", "higher_is_better": False,
+            "images_per_step": images, "episodes_per_gpu": ep, "scaling": "strong", "higher_is_better": False,
             "achieved_tflops_per_gpu": flops / world / (ms.item() * 1e-3) / 1e12, "loss_last": float(loss.item()),
             "launch_mode": mode, "ms_per_step_eager": ms_eager, "grad_allreduce": ("overlapped with backward (per-stage NCCL all-reduce on a side stream)"
                                                    if overlap else ("single flat bucket after backward" if world > 1 else "none (1 GPU)")),

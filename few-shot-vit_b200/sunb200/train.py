@@ -58,7 +58,22 @@ def gemm(A, Wt, M, Nn, K, *, lda=None, ldw=None, out=None, ldc=None, taps=1, gro
     return out
 
 
-def wgrad(dY, X, out, P, Ma, Nb, *, Ca=None, Cb=None, ldo=None, taps=1, groups=1, a_goff=0, b_goff=0, conv=None):
+# Weight gradients are off the backward's critical path (nothing downstream reads them before the optimizer), so the ones that
+# write straight into the gradient buffer run on a SIDE stream, overlapping the dgrad / BatchNorm chain.  With small per-GPU
+# batches (data-parallel shards) every kernel is latency bound and the overlap is worth ~20 % of the backward; at full batch
+# the two streams share the SMs and it is neutral.  TrainEngine.backward sets / joins the stream.
+_wg_stream = None
+_wg_keep = []
+
+
+def wgrad(dY, X, out, P, Ma, Nb, *, Ca=None, Cb=None, ldo=None, taps=1, groups=1, a_goff=0, b_goff=0, conv=None, side=False):
+    if side and _wg_stream is not None:
+        main = torch.cuda.current_stream()
+        _wg_stream.wait_stream(main)                 # producers of dY / X (and the zero fill of `out`) are enqueued on `main`
+        with torch.cuda.stream(_wg_stream):
+            wgrad(dY, X, out, P, Ma, Nb, Ca=Ca, Cb=Cb, ldo=ldo, taps=taps, groups=groups, a_goff=a_goff, b_goff=b_goff, conv=conv)
+        _wg_keep.append((dY, X))                     # keep the operands alive until `main` has joined the side stream
+        return
     d = N.WgradDesc()
     d.P, d.Ma, d.Nb = P, Ma, Nb
     d.Ca, d.Cb = Ca if Ca is not None else dY.shape[-1], Cb if Cb is not None else X.shape[-1]
@@ -68,6 +83,16 @@ def wgrad(dY, X, out, P, Ma, Nb, *, Ca=None, Cb=None, ldo=None, taps=1, groups=1
     d.dY, d.ldy, d.X, d.ldx = dY.data_ptr(), dY.shape[-1], X.data_ptr(), X.shape[-1]
     d.out, d.ldo, d.ksplit = out.data_ptr(), ldo if ldo is not None else Nb, 0
     N.check(N.lib().sunb_wgrad(C.byref(d), _st()), "sunb_wgrad")
+
+
+def on_wgrad_stream(fn, *keep):
+    """Run `fn` (weight-gradient launches plus their fold into the gradient buffer) on the side stream."""
+    if _wg_stream is None:
+        return fn()
+    _wg_stream.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(_wg_stream):
+        fn()
+    _wg_keep.append(keep)
 
 
 class BNRec:
@@ -345,9 +370,16 @@ class TrainEngine:
             spans.append((lo, off))
         done = iter(spans)
 
+        global _wg_stream
+        if getattr(self, "_side", None) is None or self._side_dev != self.dev:
+            self._side, self._side_dev = torch.cuda.Stream(device=self.dev), self.dev
+        _wg_stream = self._side
+
         def group_ready():
             lo, hi = next(done)
             if comm is not None:
+                torch.cuda.current_stream().wait_stream(self._side)      # this group's side-stream weight gradients are final
+                _wg_keep.clear()
                 comm.all_reduce_async(flat[lo:hi])
 
         Mf = B * 25
@@ -373,8 +405,11 @@ class TrainEngine:
             N.check(lib.sunb_colstats(dyp.data_ptr(), dim, None, 0, M, dim, sb[0].data_ptr(), sb[1].data_ptr(), _st()), "colstats")
             G[f"patch_embed{stage}.proj.bias"] += sb[0]
             gw = self.zeros(dim, 4 * cin)
-            wgrad(dyp, pe["xs"], gw, M, dim, 4 * cin)
-            G[f"patch_embed{stage}.proj.weight"] += gw.view(dim, 2, 2, cin).permute(0, 3, 1, 2)
+
+            def pe_wgrad(dyp=dyp, pe=pe, gw=gw, M=M, dim=dim, cin=cin, stage=stage):
+                wgrad(dyp, pe["xs"], gw, M, dim, 4 * cin)
+                G[f"patch_embed{stage}.proj.weight"] += gw.view(dim, 2, 2, cin).permute(0, 3, 1, 2)
+            on_wgrad_stream(pe_wgrad, dyp)
             dxs = gemm(dyp, W[f"pe{stage}.d"], M, 4 * cin, dim, out=self.empty(M, 4 * cin))
             g = self.empty(M * 4, cin)
             N.check(lib.sunb_s2d_reorder(dxs.data_ptr(), g.data_ptr(), B, 2 * side, 2 * side, cin, 1, _st()), "sunb_s2d_reorder")
@@ -385,6 +420,9 @@ class TrainEngine:
         group_ready()
         self._stem_backward(ctx, g, P, G, W, B)
         group_ready()
+        torch.cuda.current_stream().wait_stream(self._side)              # join the weight-gradient stream
+        _wg_keep.clear()
+        _wg_stream = None
         if comm is not None:
             comm.finish(flat)
         return G
@@ -398,19 +436,19 @@ class TrainEngine:
         gs = self.scale_rows(g, r_mlp, S, M, dim)
         dhp = gemm(g, W[name + ".conv3.d"], M, 4 * dim, dim, out=self.empty(M, 4 * dim), row_scale=r_mlp, rows_per_img=S,
                    dact_aux=b["hidp"], dact=ACT_GELU)
-        wgrad(gs, b["hid"], G[name + ".mlp.conv3.weight"], M, dim, 4 * dim)
+        wgrad(gs, b["hid"], G[name + ".mlp.conv3.weight"], M, dim, 4 * dim, side=True)
         dxn2 = gemm(dhp, W[name + ".conv1.d"], M, dim, 4 * dim, out=self.empty(M, dim))
-        wgrad(dhp, b["xn2"], G[name + ".mlp.conv1.weight"], M, 4 * dim, dim)
+        wgrad(dhp, b["xn2"], G[name + ".mlp.conv1.weight"], M, 4 * dim, dim, side=True)
         g1 = self.bn_backward(dxn2, b["bnM"], M, P, G, res=g)
         # ---- attention branch: mid = x + rs * proj(attn(qkv(BN1(x))))
         gs1 = self.scale_rows(g1, r_att, S, M, dim)
         dao = gemm(g1, W[name + ".proj.d"], M, inner, dim, out=self.empty(M, ldi), row_scale=r_att, rows_per_img=S)
-        wgrad(gs1, b["ao"], G[name + ".attn.proj.weight"], M, dim, inner, Cb=inner)
+        wgrad(gs1, b["ao"], G[name + ".attn.proj.weight"], M, dim, inner, Cb=inner, side=True)
         dqkv = self.empty(M, ld3)
         N.check(lib.sunb_attention_backward(b["qkv"].data_ptr(), dao.data_ptr(), dqkv.data_ptr(), Bn, S, d, HEADS, ld3, ldi,
                                             _st()), "sunb_attention_backward")
         dxn1 = gemm(dqkv, W[name + ".qkv.d"], M, dim, 3 * inner, out=self.empty(M, dim))
-        wgrad(dqkv, b["xn1"], G[name + ".attn.qkv.weight"], M, 3 * inner, dim, Ca=3 * inner)
+        wgrad(dqkv, b["xn1"], G[name + ".attn.qkv.weight"], M, 3 * inner, dim, Ca=3 * inner, side=True)
         return self.bn_backward(dxn1, b["bnA"], M, P, G, res=g1)
 
     def _conv_block_backward(self, b, g, P, G, W, B):
@@ -420,17 +458,20 @@ class TrainEngine:
         gs = self.scale_rows(g, r, 400, M, 128)
         dh2p = gemm(g, W[name + ".mlp.conv3.d"], M, 256, 128, out=self.empty(M, 256), row_scale=r, rows_per_img=400,
                     dact_aux=b["h2p"], dact=ACT_GELU)
-        wgrad(gs, b["h2"], G[name + ".mlp.conv3.weight"], M, 128, 256)
+        wgrad(gs, b["h2"], G[name + ".mlp.conv3.weight"], M, 128, 256, side=True)
         dh1p = self.empty(M, 256)
         N.check(lib.sunb_gconv3x3(dh2p.data_ptr(), 256, W[name + ".mlp.conv2.d"].data_ptr(), dh1p.data_ptr(), 256, None, 0,
                                   b["h1p"].data_ptr(), 256, B, ACT_NONE, ACT_GELU, _st()), "sunb_gconv3x3(dgrad)")
         scratch = self.zeros(2 * 9 * 128, 128)
-        wgrad(dh2p, b["h1"], scratch, M, 128, 128, Ca=256, Cb=256, taps=9, groups=2, a_goff=128, b_goff=128,
-              conv=(20, 20, 4, 4))
-        N.check(lib.sunb_grouped_wgrad_extract(scratch.data_ptr(), G[name + ".mlp.conv2.weight"].data_ptr(), _st()),
-                "sunb_grouped_wgrad_extract")
+
+        def conv2_wgrad():
+            wgrad(dh2p, b["h1"], scratch, M, 128, 128, Ca=256, Cb=256, taps=9, groups=2, a_goff=128, b_goff=128,
+                  conv=(20, 20, 4, 4))
+            N.check(lib.sunb_grouped_wgrad_extract(scratch.data_ptr(), G[name + ".mlp.conv2.weight"].data_ptr(), _st()),
+                    "sunb_grouped_wgrad_extract")
+        on_wgrad_stream(conv2_wgrad, dh2p)
         dxn = gemm(dh1p, W[name + ".mlp.conv1.d"], M, 128, 256, out=self.empty(M, 128))
-        wgrad(dh1p, b["xn"], G[name + ".mlp.conv1.weight"], M, 256, 128)
+        wgrad(dh1p, b["xn"], G[name + ".mlp.conv1.weight"], M, 256, 128, side=True)
         return self.bn_backward(dxn, b["bn"], M, P, G, res=g)
 
     def _stem_backward(self, ctx, g, P, G, W, B):
@@ -448,14 +489,20 @@ class TrainEngine:
         dc3r = self.bn_backward(dz, bn3, M0, P, G)
         didr = self.bn_backward(dz, bnd, M0, P, G)
         gw3 = self.zeros(9 * 128, 128)
-        wgrad(dc3r, s["a2"], gw3, M0, 128, 128, taps=9, conv=(40, 40, 8, 8))
-        G["stem.conv3.weight"] += gw3.view(9, 128, 128).permute(1, 2, 0).reshape(128, 128, 3, 3)
+
+        def conv3_wgrad():
+            wgrad(dc3r, s["a2"], gw3, M0, 128, 128, taps=9, conv=(40, 40, 8, 8))
+            G["stem.conv3.weight"] += gw3.view(9, 128, 128).permute(1, 2, 0).reshape(128, 128, 3, 3)
+        on_wgrad_stream(conv3_wgrad, dc3r)
         da2 = gemm(dc3r, W["stem.conv3.d"], M0, 128, 128, out=self.empty(M0, 128), taps=9, conv=(40, 40, 8, 8),
                    dact_aux=s["a2"], dact=ACT_LRELU)
         da2r = self.bn_backward(da2, bn2, M0, P, G)
         gw2 = self.zeros(9 * 128, 64)
-        wgrad(da2r, s["a1"], gw2, M0, 128, 64, taps=9, conv=(40, 40, 8, 8))
-        G["stem.conv2.weight"] += gw2.view(9, 128, 64).permute(1, 2, 0).reshape(128, 64, 3, 3)
+
+        def conv2_wgrad():
+            wgrad(da2r, s["a1"], gw2, M0, 128, 64, taps=9, conv=(40, 40, 8, 8))
+            G["stem.conv2.weight"] += gw2.view(9, 128, 64).permute(1, 2, 0).reshape(128, 64, 3, 3)
+        on_wgrad_stream(conv2_wgrad, da2r)
         da1 = gemm(da2r, W["stem.conv2.d"], M0, 64, 128, out=self.empty(M0, 64), taps=9, conv=(40, 40, 8, 8),
                    dact_aux=s["a1"], dact=ACT_LRELU)
         da1r = self.bn_backward(da1, bn1, M0, P, G)
