@@ -3,6 +3,7 @@
 // Reference semantics: nn.BatchNorm2d in training mode (test_phase/models/visformer.py:118-124),
 // ConvBlock tail (visformer.py:232-237), drop_path (visformer.py:89-97).
 #include "common.cuh"
+#include "../../include/sunb200.h"
 
 #include <string.h>
 
@@ -437,6 +438,41 @@ __global__ void permute_cast_kernel(const float* __restrict__ src, long off, lon
     }
 }
 
+// Every bf16 operand layout of the training step (forward + dgrad copies of all GEMM / conv weights) in ONE launch.
+// Each entry is a 4-D permute + cast  dst[a][b][c][d] = src[off + a*sa + b*sb + c*sc + d*sd]  (last dim padded to ldd);
+// the table travels by value in the kernel arguments (graph-capturable, nothing uploaded at step time).
+constexpr int PK_MAX = 96, PK_CHUNK = 2048;
+struct PackArgs {
+    SunbPackDesc d[PK_MAX];
+    int prefix[PK_MAX + 1];
+    int n;
+};
+__global__ void __launch_bounds__(256) pack_multi_kernel(const __grid_constant__ PackArgs args) {
+    const int total = args.prefix[args.n];
+    for (int c = blockIdx.x; c < total; c += gridDim.x) {
+        int lo = 0, hi = args.n;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (args.prefix[mid] <= c) lo = mid; else hi = mid;
+        }
+        const SunbPackDesc& D = args.d[lo];
+        const float* __restrict__ src = reinterpret_cast<const float*>(D.src) + D.off;
+        bf16* __restrict__ dst = reinterpret_cast<bf16*>(D.dst);
+        const int n_el = D.dims[0] * D.dims[1] * D.dims[2] * D.ldd;
+        const int base = (c - args.prefix[lo]) * PK_CHUNK;
+        const int end = min(base + PK_CHUNK, n_el);
+        for (int i = base + threadIdx.x; i < end; i += 256) {
+            const int d3 = i % D.ldd;
+            int r = i / D.ldd;
+            const int d2 = r % D.dims[2];
+            r /= D.dims[2];
+            const int d1 = r % D.dims[1], d0 = r / D.dims[1];
+            dst[i] = __float2bfloat16(d3 < D.dims[3]
+                ? src[(long)d0 * D.strides[0] + (long)d1 * D.strides[1] + (long)d2 * D.strides[2] + (long)d3 * D.strides[3]] : 0.f);
+        }
+    }
+}
+
 // grouped 3x3 weight [256,32,3,3] (8 groups) -> block-diagonal channel pairs [4][9][64][64] (bf16).
 // transpose_flip = 0: forward operand  dst[p][tap][n][k] = W[p*64+n][k - 32*(n/32)][tap]   (zero off the diagonal)
 // transpose_flip = 1: dgrad operand    dst[p][tap][k_in][n_out] with tap mirrored (8 - tap): conv-transpose weights
@@ -667,6 +703,28 @@ int sunb_permute_cast(const float* src, long off, long sa, long sb, long sc, int
     permute_cast_kernel<<<grid_for((long)A * B * ldd), 256, 0, ST(stream)>>>(src, off, sa, sb, sc, A, B, Cd, ldd,
                                                                               reinterpret_cast<bf16*>(dst));
     SUNB_CHECK_CUDA(cudaGetLastError());
+    return SUNB_OK;
+}
+
+int sunb_pack_weights(const SunbPackDesc* descs, int n, void* stream) {
+    SUNB_REQUIRE(descs && n > 0, "pack_weights: bad arguments");
+    for (int t0 = 0; t0 < n; t0 += PK_MAX) {
+        PackArgs a;
+        a.n = n - t0 < PK_MAX ? n - t0 : PK_MAX;
+        a.prefix[0] = 0;
+        for (int i = 0; i < a.n; ++i) {
+            a.d[i] = descs[t0 + i];
+            const SunbPackDesc& D = a.d[i];
+            SUNB_REQUIRE(D.src && D.dst && D.dims[0] > 0 && D.dims[1] > 0 && D.dims[2] > 0 && D.dims[3] > 0 && D.ldd >= D.dims[3],
+                         "pack_weights: bad entry %d", t0 + i);
+            const long n_el = (long)D.dims[0] * D.dims[1] * D.dims[2] * D.ldd;
+            SUNB_REQUIRE(n_el < (1L << 30), "pack_weights: entry %d too large", t0 + i);
+            a.prefix[i + 1] = a.prefix[i] + (int)((n_el + PK_CHUNK - 1) / PK_CHUNK);
+        }
+        const int total = a.prefix[a.n];
+        pack_multi_kernel<<<total < 148 * 16 ? total : 148 * 16, 256, 0, ST(stream)>>>(a);
+        SUNB_CHECK_CUDA(cudaGetLastError());
+    }
     return SUNB_OK;
 }
 

@@ -53,6 +53,11 @@ class OptTensor(C.Structure):
     _fields_ = [("p", vp), ("g", vp), ("m", vp), ("v", vp), ("n", C.c_int64)]
 
 
+class PackDesc(C.Structure):
+    _fields_ = [("src", vp), ("dst", vp), ("off", C.c_int64), ("strides", C.c_int32 * 4), ("dims", C.c_int32 * 4),
+                ("ldd", C.c_int32), ("reserved", C.c_int32)]
+
+
 class ConvMlpW(C.Structure):
     _fields_ = [("w1", vp), ("b1", fp), ("w2", vp), ("w3", vp), ("w23", vp)]
 
@@ -118,6 +123,7 @@ SIGNATURES = {
     "sunb_scale_rows": (C.c_int, [vp, fp, C.c_int, vp, C.c_long, C.c_int, vp]),
     "sunb_s2d_reorder": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "sunb_batch_sum": (C.c_int, [vp, C.c_int, C.c_long, fp, vp]),
+    "sunb_pack_weights": (C.c_int, [C.POINTER(PackDesc), C.c_int, vp]),
     "sunb_permute_cast": (C.c_int, [fp, C.c_long, C.c_long, C.c_long, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
     "sunb_grouped_pairs": (C.c_int, [fp, vp, C.c_int, vp]),
     "sunb_grouped_wgrad_extract": (C.c_int, [fp, fp, vp]),
@@ -136,7 +142,7 @@ SIGNATURES = {
 }
 
 _lib = None
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 
 def lib() -> C.CDLL:

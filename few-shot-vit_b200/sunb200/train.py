@@ -206,41 +206,70 @@ class TrainEngine:
 
     # ------------------------------------------------------------------ weight preparation (fp32 masters -> bf16 operands)
     def prep_weights(self, P) -> Dict[str, torch.Tensor]:
-        W = {}
+        """Forward (.f) and data-gradient (.d) bf16 operand layouts of every GEMM / conv weight, written by ONE launch.
+        The descriptor table and the destination buffer are built once per parameter set and reused every step."""
+        key = tuple(t.data_ptr() for t in P.values())
+        cached = getattr(self, "_pack", None)
+        if cached is None or cached[0] != key:
+            cached = (key,) + self._plan_weight_pack(P)
+            self._pack = cached
+        _, descs, n, W, _buf = cached
+        N.check(self.lib.sunb_pack_weights(descs, n, _st()), "sunb_pack_weights")
+        return W
+
+    def _plan_weight_pack(self, P):
+        plan = []                                   # (key, src, dims4, strides4, off, ldd, row length of the 2-D view)
+
+        def add(key, src, dims, strides, off=0, ldd=None, cols=None):
+            dims, strides = tuple(dims), tuple(strides)
+            while len(dims) < 4:                    # leading unit dims
+                dims, strides = (1,) + dims, (0,) + strides
+            plan.append((key, src, dims, strides, off, ldd or dims[3], cols or ldd or dims[3]))
+
         for name, cin, cout in (("stem.conv2", 64, 128), ("stem.conv3", 128, 128)):
             w = P[name + ".weight"]
-            W[name + ".f"] = self.pcast(w, (9, cout, cin), (1, cin * 9, 9))                 # [tap][n][c]
-            W[name + ".d"] = self.pcast(w, (9, cin, cout), (-1, 9, cin * 9), off=8)          # [tap][c][n], taps mirrored
+            add(name + ".f", w, (9, cout, cin), (1, cin * 9, 9))                          # [tap][n][c]
+            add(name + ".d", w, (9, cin, cout), (-1, 9, cin * 9), off=8)                   # [tap][c][n], taps mirrored
         for i in range(DEPTH[0]):
             b = f"stage1.{i}.mlp."
-            W[b + "conv1.f"] = self.pcast(P[b + "conv1.weight"], (1, 256, 128), (0, 128, 1))
-            W[b + "conv1.d"] = self.pcast(P[b + "conv1.weight"], (1, 128, 256), (0, 1, 128))
-            W[b + "conv3.f"] = self.pcast(P[b + "conv3.weight"], (1, 128, 256), (0, 256, 1))
-            W[b + "conv3.d"] = self.pcast(P[b + "conv3.weight"], (1, 256, 128), (0, 1, 256))
-            for key, flip in ((".f", 0), (".d", 1)):
-                dst = self.empty(8 * 9 * 32, 32)
-                N.check(self.lib.sunb_gconv_pack(P[b + "conv2.weight"].data_ptr(), dst.data_ptr(), flip, _st()),
-                        "sunb_gconv_pack")
-                W[b + "conv2" + key] = dst
+            add(b + "conv1.f", P[b + "conv1.weight"], (256, 128), (128, 1))
+            add(b + "conv1.d", P[b + "conv1.weight"], (128, 256), (1, 128))
+            add(b + "conv3.f", P[b + "conv3.weight"], (128, 256), (256, 1))
+            add(b + "conv3.d", P[b + "conv3.weight"], (256, 128), (1, 256))
+            # grouped [256][32][3][3] -> [8 groups][9 taps][32 n][32 k]; the dgrad copy swaps n / k and mirrors the taps
+            add(b + "conv2.f", P[b + "conv2.weight"], (8, 9, 32, 32), (32 * 288, 1, 288, 9))
+            add(b + "conv2.d", P[b + "conv2.weight"], (8, 9, 32, 32), (32 * 288, -1, 9, 288), off=8)
         for stage, cin, dim, depth in (("2", 128, 256, DEPTH[1]), ("3", 256, 512, DEPTH[2])):
             w = P[f"patch_embed{stage}.proj.weight"]
-            W[f"pe{stage}.f"] = self.pcast(w, (dim, 4, cin), (cin * 4, 1, 4)).view(dim, 4 * cin)       # [n][(tap,c)]
-            W[f"pe{stage}.d"] = self.pcast(w, (4, cin, dim), (1, 4, cin * 4)).view(4 * cin, dim)       # [(tap,c)][n]
+            add(f"pe{stage}.f", w, (dim, 4, cin), (cin * 4, 1, 4), cols=4 * cin)          # [n][(tap,c)]
+            add(f"pe{stage}.d", w, (4, cin, dim), (1, 4, cin * 4))                        # [(tap,c)][n]
             d = round(dim // HEADS)
             inner = HEADS * d
             ldi = (inner + 7) // 8 * 8
             ld3 = (3 * inner + 15) // 16 * 16
             for i in range(depth):
                 b = f"stage{stage}.{i}."
-                W[b + "qkv.f"] = self.pcast(P[b + "attn.qkv.weight"], (1, 3 * inner, dim), (0, dim, 1))
-                W[b + "qkv.d"] = self.pcast(P[b + "attn.qkv.weight"], (1, dim, 3 * inner), (0, 1, dim), ldd=ld3)
-                W[b + "proj.f"] = self.pcast(P[b + "attn.proj.weight"], (1, dim, inner), (0, inner, 1), ldd=ldi)
-                W[b + "proj.d"] = self.pcast(P[b + "attn.proj.weight"], (1, inner, dim), (0, 1, inner))
-                W[b + "conv1.f"] = self.pcast(P[b + "mlp.conv1.weight"], (1, 4 * dim, dim), (0, dim, 1))
-                W[b + "conv1.d"] = self.pcast(P[b + "mlp.conv1.weight"], (1, dim, 4 * dim), (0, 1, dim))
-                W[b + "conv3.f"] = self.pcast(P[b + "mlp.conv3.weight"], (1, dim, 4 * dim), (0, 4 * dim, 1))
-                W[b + "conv3.d"] = self.pcast(P[b + "mlp.conv3.weight"], (1, 4 * dim, dim), (0, 1, 4 * dim))
-        return {k: v.view(-1, v.shape[-1]) for k, v in W.items()}
+                add(b + "qkv.f", P[b + "attn.qkv.weight"], (3 * inner, dim), (dim, 1))
+                add(b + "qkv.d", P[b + "attn.qkv.weight"], (dim, 3 * inner), (1, dim), ldd=ld3)
+                add(b + "proj.f", P[b + "attn.proj.weight"], (dim, inner), (inner, 1), ldd=ldi)
+                add(b + "proj.d", P[b + "attn.proj.weight"], (inner, dim), (1, inner))
+                add(b + "conv1.f", P[b + "mlp.conv1.weight"], (4 * dim, dim), (dim, 1))
+                add(b + "conv1.d", P[b + "mlp.conv1.weight"], (dim, 4 * dim), (1, dim))
+                add(b + "conv3.f", P[b + "mlp.conv3.weight"], (dim, 4 * dim), (4 * dim, 1))
+                add(b + "conv3.d", P[b + "mlp.conv3.weight"], (4 * dim, dim), (1, 4 * dim))
+        sizes = [(dm[0] * dm[1] * dm[2] * ldd + 127) // 128 * 128 for _, _, dm, _, _, ldd, _ in plan]  # 256-byte aligned slices
+        buf = torch.empty(sum(sizes), dtype=torch.bfloat16, device=self.dev)
+        descs = (N.PackDesc * len(plan))()
+        W, o = {}, 0
+        for e, ((key, src, dims, strides, off, ldd, cols), sz) in enumerate(zip(plan, sizes)):
+            n_el = dims[0] * dims[1] * dims[2] * ldd
+            dst = buf[o:o + n_el]
+            o += sz
+            descs[e].src, descs[e].dst, descs[e].off, descs[e].ldd = src.data_ptr(), dst.data_ptr(), off, ldd
+            for j in range(4):
+                descs[e].strides[j], descs[e].dims[j] = strides[j], dims[j]
+            W[key] = dst.view(-1, cols)
+        return descs, len(plan), W, buf
 
     # ------------------------------------------------------------------ forward
     def forward(self, P, Bf, x, rs: Dict[str, List[Optional[torch.Tensor]]], update_running=True):

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SUNB_ABI_VERSION 6
+#define SUNB_ABI_VERSION 7
 
 int sunb_abi_version(void);
 const char* sunb_last_error(void);
@@ -229,6 +229,19 @@ int sunb_pool_backward(const float* dpooled, const float* ddense, void* dy, int 
 int sunb_scale_rows(const void* in, const float* rs, int rows_per_img, void* out, long M, int C, void* stream);
 int sunb_s2d_reorder(const void* in, void* out, int B, int H, int W, int C, int dir, void* stream);
 int sunb_batch_sum(const void* g, int B, long n, float* out, void* stream);
+/* All weight operand copies of one training step in ONE launch: entry i writes the bf16 tensor
+ * dst[a][b][c][d] = src[off + a*strides[0] + b*strides[1] + c*strides[2] + d*strides[3]] for d < dims[3], zero for
+ * dims[3] <= d < ldd.  descs: HOST array, passed to the kernel by value (nothing is uploaded; CUDA-graph capturable). */
+typedef struct SunbPackDesc {
+    const void* src;    /* fp32 master weight */
+    void* dst;          /* bf16 operand, contiguous [dims0][dims1][dims2][ldd] */
+    int64_t off;        /* element offset added to every source index (mirrored taps start at the last tap) */
+    int32_t strides[4]; /* source strides in elements (may be negative or zero) */
+    int32_t dims[4];
+    int32_t ldd;        /* padded length of the last destination dimension */
+    int32_t reserved;
+} SunbPackDesc;
+int sunb_pack_weights(const SunbPackDesc* descs, int n, void* stream);
 int sunb_permute_cast(const float* src, long off, long sa, long sb, long sc, int A, int B, int Cd, int ldd, void* dst,
                       void* stream);
 int sunb_grouped_pairs(const float* w, void* dst, int transpose_flip, void* stream);
