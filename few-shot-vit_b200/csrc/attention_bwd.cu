@@ -246,13 +246,24 @@ int launch_bwd(const bf16* qkv, const bf16* dout, bf16* dqkv, int n_pairs, int S
 
 }  // namespace
 
-extern "C" int sunb_attention_backward(const void* qkv, const void* dout, void* dqkv, int B, int S, int d, int heads,
-                                       int ld_qkv, int ld_out, void* stream) {
-    SUNB_REQUIRE(qkv && dout && dqkv && B > 0 && heads > 0, "attention_backward: bad arguments");
+int sunb_attention_bwd_tc_supported(const bf16* qkv, const bf16* dout, const bf16* dqkv, int S, int d, int ds, int ld_qkv,
+                                    int ld_out);
+int sunb_launch_attention_bwd_tc(const bf16* qkv, const bf16* dout, bf16* dqkv, int B, int S, int d, int ds, int heads,
+                                 int ld_qkv, int ld_out, cudaStream_t stream);
+
+extern "C" int sunb_attention_backward(const void* qkv, const void* dout, void* dqkv, int B, int S, int d, int d_stride,
+                                       int heads, int ld_qkv, int ld_out, void* stream) {
+    SUNB_REQUIRE(qkv && dout && dqkv && B > 0 && heads > 0 && d > 0 && d_stride >= d, "attention_backward: bad arguments");
+    SUNB_REQUIRE(ld_qkv >= 3 * heads * d_stride && ld_out >= heads * d_stride, "attention_backward: row strides too small");
     const bf16* q = reinterpret_cast<const bf16*>(qkv);
     const bf16* o = reinterpret_cast<const bf16*>(dout);
     bf16* dq = reinterpret_cast<bf16*>(dqkv);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (d_stride != d) {                                    // padded heads: the tcgen05 kernel (attention_bwd_tc.cu)
+        SUNB_REQUIRE(sunb_attention_bwd_tc_supported(q, o, dq, S, d, d_stride, ld_qkv, ld_out),
+                     "attention_backward: padded layout S=%d d=%d d_stride=%d is not supported", S, d, d_stride);
+        return sunb_launch_attention_bwd_tc(q, o, dq, B, S, d, d_stride, heads, ld_qkv, ld_out, st);
+    }
     const int n_pairs = B * heads;
     if (S <= 32 && d <= 96 && d > 48) return launch_bwd<32, 96, 2>(q, o, dq, n_pairs, S, d, heads, ld_qkv, ld_out, st);
     if (S <= 32 && d <= 48) return launch_bwd<32, 48, 2>(q, o, dq, n_pairs, S, d, heads, ld_qkv, ld_out, st);

@@ -467,7 +467,7 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const __grid_constant__
             const int d2 = r % D.dims[2];
             r /= D.dims[2];
             const int d1 = r % D.dims[1], d0 = r / D.dims[1];
-            dst[i] = __float2bfloat16(d3 < D.dims[3]
+            dst[i] = __float2bfloat16(d3 < D.dims[3] && (D.valid2 == 0 || d2 < D.valid2)
                 ? src[(long)d0 * D.strides[0] + (long)d1 * D.strides[1] + (long)d2 * D.strides[2] + (long)d3 * D.strides[3]] : 0.f);
         }
     }

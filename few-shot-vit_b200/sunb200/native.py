@@ -55,7 +55,7 @@ class OptTensor(C.Structure):
 
 class PackDesc(C.Structure):
     _fields_ = [("src", vp), ("dst", vp), ("off", C.c_int64), ("strides", C.c_int32 * 4), ("dims", C.c_int32 * 4),
-                ("ldd", C.c_int32), ("reserved", C.c_int32)]
+                ("ldd", C.c_int32), ("valid2", C.c_int32)]
 
 
 class ConvMlpW(C.Structure):
@@ -131,7 +131,7 @@ SIGNATURES = {
     "sunb_gconv_pack": (C.c_int, [fp, vp, C.c_int, vp]),
     "sunb_convmlp_tail": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, vp]),
     "sunb_layernorm_rows": (C.c_int, [fp, fp, fp, fp, C.c_long, C.c_int, C.c_float, vp]),
-    "sunb_attention_backward": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "sunb_attention_backward": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "sunb_episode_logits_backward": (C.c_int, [fp, fp, fp, fp, fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                C.c_int, fp, C.c_float, vp]),
     "sunb_emd_head": (C.c_int, [fp, fp, fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp]),

@@ -95,6 +95,12 @@ def on_wgrad_stream(fn, *keep):
     _wg_keep.append(keep)
 
 
+def head_dims(dim):
+    """(d, ds): channels per head (visformer.py:170-171) and the padded head stride of the tcgen05 attention kernels."""
+    d = round(dim // HEADS)
+    return d, (48 if d <= 48 else 96)
+
+
 class BNRec:
     """Per-layer BatchNorm record: statistics of this step and the tensors the backward needs."""
     __slots__ = ("name", "C", "count", "buf", "x", "frozen")
@@ -220,11 +226,11 @@ class TrainEngine:
     def _plan_weight_pack(self, P):
         plan = []                                   # (key, src, dims4, strides4, off, ldd, row length of the 2-D view)
 
-        def add(key, src, dims, strides, off=0, ldd=None, cols=None):
+        def add(key, src, dims, strides, off=0, ldd=None, cols=None, valid2=0):
             dims, strides = tuple(dims), tuple(strides)
             while len(dims) < 4:                    # leading unit dims
                 dims, strides = (1,) + dims, (0,) + strides
-            plan.append((key, src, dims, strides, off, ldd or dims[3], cols or ldd or dims[3]))
+            plan.append((key, src, dims, strides, off, ldd or dims[3], cols or ldd or dims[3], valid2))
 
         for name, cin, cout in (("stem.conv2", 64, 128), ("stem.conv3", 128, 128)):
             w = P[name + ".weight"]
@@ -243,29 +249,30 @@ class TrainEngine:
             w = P[f"patch_embed{stage}.proj.weight"]
             add(f"pe{stage}.f", w, (dim, 4, cin), (cin * 4, 1, 4), cols=4 * cin)          # [n][(tap,c)]
             add(f"pe{stage}.d", w, (4, cin, dim), (1, 4, cin * 4))                        # [(tap,c)][n]
-            d = round(dim // HEADS)
+            d, ds = head_dims(dim)
             inner = HEADS * d
-            ldi = (inner + 7) // 8 * 8
-            ld3 = (3 * inner + 15) // 16 * 16
             for i in range(depth):
                 b = f"stage{stage}.{i}."
-                add(b + "qkv.f", P[b + "attn.qkv.weight"], (3 * inner, dim), (dim, 1))
-                add(b + "qkv.d", P[b + "attn.qkv.weight"], (dim, 3 * inner), (1, dim), ldd=ld3)
-                add(b + "proj.f", P[b + "attn.proj.weight"], (dim, inner), (inner, 1), ldd=ldi)
-                add(b + "proj.d", P[b + "attn.proj.weight"], (inner, dim), (1, inner))
+                # heads padded from d to ds channels (zero weights): the tcgen05 attention kernels' layout
+                wq, wp = P[b + "attn.qkv.weight"], P[b + "attn.proj.weight"]
+                add(b + "qkv.f", wq, (3 * HEADS, ds, dim), (d * dim, dim, 1), valid2=d)          # [(x,y)][z][c]
+                add(b + "qkv.d", wq, (dim, 3 * HEADS, d), (1, d * dim, dim), ldd=ds, cols=3 * HEADS * ds)   # [c][(x,y)][z]
+                add(b + "proj.f", wp, (dim, HEADS, d), (inner, d, 1), ldd=ds, cols=HEADS * ds)     # [n][y][z]
+                add(b + "proj.d", wp, (HEADS, ds, dim), (d, 1, inner), valid2=d)                    # [y][z][n]
                 add(b + "conv1.f", P[b + "mlp.conv1.weight"], (4 * dim, dim), (dim, 1))
                 add(b + "conv1.d", P[b + "mlp.conv1.weight"], (dim, 4 * dim), (1, dim))
                 add(b + "conv3.f", P[b + "mlp.conv3.weight"], (dim, 4 * dim), (4 * dim, 1))
                 add(b + "conv3.d", P[b + "mlp.conv3.weight"], (4 * dim, dim), (1, 4 * dim))
-        sizes = [(dm[0] * dm[1] * dm[2] * ldd + 127) // 128 * 128 for _, _, dm, _, _, ldd, _ in plan]  # 256-byte aligned slices
+        sizes = [(dm[0] * dm[1] * dm[2] * ldd + 127) // 128 * 128 for _, _, dm, _, _, ldd, _, _ in plan]  # 256-byte aligned
         buf = torch.empty(sum(sizes), dtype=torch.bfloat16, device=self.dev)
         descs = (N.PackDesc * len(plan))()
         W, o = {}, 0
-        for e, ((key, src, dims, strides, off, ldd, cols), sz) in enumerate(zip(plan, sizes)):
+        for e, ((key, src, dims, strides, off, ldd, cols, valid2), sz) in enumerate(zip(plan, sizes)):
             n_el = dims[0] * dims[1] * dims[2] * ldd
             dst = buf[o:o + n_el]
             o += sz
             descs[e].src, descs[e].dst, descs[e].off, descs[e].ldd = src.data_ptr(), dst.data_ptr(), off, ldd
+            descs[e].valid2 = valid2
             for j in range(4):
                 descs[e].strides[j], descs[e].dims[j] = strides[j], dims[j]
             W[key] = dst.view(-1, cols)
@@ -334,9 +341,9 @@ class TrainEngine:
             pos = P[f"pos_embed{stage}"][0].permute(1, 2, 0).reshape(S, dim).contiguous()
             cur = self.bn_apply(y, bnp, M, ACT_NONE, tab=pos, tab_mod=S)
             ctx[f"pe{stage}"] = dict(xs=xs, y=y, bn=bnp)
-            d = round(dim // HEADS)
-            inner = HEADS * d
-            ldi, ld3 = (inner + 15) // 16 * 16, (3 * inner + 15) // 16 * 16
+            d, ds = head_dims(dim)
+            inner = HEADS * ds                                       # padded heads: pad channels are exact zeros everywhere
+            ldi, ld3 = inner, 3 * inner
             for i in range(depth):
                 name = f"stage{stage}.{i}"
                 rr = rs.get(name) or [None, None]
@@ -344,7 +351,7 @@ class TrainEngine:
                 xn1 = self.bn_apply(cur, bnA, M)
                 qkv = gemm(xn1, W[name + ".qkv.f"], M, 3 * inner, dim, out=self.empty(M, ld3))
                 ao = self.empty(M, ldi)
-                N.check(lib.sunb_attention(qkv.data_ptr(), ao.data_ptr(), B, S, d, d, HEADS, ld3, ldi, _st()), "sunb_attention")
+                N.check(lib.sunb_attention(qkv.data_ptr(), ao.data_ptr(), B, S, d, ds, HEADS, ld3, ldi, _st()), "sunb_attention")
                 mid = gemm(ao, W[name + ".proj.f"], M, dim, inner, out=self.empty(M, dim), resid=cur, row_scale=rr[0],
                            rows_per_img=S)
                 bnM = self.bn_forward(mid, name + ".norm2.bn", dim, M, P, Bf, update_running)
@@ -354,7 +361,7 @@ class TrainEngine:
                 nxt = gemm(hid, W[name + ".conv3.f"], M, dim, 4 * dim, out=self.empty(M, dim), resid=mid, row_scale=rr[1],
                            rows_per_img=S)
                 ctx["blocks"].append(dict(kind="attn", name=name, x=cur, bnA=bnA, xn1=xn1, qkv=qkv, ao=ao, mid=mid, bnM=bnM,
-                                          xn2=xn2, hid=hid, hidp=hidp, rs=rr, S=S, dim=dim, d=d, inner=inner, ldi=ldi,
+                                          xn2=xn2, hid=hid, hidp=hidp, rs=rr, S=S, dim=dim, d=d, ds=ds, inner=inner, ldi=ldi,
                                           ld3=ld3, M=M, stage=stage))
                 cur = nxt
 
@@ -389,7 +396,7 @@ class TrainEngine:
         order = [n for grp in groups for n in grp]
         assert len(order) == len(P), "parameter grouping must cover every encoder parameter"
         flat = torch.zeros(sum(P[n].numel() for n in order), dtype=torch.float32, device=self.dev)
-        self.arena = _ZeroArena(2560 * 1024, self.dev)              # backward: tickets, pos / bias sums, weight-gradient scratch
+        self.arena = _ZeroArena(7168 * 1024, self.dev)              # backward: tickets, pos / bias sums, weight-gradient scratch
         G, spans, off = {}, [], 0
         for grp in groups:
             lo = off
@@ -459,6 +466,7 @@ class TrainEngine:
     def _attn_block_backward(self, b, g, P, G, W, ):
         lib = self.lib
         name, M, dim, S, d, inner, ldi, ld3 = b["name"], b["M"], b["dim"], b["S"], b["d"], b["inner"], b["ldi"], b["ld3"]
+        ds = b["ds"]
         Bn = M // S
         r_att, r_mlp = b["rs"]
         # ---- MLP branch: out = mid + rs * conv3(gelu(conv1(BN2(mid))))
@@ -472,12 +480,22 @@ class TrainEngine:
         # ---- attention branch: mid = x + rs * proj(attn(qkv(BN1(x))))
         gs1 = self.scale_rows(g1, r_att, S, M, dim)
         dao = gemm(g1, W[name + ".proj.d"], M, inner, dim, out=self.empty(M, ldi), row_scale=r_att, rows_per_img=S)
-        wgrad(gs1, b["ao"], G[name + ".attn.proj.weight"], M, dim, inner, Cb=inner, side=True)
+        gwp = self.zeros(dim, inner)                                   # padded-head layouts; folded into the packed gradient
+
+        def proj_wgrad():
+            wgrad(gs1, b["ao"], gwp, M, dim, inner, Cb=inner)
+            G[name + ".attn.proj.weight"].view(dim, HEADS, d).add_(gwp.view(dim, HEADS, ds)[:, :, :d])
+        on_wgrad_stream(proj_wgrad, gs1)
         dqkv = self.empty(M, ld3)
-        N.check(lib.sunb_attention_backward(b["qkv"].data_ptr(), dao.data_ptr(), dqkv.data_ptr(), Bn, S, d, HEADS, ld3, ldi,
-                                            _st()), "sunb_attention_backward")
+        N.check(lib.sunb_attention_backward(b["qkv"].data_ptr(), dao.data_ptr(), dqkv.data_ptr(), Bn, S, d, ds, HEADS, ld3,
+                                            ldi, _st()), "sunb_attention_backward")
         dxn1 = gemm(dqkv, W[name + ".qkv.d"], M, dim, 3 * inner, out=self.empty(M, dim))
-        wgrad(dqkv, b["xn1"], G[name + ".attn.qkv.weight"], M, 3 * inner, dim, Ca=3 * inner, side=True)
+        gwq = self.zeros(3 * inner, dim)
+
+        def qkv_wgrad():
+            wgrad(dqkv, b["xn1"], gwq, M, 3 * inner, dim, Ca=3 * inner)
+            G[name + ".attn.qkv.weight"].view(3 * HEADS, d, dim).add_(gwq.view(3 * HEADS, ds, dim)[:, :d])
+        on_wgrad_stream(qkv_wgrad, dqkv)
         return self.bn_backward(dxn1, b["bnA"], M, P, G, res=g1)
 
     def _conv_block_backward(self, b, g, P, G, W, B):

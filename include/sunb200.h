@@ -231,7 +231,7 @@ int sunb_s2d_reorder(const void* in, void* out, int B, int H, int W, int C, int 
 int sunb_batch_sum(const void* g, int B, long n, float* out, void* stream);
 /* All weight operand copies of one training step in ONE launch: entry i writes the bf16 tensor
  * dst[a][b][c][d] = src[off + a*strides[0] + b*strides[1] + c*strides[2] + d*strides[3]] for d < dims[3], zero for
- * dims[3] <= d < ldd.  descs: HOST array, passed to the kernel by value (nothing is uploaded; CUDA-graph capturable). */
+ * dims[3] <= d < ldd (and for c >= valid2 when valid2 != 0).  descs: HOST array, passed to the kernel by value (nothing is uploaded; CUDA-graph capturable). */
 typedef struct SunbPackDesc {
     const void* src;    /* fp32 master weight */
     void* dst;          /* bf16 operand, contiguous [dims0][dims1][dims2][ldd] */
@@ -239,7 +239,7 @@ typedef struct SunbPackDesc {
     int32_t strides[4]; /* source strides in elements (may be negative or zero) */
     int32_t dims[4];
     int32_t ldd;        /* padded length of the last destination dimension */
-    int32_t reserved;
+    int32_t valid2;     /* 0, or the number of dims[2] entries that come from the source (the rest are zero: padded heads) */
 } SunbPackDesc;
 int sunb_pack_weights(const SunbPackDesc* descs, int n, void* stream);
 int sunb_permute_cast(const float* src, long off, long sa, long sb, long sc, int A, int B, int Cd, int ldd, void* dst,
@@ -265,9 +265,11 @@ int sunb_gconv_pack(const float* w, void* dst, int transpose_flip, void* stream)
  * PatchEmbed GEMM).  The 256-channel hidden tensor between the grouped conv and conv3 never leaves the SM. */
 int sunb_convmlp_tail(const void* h1, const void* wblob, const void* resid, void* out, int B, int s2d, void* stream);
 
-/* backward of the attention core and of the episode head */
-int sunb_attention_backward(const void* qkv, const void* dout, void* dqkv, int B, int S, int d, int heads, int ld_qkv,
-                            int ld_out, void* stream);
+/* backward of the attention core (same layouts as sunb_attention: d_stride == d packed -> warp-MMA kernel, padded heads
+ * d_stride = 48 (S = 100) / 96 (S = 25) -> tcgen05 kernel; dout: gradient of `out`; dqkv pad channels are written as zero)
+ * and of the episode head */
+int sunb_attention_backward(const void* qkv, const void* dout, void* dqkv, int B, int S, int d, int d_stride, int heads,
+                            int ld_qkv, int ld_out, void* stream);
 int sunb_episode_logits_backward(const float* feat_shot, const float* feat_query, const float* dlogits, float* dshot,
                                  float* dquery, float* dtemp, int E, int way, int shot, int Q, int D, int metric,
                                  const float* temp_dev, float temp_host, void* stream);

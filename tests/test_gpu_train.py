@@ -111,25 +111,36 @@ def test_bn_forward_backward_kernels():
     assert int(Bf["bn.num_batches_tracked"]) == 1
 
 
-@pytest.mark.parametrize("S,d", [(100, 42), (25, 85)])
-def test_attention_backward(S, d):
-    B, heads = 3, 6
-    inner = heads * d
-    ld3, ldi = (3 * inner + 7) // 8 * 8, (inner + 7) // 8 * 8
+@pytest.mark.parametrize("S,d,ds,B", [(100, 42, 42, 3), (25, 85, 85, 3)] +
+                         [(S, d, ds, B) for S, d, ds in ((100, 42, 48), (25, 85, 96)) for B in (3, 7, 61)])
+def test_attention_backward(S, d, ds, B):
+    """Packed heads (ds == d: warp-MMA kernel) and padded heads (ds = 48 / 96: tcgen05 kernel, five images per tile for
+    S = 25 -- B = 3, 7, 61 leave ragged last tiles) against autograd through the fp32 formula of visformer.py:183-190."""
+    heads = 6
+    inner = heads * ds
+    ld3, ldi = (3 * inner + 15) // 16 * 16, (inner + 15) // 16 * 16
+    val = torch.zeros(3 * heads, ds, device=DEV)
+    val[:, :d] = 1.0                                                   # pad channels are exact zeros on input
     qkv = torch.zeros(B * S, ld3, device=DEV, dtype=torch.bfloat16)
-    qkv[:, : 3 * inner] = rnd(B * S, 3 * inner, seed=13).bfloat16()
+    qkv[:, : 3 * inner] = (rnd(B * S, 3 * inner, seed=13) * val.reshape(1, -1)).bfloat16()
     dout = torch.zeros(B * S, ldi, device=DEV, dtype=torch.bfloat16)
-    dout[:, :inner] = rnd(B * S, inner, seed=14).bfloat16()
-    dqkv = torch.zeros(B * S, ld3, device=DEV, dtype=torch.bfloat16)
-    N.check(N.lib().sunb_attention_backward(qkv.data_ptr(), dout.data_ptr(), dqkv.data_ptr(), B, S, d, heads, ld3, ldi,
+    dout[:, :inner] = (rnd(B * S, inner, seed=14) * val[:heads].reshape(1, -1)).bfloat16()
+    dqkv = torch.full((B * S, ld3), float("nan"), device=DEV, dtype=torch.bfloat16)
+    N.check(N.lib().sunb_attention_backward(qkv.data_ptr(), dout.data_ptr(), dqkv.data_ptr(), B, S, d, ds, heads, ld3, ldi,
                                             N.current_stream()), "attention_backward")
     torch.cuda.synchronize()
     t = qkv[:, : 3 * inner].float().requires_grad_(True)
-    u = t.reshape(B, S, 3, heads, d).permute(2, 0, 3, 1, 4)
+    u = t.reshape(B, S, 3, heads, ds).permute(2, 0, 3, 1, 4)
     p = torch.softmax(u[0] @ u[1].transpose(-1, -2) * d ** -0.5, dim=-1)
     o = (p @ u[2]).permute(0, 2, 1, 3).reshape(B * S, inner)
     o.backward(dout[:, :inner].float())
-    assert rel_err(dqkv[:, : 3 * inner], t.grad) < 1e-2
+    got = dqkv[:, : 3 * inner].float()
+    assert torch.isfinite(got).all()
+    for x, nm in enumerate("qkv"):                                     # per-operand error: dq, dk, dv
+        sl = slice(x * inner, (x + 1) * inner)
+        assert rel_err(got[:, sl], t.grad[:, sl]) < 1e-2, nm
+    if ds != d:                                                        # pad channels of the gradient are exact zeros
+        assert float(got.reshape(B * S, 3 * heads, ds)[:, :, d:].abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("metric", ["cos", "sqr", "dot"])
