@@ -92,6 +92,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();      // the next kernel may start its set-up; nothing above touched global memory
+    pdl_wait();         // the previous kernel has completed, its writes are visible
 
     if (warp == 0) {
         // ================================================================ TMA producer
@@ -338,8 +340,8 @@ int launch_bwd_tc(const bf16* qkv, const bf16* dout, bf16* dqkv, int B, int head
     const int n_tiles = ((B + C::IPT - 1) / C::IPT) * heads;
     const int sms = sunb_num_sms();
     const int grid = n_tiles < sms ? n_tiles : sms;
-    attention_bwd_tc_kernel<C><<<grid, C::THREADS, C::SMEM, stream>>>(tmQ, tmKV, tmDO, dqkv, B, heads, ld_qkv, scale);
-    SUNB_CHECK_CUDA(cudaGetLastError());
+    SUNB_CHECK_CUDA(sunb_launch(&attention_bwd_tc_kernel<C>, dim3(grid), dim3(C::THREADS), C::SMEM, stream, tmQ, tmKV, tmDO, dqkv, B,
+                                heads, ld_qkv, scale));
     return SUNB_OK;
 }
 

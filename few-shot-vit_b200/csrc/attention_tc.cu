@@ -92,6 +92,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();      // the next kernel may start its set-up; nothing above touched global memory
+    pdl_wait();         // the previous kernel has completed, its writes are visible
 
     if (warp == 0) {
         // ================================================================ TMA producer
@@ -325,8 +327,8 @@ int launch_tc(const bf16* qkv, bf16* out, int B, int heads, int ld_qkv, int ld_o
     const int n_tiles = ((B + C::IPT - 1) / C::IPT) * heads;
     const int sms = sunb_num_sms();
     const int grid = n_tiles < sms ? n_tiles : sms;
-    attention_tc_kernel<C><<<grid, C::THREADS, C::SMEM, stream>>>(tmQ, tmKV, out, B, heads, ld_out, scale * 1.4426950408889634f);
-    SUNB_CHECK_CUDA(cudaGetLastError());
+    SUNB_CHECK_CUDA(sunb_launch(&attention_tc_kernel<C>, dim3(grid), dim3(C::THREADS), C::SMEM, stream, tmQ, tmKV, out, B, heads,
+                                ld_out, scale * 1.4426950408889634f));
     return SUNB_OK;
 }
 

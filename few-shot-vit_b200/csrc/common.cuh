@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <utility>
 
 typedef __nv_bfloat16 bf16;
 
@@ -360,5 +361,39 @@ inline int sunb_launch_gemm(const GemmParams& p, cudaStream_t stream) { return s
 
 // Opt a kernel in to `bytes` (> 48 KB) of dynamic shared memory on the CURRENT device.  The attribute is per device, so the
 // bookkeeping is per (kernel, device): a process that drives several GPUs configures each of them (api.cu).
+// ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  Every step is a chain of 40 (eval forward) to ~230 (training step) dependent kernels on
+// one stream; at data-parallel shard sizes each kernel runs for 5-15 us and the launch + prologue latency between two
+// kernels is a quarter of the step.  Kernels launched through sunb_launch carry the programmatic-stream-serialization
+// attribute and follow one protocol:
+//   * set up everything that does not touch global memory (barrier init, TMEM allocation, tensor-map prefetch),
+//   * pdl_trigger(): once EVERY CTA of this grid has got here the next kernel of the stream may start launching -- its CTAs
+//     become resident as SM resources free up and run their own set-up,
+//   * pdl_wait(): returns when the PREVIOUS grid has completed and its writes are visible; no global memory is read or
+//     written before it.  Completion is transitive (a grid cannot complete before its own wait has returned), and since
+//     all CTAs of a grid are resident (or done) when its trigger fires, a waiting successor never holds a resource an
+//     unscheduled predecessor CTA needs.
+// In a kernel launched without the attribute both instructions are no-ops.  -DSUNB_NO_PDL builds without the attribute.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t sunb_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+#ifndef SUNB_NO_PDL
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+#endif
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 int sunb_opt_in_smem(const void* kernel, int bytes);
 int sunb_num_sms();      // SM count of the current device

@@ -220,6 +220,8 @@ conv_slab2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();      // the next kernel may start its set-up; nothing above touched global memory
+    pdl_wait();         // the previous kernel has completed, its writes are visible
 
     if (warp == 0) {
         // ================================================================ slab producer (own band; bytes reported to the leader)
@@ -392,8 +394,7 @@ int launch2(const GemmParams& p, const SlabGeom& g, const CUtensorMap& tmA, cons
     const int sms = sunb_num_sms();
     const int pairs = (g.tiles + 1) / 2, cl = sms / 2;
     const int grid = 2 * (pairs < cl ? pairs : cl);
-    conv_slab2_kernel<BN><<<grid, THREADS, smem, stream>>>(tmA, tmB2, p, g);
-    SUNB_CHECK_CUDA(cudaGetLastError());
+    SUNB_CHECK_CUDA(sunb_launch(&conv_slab2_kernel<BN>, dim3(grid), dim3(THREADS), smem, stream, tmA, tmB2, p, g));
     return SUNB_OK;
 }
 

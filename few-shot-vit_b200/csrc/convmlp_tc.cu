@@ -107,6 +107,8 @@ convmlp_tail_kernel(const __grid_constant__ CUtensorMap tmH, const uint8_t* __re
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();      // the next kernel may start its set-up; nothing above touched global memory
+    pdl_wait();         // the previous kernel has completed, its writes are visible
 
     if (warp == 0) {
         // ================================================================ activation atoms: one haloed TMA box per 64 channels
@@ -326,8 +328,8 @@ extern "C" int sunb_convmlp_tail(const void* h1, const void* wblob, const void* 
     SUNB_TRY(sunb_opt_in_smem(reinterpret_cast<const void*>(&convmlp_tail_kernel), SMEM_BYTES));
     const int sms = sunb_num_sms();
     const int grid = 2 * B < sms ? 2 * B : sms;
-    convmlp_tail_kernel<<<grid, THREADS, SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(
-        tmH, reinterpret_cast<const uint8_t*>(wblob), reinterpret_cast<const bf16*>(resid), reinterpret_cast<bf16*>(out), B, s2d);
-    SUNB_CHECK_CUDA(cudaGetLastError());
+    SUNB_CHECK_CUDA(sunb_launch(&convmlp_tail_kernel, dim3(grid), dim3(THREADS), SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream), tmH,
+                                reinterpret_cast<const uint8_t*>(wblob), reinterpret_cast<const bf16*>(resid),
+                                reinterpret_cast<bf16*>(out), B, s2d));
     return SUNB_OK;
 }

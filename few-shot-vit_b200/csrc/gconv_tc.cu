@@ -175,6 +175,7 @@ gconv3x3_tc_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__
     {
         uint4* z = reinterpret_cast<uint4*>(base_ptr);
         for (int i = tid; i < STAGES * SLAB_BYTES / 16; i += THREADS) z[i] = make_uint4(0, 0, 0, 0);
+        pdl_wait();               // the packed weights (and everything after) come from earlier kernels of the stream
         uint8_t* wdst = base_ptr + STAGES * SLAB_BYTES;
         for (int i = tid; i < 2 * 9 * GC * 4; i += THREADS) {
             const int c = i & 3, n = (i >> 2) & 31, gt = i >> 7;          // gt = g2 * 9 + tap
@@ -205,6 +206,7 @@ gconv3x3_tc_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();                // TMEM is allocated: the next kernel may start its set-up
 
     if (warp == 0) {
         // ================================================================ MMA issuer
@@ -361,8 +363,8 @@ int sunb_launch_gconv_tc(const bf16* x, int ldx, const bf16* wg, bf16* y, int ld
     SUNB_REQUIRE(!aux || (ldaux % 8 == 0 && (((size_t)aux) & 15) == 0), "gconv3x3: aux must be 16-byte aligned");
     SUNB_TRY(sunb_opt_in_smem(reinterpret_cast<const void*>(&gconv3x3_tc_kernel), SMEM_BYTES));
     const int per_pair = max(1, min(sunb_num_sms() / 4, B));        // CTAs per group pair; 148 SMs = 4 pairs x 37
-    gconv3x3_tc_kernel<<<4 * per_pair, THREADS, SMEM_BYTES, stream>>>(x, ldx, wg, y, ldy, y2, ldy2, aux, ldaux, B, act, dact);
-    SUNB_CHECK_CUDA(cudaGetLastError());
+    SUNB_CHECK_CUDA(sunb_launch(&gconv3x3_tc_kernel, dim3(4 * per_pair), dim3(THREADS), SMEM_BYTES, stream, x, ldx, wg, y, ldy, y2, ldy2,
+                                aux, ldaux, B, act, dact));
     return SUNB_OK;
 }
 

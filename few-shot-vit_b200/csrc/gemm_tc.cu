@@ -195,6 +195,8 @@ __global__ void __launch_bounds__(THREADS1, 1) gemm_tc_kernel(const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();      // the next kernel may start its set-up; nothing above touched global memory
+    pdl_wait();         // the previous kernel has completed, its writes are visible
 
     if (warp == 0) {
         // whole warp walks the schedule; one elected lane issues the TMA traffic
@@ -352,8 +354,7 @@ int launch_bn(const GemmParams& p, const CUtensorMap& tmA, const CUtensorMap& tm
     SUNB_REQUIRE(total < (1L << 31), "gemm_tc: too many tiles");
     const int sms = sunb_num_sms();
     const int grid = (int)(total < sms ? total : sms);     // persistent: one CTA per SM
-    gemm_tc_kernel<BN><<<grid, THREADS1, L::TOTAL, stream>>>(tmA, tmB, p, n_tiles, (int)total);
-    SUNB_CHECK_CUDA(cudaGetLastError());
+    SUNB_CHECK_CUDA(sunb_launch(&gemm_tc_kernel<BN>, dim3(grid), dim3(THREADS1), L::TOTAL, stream, tmA, tmB, p, n_tiles, (int)total));
     return SUNB_OK;
 }
 

@@ -14,6 +14,8 @@ __global__ void final_norm_pool_kernel(const bf16* __restrict__ x, const float* 
                                        const float* __restrict__ shift, float* __restrict__ dense,
                                        bf16* __restrict__ dense_bf16, float* __restrict__ pooled,
                                        bf16* __restrict__ pooled_bf16, int B, int T, int C) {
+    pdl_trigger();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * C) return;
     const int img = i / C, c = i % C;
@@ -43,6 +45,8 @@ __global__ void __launch_bounds__(256) episode_logits_kernel(const float* __rest
                                                              float* __restrict__ logits, int way, int shot, int Q, int D,
                                                              int metric, const float* __restrict__ temp_dev,
                                                              float temp_host) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float proto[];            // [way][D]
     const int e = blockIdx.x;
     const float temp = temp_dev ? *temp_dev : temp_host;
@@ -96,6 +100,8 @@ __global__ void __launch_bounds__(256) episode_logits_kernel(const float* __rest
 __global__ void __launch_bounds__(256) logits_ce_acc_kernel(const float* __restrict__ logits,
                                                             const long long* __restrict__ label, int R, int W,
                                                             float* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float s_loss[256], s_hit[256];
     float loss = 0.f, hit = 0.f;
     for (int r = threadIdx.x; r < R; r += blockDim.x) {
@@ -131,8 +137,8 @@ __global__ void __launch_bounds__(256) logits_ce_acc_kernel(const float* __restr
 int sunb_launch_final_norm_pool(const bf16* x, const float* scale, const float* shift, float* dense, bf16* dense_bf16,
                                 float* pooled, bf16* pooled_bf16, int B, int T, int C, cudaStream_t stream) {
     SUNB_REQUIRE(B > 0 && pooled, "final_norm_pool: bad arguments");
-    final_norm_pool_kernel<<<(B * C + 255) / 256, 256, 0, stream>>>(x, scale, shift, dense, dense_bf16, pooled,
-                                                                    pooled_bf16, B, T, C);
+    SUNB_CHECK_CUDA(sunb_launch(&final_norm_pool_kernel, dim3((B * C + 255) / 256), dim3(256), 0, stream, x, scale, shift, dense, dense_bf16, pooled,
+                                                                    pooled_bf16, B, T, C));
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
 }
@@ -146,15 +152,15 @@ int sunb_launch_episode_logits(const float* feat_shot, const float* feat_query, 
     if (smem > 48 * 1024) SUNB_TRY(sunb_opt_in_smem(reinterpret_cast<const void*>(&episode_logits_kernel), (int)smem));
     int qs = E >= 64 ? 1 : (Q + 7) / 8;           // few episodes: split the queries of an episode over several blocks
     if (qs > 16) qs = 16;
-    episode_logits_kernel<<<dim3(E, qs), 256, smem, stream>>>(feat_shot, feat_query, logits, way, shot, Q, D, metric, temp_dev,
-                                                    temp_host);
+    SUNB_CHECK_CUDA(sunb_launch(&episode_logits_kernel, dim3(E, qs), dim3(256), smem, stream, feat_shot, feat_query, logits, way, shot, Q, D, metric, temp_dev,
+                                                    temp_host));
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
 }
 
 int sunb_launch_logits_ce_acc(const float* logits, const long long* label, int R, int W, float* out, cudaStream_t stream) {
     SUNB_REQUIRE(R > 0 && W > 0, "logits_ce_acc: empty problem");
-    logits_ce_acc_kernel<<<1, 256, 0, stream>>>(logits, label, R, W, out);
+    SUNB_CHECK_CUDA(sunb_launch(&logits_ce_acc_kernel, dim3(1), dim3(256), 0, stream, logits, label, R, W, out));
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
 }
@@ -175,6 +181,8 @@ __global__ void __launch_bounds__(256) episode_logits_bwd_kernel(const float* __
                                                                  float* __restrict__ dtemp, int way, int shot, int Q, int D,
                                                                  int metric, const float* __restrict__ temp_dev,
                                                                  float temp_host) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float smh[];
     float* proto = smh;                    // [way][D]  (normalised for cos)
     float* dph = proto + way * D;          // [way][D]  partial gradient w.r.t. the (normalised) prototype
@@ -259,6 +267,8 @@ __global__ void __launch_bounds__(256) episode_logits_bwd_kernel(const float* __
 __global__ void __launch_bounds__(256) episode_logits_bwd_finish_kernel(const float* __restrict__ feat_shot,
                                                                         float* __restrict__ dshot, int way, int shot, int D,
                                                                         int metric) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float smh[];
     float* proto = smh;                    // [way][D]
     float* dph = proto + way * D;          // [way][D]
@@ -308,10 +318,10 @@ int sunb_launch_episode_logits_bwd(const float* feat_shot, const float* feat_que
     int qs = (Q + 7) / 8;
     if (qs > 16) qs = 16;
     SUNB_CHECK_CUDA(cudaMemsetAsync(dshot, 0, (size_t)E * way * shot * D * sizeof(float), stream));
-    episode_logits_bwd_kernel<<<dim3(E, qs), 256, smem, stream>>>(feat_shot, feat_query, dlogits, dshot, dquery, dtemp, way, shot, Q,
-                                                                  D, metric, temp_dev, temp_host);
+    SUNB_CHECK_CUDA(sunb_launch(&episode_logits_bwd_kernel, dim3(E, qs), dim3(256), smem, stream, feat_shot, feat_query, dlogits, dshot, dquery, dtemp, way, shot, Q,
+                                                                  D, metric, temp_dev, temp_host));
     SUNB_CHECK_CUDA(cudaGetLastError());
-    episode_logits_bwd_finish_kernel<<<E, 256, (size_t)(2 * way * D) * sizeof(float), stream>>>(feat_shot, dshot, way, shot, D, metric);
+    SUNB_CHECK_CUDA(sunb_launch(&episode_logits_bwd_finish_kernel, dim3(E), dim3(256), (size_t)(2 * way * D) * sizeof(float), stream, feat_shot, dshot, way, shot, D, metric));
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
 }
@@ -324,6 +334,8 @@ namespace {
 __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, float* __restrict__ y, long M,
                                                              int C, float eps) {
+    pdl_trigger();
+    pdl_wait();
     const long row = blockIdx.x * 8L + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
@@ -341,7 +353,7 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __rest
 int sunb_launch_layernorm_rows(const float* x, const float* gamma, const float* beta, float* y, long M, int C, float eps,
                                cudaStream_t stream) {
     SUNB_REQUIRE(x && gamma && beta && y && M > 0 && C > 0, "layernorm_rows: bad arguments");
-    layernorm_rows_kernel<<<(int)((M + 7) / 8), 256, 0, stream>>>(x, gamma, beta, y, M, C, eps);
+    SUNB_CHECK_CUDA(sunb_launch(&layernorm_rows_kernel, dim3((int)((M + 7) / 8)), dim3(256), 0, stream, x, gamma, beta, y, M, C, eps));
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
 }

@@ -34,6 +34,8 @@ struct OptArgs {
 
 template <bool ADAMW>
 __global__ void __launch_bounds__(THREADS) fused_opt_kernel(const __grid_constant__ OptArgs args, const float* __restrict__ hp) {
+    pdl_trigger();
+    pdl_wait();
     const SunbOptTensor* tensors = args.t;
     const long long* chunk_prefix = args.prefix;
     const int n_tensors = args.n;
@@ -112,7 +114,11 @@ __global__ void __launch_bounds__(THREADS) fused_opt_kernel(const __grid_constan
     }
 }
 
-__global__ void opt_step_inc_kernel(float* hp) { hp[5] += 1.f; }
+__global__ void opt_step_inc_kernel(float* hp) {
+    pdl_trigger();
+    pdl_wait();
+    hp[5] += 1.f;
+}
 
 template <bool ADAMW>
 int launch_opt(const SunbOptTensor* tensors, int n_tensors, float* hp_dev, cudaStream_t st) {
@@ -127,7 +133,7 @@ int launch_opt(const SunbOptTensor* tensors, int n_tensors, float* hp_dev, cudaS
         }
         const long long total = a.prefix[a.n];
         const int grid = (int)(total < 148 * 8 ? total : 148 * 8);
-        fused_opt_kernel<ADAMW><<<grid, THREADS, 0, st>>>(a, hp_dev);
+        SUNB_CHECK_CUDA(sunb_launch(&fused_opt_kernel<ADAMW>, dim3(grid), dim3(THREADS), 0, st, a, hp_dev));
         SUNB_CHECK_CUDA(cudaGetLastError());
     }
     return SUNB_OK;
@@ -145,7 +151,7 @@ int sunb_fused_sgd(const SunbOptTensor* tensors, int n_tensors, float* hp_dev, v
 int sunb_fused_adamw(const SunbOptTensor* tensors, int n_tensors, float* hp_dev, void* stream) {
     SUNB_REQUIRE(tensors && hp_dev && n_tensors > 0, "fused_adamw: bad arguments");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    opt_step_inc_kernel<<<1, 1, 0, st>>>(hp_dev);                  // the step counter lives on the device (graph replays)
+    SUNB_CHECK_CUDA(sunb_launch(&opt_step_inc_kernel, dim3(1), dim3(1), 0, st, hp_dev));    // the step counter lives on the device
     return launch_opt<true>(tensors, n_tensors, hp_dev, st);
 }
 

@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(THREADS, 1) stem_in_tc_kernel(const float* __r
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot_addr) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    pdl_wait();                   // the master weights below may have been updated by an earlier kernel of the stream
     // weight tile: rows 0..63 conv1, 64..191 downsample; k >= 27 zero (k in [32,64) is never read: K = 32)
     for (int i = tid; i < NOUT * 32; i += THREADS) {
         const int n = i >> 5, k = i & 31;
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(THREADS, 1) stem_in_tc_kernel(const float* __r
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
+    pdl_trigger();                // TMEM is allocated: the next kernel may start its set-up
     // kind::f16: D fp32, A/B bf16 K-major, M = 128, N = 192
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NOUT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const int total = B * NPIX;
@@ -248,7 +250,7 @@ int sunb_launch_stem_in_tc(const float* x, const float* w1, const float* b1, con
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = n_tiles < sms ? n_tiles : sms;      // persistent: one CTA per SM
-    stem_in_tc_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(x, w1, b1, wd, bd, a1, idn, B, lrelu, n_tiles);
+    SUNB_CHECK_CUDA(sunb_launch(&stem_in_tc_kernel, dim3(grid), dim3(THREADS), SMEM_BYTES, stream, x, w1, b1, wd, bd, a1, idn, B, lrelu, n_tiles));
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
 }

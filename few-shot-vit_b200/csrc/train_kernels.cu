@@ -31,6 +31,8 @@ struct BnFin {
 __global__ void __launch_bounds__(256) colstats_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ u,
                                                        int ldu, int M, int C, int rows_per_block,
                                                        float* __restrict__ sum, float* __restrict__ sq, const BnFin fin) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float red[];          // [2][256][8]
     const int nvec = C / 8;
     const int lanes = 256 / nvec;
@@ -123,6 +125,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* _
                                    float* __restrict__ rmean, float* __restrict__ rvar, long long* __restrict__ nbt,
                                    float momentum, float eps, int C, float* __restrict__ scale, float* __restrict__ shift,
                                    float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+    pdl_trigger();
+    pdl_wait();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c == 0 && nbt) *nbt += 1;
     if (c >= C) return;
@@ -145,6 +149,8 @@ __global__ void bn_frozen_kernel(const float* __restrict__ gamma, const float* _
                                  const float* __restrict__ rmean, const float* __restrict__ rvar, float eps, int C,
                                  float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
                                  float* __restrict__ rstd_out) {
+    pdl_trigger();
+    pdl_wait();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const float rstd = rsqrtf(rvar[c] + eps);
@@ -158,6 +164,8 @@ __global__ void bn_frozen_kernel(const float* __restrict__ gamma, const float* _
 __global__ void bn_apply_kernel(const bf16* __restrict__ x, int ldx, const float* __restrict__ scale,
                                 const float* __restrict__ shift, int act, const float* __restrict__ tab, int tab_mod,
                                 bf16* __restrict__ out, int ldo, long M, int C) {
+    pdl_trigger();
+    pdl_wait();
     const int nvec = C / 8;
     if (blockDim.x % nvec == 0) {
         // a thread keeps one 8-channel vector for its whole life (scale / shift in registers) and walks the rows
@@ -221,6 +229,8 @@ __global__ void stem_tail_fwd_kernel(const bf16* __restrict__ c3, const bf16* __
                                      const float* __restrict__ s3, const float* __restrict__ t3,
                                      const float* __restrict__ sd, const float* __restrict__ td,
                                      const float* __restrict__ pos, bf16* __restrict__ out, int B, int H, int W, int C) {
+    pdl_trigger();
+    pdl_wait();
     const int oH = H / 2, oW = W / 2, cv = C / 8;
     const long total = (long)B * oH * oW * cv;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -259,6 +269,8 @@ __global__ void stem_tail_bwd_kernel(const bf16* __restrict__ c3, const bf16* __
                                      const float* __restrict__ s3, const float* __restrict__ t3,
                                      const float* __restrict__ sd, const float* __restrict__ td,
                                      const bf16* __restrict__ g, bf16* __restrict__ dz, int B, int H, int W, int C) {
+    pdl_trigger();
+    pdl_wait();
     const int oH = H / 2, oW = W / 2, cv = C / 8;
     const long total = (long)B * oH * oW * cv;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -307,6 +319,8 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ sdz, const floa
                                        const float* __restrict__ gamma, int C, int frozen, float* __restrict__ a,
                                        float* __restrict__ c1, float* __restrict__ c2, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta) {
+    pdl_trigger();
+    pdl_wait();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const float cen = sdzx[c] - mean[c] * sdz[c];        // sum dz*(x-mean)
@@ -323,6 +337,8 @@ __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dz, int lddz, const
                                     const float* __restrict__ a, const float* __restrict__ c1,
                                     const float* __restrict__ c2, const float* __restrict__ mean,
                                     const bf16* __restrict__ res, int ldr, bf16* __restrict__ out, int ldo, long M, int C) {
+    pdl_trigger();
+    pdl_wait();
     const int nvec = C / 8;
     if (blockDim.x % nvec == 0) {
         // fixed 8-channel vector per thread: dx = k1*dz + k2*x + k3 with k1 = a, k2 = -a*c2, k3 = a*(c2*mean - c1) in registers
@@ -386,6 +402,8 @@ __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dz, int lddz, const
 // out[r, c] = in[r, c] * rs[r / rows_per_img]
 __global__ void scale_rows_kernel(const bf16* __restrict__ in, const float* __restrict__ rs, int rows_per_img,
                                   bf16* __restrict__ out, long M, int C) {
+    pdl_trigger();
+    pdl_wait();
     const int nvec = C / 8;
     const long total = M * nvec;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -404,6 +422,8 @@ __global__ void scale_rows_kernel(const bf16* __restrict__ in, const float* __re
 
 // out[s2d_row(m)] <- in[m] (dir 0: raster -> space-to-depth) or out[m] <- in[s2d_row(m)] (dir 1), rows of C channels
 __global__ void s2d_reorder_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int B, int H, int W, int C, int dir) {
+    pdl_trigger();
+    pdl_wait();
     const int nvec = C / 8;
     const long total = (long)B * H * W * nvec;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -419,6 +439,8 @@ __global__ void s2d_reorder_kernel(const bf16* __restrict__ in, bf16* __restrict
 
 // out[i] += sum_b g[b, i]   (i over S*C), fp32 accumulate -- gradient of a broadcast positional embedding
 __global__ void batch_sum_kernel(const bf16* __restrict__ g, int B, long n, float* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
         float a = 0.f;
         for (int b = 0; b < B; ++b) a += __bfloat162float(g[(size_t)b * n + i]);
@@ -429,6 +451,8 @@ __global__ void batch_sum_kernel(const bf16* __restrict__ g, int B, long n, floa
 // generic permute + cast: dst[a][b][c] (bf16, contiguous, last dim padded to ldd) = src[off + a*sa + b*sb + c*sc] (fp32)
 __global__ void permute_cast_kernel(const float* __restrict__ src, long off, long sa, long sb, long sc, int A, int Bd,
                                     int Cd, int ldd, bf16* __restrict__ dst) {
+    pdl_trigger();
+    pdl_wait();
     const long total = (long)A * Bd * ldd;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const int c = (int)(i % ldd);
@@ -448,6 +472,8 @@ struct PackArgs {
     int n;
 };
 __global__ void __launch_bounds__(256) pack_multi_kernel(const __grid_constant__ PackArgs args) {
+    pdl_trigger();
+    pdl_wait();
     const int total = args.prefix[args.n];
     for (int c = blockIdx.x; c < total; c += gridDim.x) {
         int lo = 0, hi = args.n;
@@ -477,6 +503,8 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const __grid_constant__
 // transpose_flip = 0: forward operand  dst[p][tap][n][k] = W[p*64+n][k - 32*(n/32)][tap]   (zero off the diagonal)
 // transpose_flip = 1: dgrad operand    dst[p][tap][k_in][n_out] with tap mirrored (8 - tap): conv-transpose weights
 __global__ void grouped_pairs_kernel(const float* __restrict__ w, bf16* __restrict__ dst, int transpose_flip) {
+    pdl_trigger();
+    pdl_wait();
     const int total = 4 * 9 * 64 * 64;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int col = i % 64, row = (i / 64) % 64, tap = (i / 4096) % 9, p = i / (4096 * 9);
@@ -493,6 +521,8 @@ __global__ void grouped_pairs_kernel(const float* __restrict__ w, bf16* __restri
 
 // dW2[256][32][3][3] += diagonal 32x32 blocks of the pair-wise wgrad scratch [2 halves][9][128][128]
 __global__ void grouped_wgrad_extract_kernel(const float* __restrict__ scratch, float* __restrict__ dw) {
+    pdl_trigger();
+    pdl_wait();
     const int total = 256 * 32 * 9;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int tap = i % 9, ci = (i / 9) % 32, co = i / (9 * 32);
@@ -504,6 +534,8 @@ __global__ void grouped_wgrad_extract_kernel(const float* __restrict__ scratch, 
 // dy[b, t, c] = dpooled[b, c] / T (+ ddense[b, t, c])  -> bf16
 __global__ void pool_bwd_kernel(const float* __restrict__ dpooled, const float* __restrict__ ddense, bf16* __restrict__ dy,
                                 int B, int T, int C) {
+    pdl_trigger();
+    pdl_wait();
     const long total = (long)B * T * C;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const int c = (int)(i % C);
@@ -520,6 +552,8 @@ __global__ void pool_bwd_kernel(const float* __restrict__ dpooled, const float* 
 // over it (wgrad_tc.cu).  The first version kept 27 register accumulators per channel lane and was bound by its
 // shared-memory broadcast loads (869 us at 480 images).
 __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x, bf16* __restrict__ patches, int total) {
+    pdl_trigger();
+    pdl_wait();
     for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < total; m += gridDim.x * blockDim.x) {
         const int img = m / 1600, rem = m - img * 1600, oy = rem / 40, ox = rem - oy * 40;
         const float* xi = x + (size_t)img * 3 * 80 * 80;
@@ -559,8 +593,8 @@ int sunb_colstats(const void* x, int ldx, const void* u, int ldu, long M, int C,
     if (blocks > 148L * 8) { rpb = (int)((M + 148L * 8 - 1) / (148L * 8)); rpb = (rpb + lanes - 1) / lanes * lanes; blocks = (M + rpb - 1) / rpb; }
     BnFin fin;
     memset(&fin, 0, sizeof(fin));
-    colstats_kernel<<<(int)blocks, 256, 2 * 2048 * sizeof(float), ST(stream)>>>(
-        reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<const bf16*>(u), ldu, (int)M, C, rpb, sum, sq, fin);
+    SUNB_CHECK_CUDA(sunb_launch(&colstats_kernel, dim3((int)blocks), dim3(256), 2 * 2048 * sizeof(float), ST(stream), 
+        reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<const bf16*>(u), ldu, (int)M, C, rpb, sum, sq, fin));
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
 }
@@ -572,8 +606,8 @@ static int launch_colstats_fin(const void* x, int ldx, const void* u, int ldu, l
     int rpb = lanes * 16;
     long blocks = (M + rpb - 1) / rpb;
     if (blocks > 148L * 8) { rpb = (int)((M + 148L * 8 - 1) / (148L * 8)); rpb = (rpb + lanes - 1) / lanes * lanes; blocks = (M + rpb - 1) / rpb; }
-    colstats_kernel<<<(int)blocks, 256, 2 * 2048 * sizeof(float), ST(stream)>>>(
-        reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<const bf16*>(u), ldu, (int)M, C, rpb, sum, sq, fin);
+    SUNB_CHECK_CUDA(sunb_launch(&colstats_kernel, dim3((int)blocks), dim3(256), 2 * 2048 * sizeof(float), ST(stream), 
+        reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<const bf16*>(u), ldu, (int)M, C, rpb, sum, sq, fin));
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
 }
@@ -609,9 +643,9 @@ int sunb_bn_finalize(const float* sum, const float* sq, float count, const float
                      float* rvar, int64_t* nbt, float momentum, float eps, int C, float* scale, float* shift, float* mean,
                      float* rstd, void* stream) {
     SUNB_REQUIRE(sum && sq && gamma && beta && scale && shift && mean && rstd && C > 0, "bn_finalize: bad arguments");
-    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(sum, sq, count, gamma, beta, rmean, rvar,
+    SUNB_CHECK_CUDA(sunb_launch(&bn_finalize_kernel, dim3((C + 127) / 128), dim3(128), 0, ST(stream), sum, sq, count, gamma, beta, rmean, rvar,
                                                                  reinterpret_cast<long long*>(nbt), momentum, eps, C,
-                                                                 scale, shift, mean, rstd);
+                                                                 scale, shift, mean, rstd));
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
 }
@@ -619,9 +653,9 @@ int sunb_bn_finalize(const float* sum, const float* sq, float count, const float
 int sunb_bn_apply(const void* x, int ldx, const float* scale, const float* shift, int act, const float* tab, int tab_mod,
                   void* out, int ldo, long M, int C, void* stream) {
     SUNB_REQUIRE(x && out && scale && shift && C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0, "bn_apply: bad arguments");
-    bn_apply_kernel<<<grid_for(M * (C / 8)), 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(x), ldx, scale, shift, act,
+    SUNB_CHECK_CUDA(sunb_launch(&bn_apply_kernel, dim3(grid_for(M * (C / 8))), dim3(256), 0, ST(stream), reinterpret_cast<const bf16*>(x), ldx, scale, shift, act,
                                                                     tab, tab_mod > 0 ? tab_mod : 1,
-                                                                    reinterpret_cast<bf16*>(out), ldo, M, C);
+                                                                    reinterpret_cast<bf16*>(out), ldo, M, C));
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
 }
@@ -629,9 +663,9 @@ int sunb_bn_apply(const void* x, int ldx, const float* scale, const float* shift
 int sunb_stem_tail_forward(const void* c3, const void* idn, const float* s3, const float* t3, const float* sd,
                            const float* td, const float* pos, void* out, int B, void* stream) {
     SUNB_REQUIRE(c3 && idn && out && pos, "stem_tail_forward: bad arguments");
-    stem_tail_fwd_kernel<<<grid_for((long)B * 400 * 16), 256, 0, ST(stream)>>>(
+    SUNB_CHECK_CUDA(sunb_launch(&stem_tail_fwd_kernel, dim3(grid_for((long)B * 400 * 16)), dim3(256), 0, ST(stream), 
         reinterpret_cast<const bf16*>(c3), reinterpret_cast<const bf16*>(idn), s3, t3, sd, td, pos,
-        reinterpret_cast<bf16*>(out), B, 40, 40, 128);
+        reinterpret_cast<bf16*>(out), B, 40, 40, 128));
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
 }
@@ -639,9 +673,9 @@ int sunb_stem_tail_forward(const void* c3, const void* idn, const float* s3, con
 int sunb_stem_tail_backward(const void* c3, const void* idn, const float* s3, const float* t3, const float* sd,
                             const float* td, const void* g, void* dz, int B, void* stream) {
     SUNB_REQUIRE(c3 && idn && g && dz, "stem_tail_backward: bad arguments");
-    stem_tail_bwd_kernel<<<grid_for((long)B * 400 * 16), 256, 0, ST(stream)>>>(
+    SUNB_CHECK_CUDA(sunb_launch(&stem_tail_bwd_kernel, dim3(grid_for((long)B * 400 * 16)), dim3(256), 0, ST(stream), 
         reinterpret_cast<const bf16*>(c3), reinterpret_cast<const bf16*>(idn), s3, t3, sd, td,
-        reinterpret_cast<const bf16*>(g), reinterpret_cast<bf16*>(dz), B, 40, 40, 128);
+        reinterpret_cast<const bf16*>(g), reinterpret_cast<bf16*>(dz), B, 40, 40, 128));
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
 }
@@ -649,7 +683,7 @@ int sunb_stem_tail_backward(const void* c3, const void* idn, const float* s3, co
 int sunb_bn_frozen(const float* gamma, const float* beta, const float* rmean, const float* rvar, float eps, int C,
                    float* scale, float* shift, float* mean, float* rstd, void* stream) {
     SUNB_REQUIRE(gamma && beta && rmean && rvar && scale && shift && mean && rstd && C > 0, "bn_frozen: bad arguments");
-    bn_frozen_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(gamma, beta, rmean, rvar, eps, C, scale, shift, mean, rstd);
+    SUNB_CHECK_CUDA(sunb_launch(&bn_frozen_kernel, dim3((C + 127) / 128), dim3(128), 0, ST(stream), gamma, beta, rmean, rvar, eps, C, scale, shift, mean, rstd));
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
 }
@@ -658,8 +692,8 @@ int sunb_bn_bwd_finalize(const float* sdz, const float* sdzx, float count, const
                          const float* gamma, int C, int frozen, float* a, float* c1, float* c2, float* dgamma, float* dbeta,
                          void* stream) {
     SUNB_REQUIRE(sdz && sdzx && mean && rstd && gamma && a && c1 && c2 && dgamma && dbeta, "bn_bwd_finalize: bad arguments");
-    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(sdz, sdzx, count, mean, rstd, gamma, C, frozen, a, c1, c2,
-                                                                     dgamma, dbeta);
+    SUNB_CHECK_CUDA(sunb_launch(&bn_bwd_finalize_kernel, dim3((C + 127) / 128), dim3(128), 0, ST(stream), sdz, sdzx, count, mean, rstd, gamma, C, frozen, a, c1, c2,
+                                                                     dgamma, dbeta));
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
 }
@@ -667,32 +701,32 @@ int sunb_bn_bwd_finalize(const float* sdz, const float* sdzx, float count, const
 int sunb_bn_bwd_apply(const void* dz, int lddz, const void* x, int ldx, const float* a, const float* c1, const float* c2,
                       const float* mean, const void* res, int ldr, void* out, int ldo, long M, int C, void* stream) {
     SUNB_REQUIRE(dz && x && out && C % 8 == 0, "bn_bwd_apply: bad arguments");
-    bn_bwd_apply_kernel<<<grid_for(M * (C / 8)), 256, 0, ST(stream)>>>(
+    SUNB_CHECK_CUDA(sunb_launch(&bn_bwd_apply_kernel, dim3(grid_for(M * (C / 8))), dim3(256), 0, ST(stream), 
         reinterpret_cast<const bf16*>(dz), lddz, reinterpret_cast<const bf16*>(x), ldx, a, c1, c2, mean,
-        reinterpret_cast<const bf16*>(res), ldr, reinterpret_cast<bf16*>(out), ldo, M, C);
+        reinterpret_cast<const bf16*>(res), ldr, reinterpret_cast<bf16*>(out), ldo, M, C));
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
 }
 
 int sunb_scale_rows(const void* in, const float* rs, int rows_per_img, void* out, long M, int C, void* stream) {
     SUNB_REQUIRE(in && rs && out && C % 8 == 0 && rows_per_img > 0, "scale_rows: bad arguments");
-    scale_rows_kernel<<<grid_for(M * (C / 8)), 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(in), rs, rows_per_img,
-                                                                      reinterpret_cast<bf16*>(out), M, C);
+    SUNB_CHECK_CUDA(sunb_launch(&scale_rows_kernel, dim3(grid_for(M * (C / 8))), dim3(256), 0, ST(stream), reinterpret_cast<const bf16*>(in), rs, rows_per_img,
+                                                                      reinterpret_cast<bf16*>(out), M, C));
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
 }
 
 int sunb_s2d_reorder(const void* in, void* out, int B, int H, int W, int C, int dir, void* stream) {
     SUNB_REQUIRE(in && out && C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "s2d_reorder: bad arguments");
-    s2d_reorder_kernel<<<grid_for((long)B * H * W * (C / 8)), 256, 0, ST(stream)>>>(
-        reinterpret_cast<const bf16*>(in), reinterpret_cast<bf16*>(out), B, H, W, C, dir);
+    SUNB_CHECK_CUDA(sunb_launch(&s2d_reorder_kernel, dim3(grid_for((long)B * H * W * (C / 8))), dim3(256), 0, ST(stream), 
+        reinterpret_cast<const bf16*>(in), reinterpret_cast<bf16*>(out), B, H, W, C, dir));
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
 }
 
 int sunb_batch_sum(const void* g, int B, long n, float* out, void* stream) {
     SUNB_REQUIRE(g && out && B > 0 && n > 0, "batch_sum: bad arguments");
-    batch_sum_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(g), B, n, out);
+    SUNB_CHECK_CUDA(sunb_launch(&batch_sum_kernel, dim3(grid_for(n)), dim3(256), 0, ST(stream), reinterpret_cast<const bf16*>(g), B, n, out));
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
 }
@@ -700,8 +734,8 @@ int sunb_batch_sum(const void* g, int B, long n, float* out, void* stream) {
 int sunb_permute_cast(const float* src, long off, long sa, long sb, long sc, int A, int B, int Cd, int ldd, void* dst,
                       void* stream) {
     SUNB_REQUIRE(src && dst && A > 0 && B > 0 && Cd > 0 && ldd >= Cd, "permute_cast: bad arguments");
-    permute_cast_kernel<<<grid_for((long)A * B * ldd), 256, 0, ST(stream)>>>(src, off, sa, sb, sc, A, B, Cd, ldd,
-                                                                              reinterpret_cast<bf16*>(dst));
+    SUNB_CHECK_CUDA(sunb_launch(&permute_cast_kernel, dim3(grid_for((long)A * B * ldd)), dim3(256), 0, ST(stream), src, off, sa, sb, sc, A, B, Cd, ldd,
+                                                                              reinterpret_cast<bf16*>(dst)));
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
 }
@@ -722,7 +756,7 @@ int sunb_pack_weights(const SunbPackDesc* descs, int n, void* stream) {
             a.prefix[i + 1] = a.prefix[i] + (int)((n_el + PK_CHUNK - 1) / PK_CHUNK);
         }
         const int total = a.prefix[a.n];
-        pack_multi_kernel<<<total < 148 * 16 ? total : 148 * 16, 256, 0, ST(stream)>>>(a);
+        SUNB_CHECK_CUDA(sunb_launch(&pack_multi_kernel, dim3(total < 148 * 16 ? total : 148 * 16), dim3(256), 0, ST(stream), a));
         SUNB_CHECK_CUDA(cudaGetLastError());
     }
     return SUNB_OK;
@@ -730,21 +764,21 @@ int sunb_pack_weights(const SunbPackDesc* descs, int n, void* stream) {
 
 int sunb_grouped_pairs(const float* w, void* dst, int transpose_flip, void* stream) {
     SUNB_REQUIRE(w && dst, "grouped_pairs: bad arguments");
-    grouped_pairs_kernel<<<grid_for(4 * 9 * 64 * 64), 256, 0, ST(stream)>>>(w, reinterpret_cast<bf16*>(dst), transpose_flip);
+    SUNB_CHECK_CUDA(sunb_launch(&grouped_pairs_kernel, dim3(grid_for(4 * 9 * 64 * 64)), dim3(256), 0, ST(stream), w, reinterpret_cast<bf16*>(dst), transpose_flip));
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
 }
 
 int sunb_grouped_wgrad_extract(const float* scratch, float* dw, void* stream) {
     SUNB_REQUIRE(scratch && dw, "grouped_wgrad_extract: bad arguments");
-    grouped_wgrad_extract_kernel<<<grid_for(256 * 32 * 9), 256, 0, ST(stream)>>>(scratch, dw);
+    SUNB_CHECK_CUDA(sunb_launch(&grouped_wgrad_extract_kernel, dim3(grid_for(256 * 32 * 9)), dim3(256), 0, ST(stream), scratch, dw));
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
 }
 
 int sunb_pool_backward(const float* dpooled, const float* ddense, void* dy, int B, int T, int C, void* stream) {
     SUNB_REQUIRE(dy && (dpooled || ddense), "pool_backward: bad arguments");
-    pool_bwd_kernel<<<grid_for((long)B * T * C), 256, 0, ST(stream)>>>(dpooled, ddense, reinterpret_cast<bf16*>(dy), B, T, C);
+    SUNB_CHECK_CUDA(sunb_launch(&pool_bwd_kernel, dim3(grid_for((long)B * T * C)), dim3(256), 0, ST(stream), dpooled, ddense, reinterpret_cast<bf16*>(dy), B, T, C));
     SUNB_CHECK_CUDA(cudaGetLastError());
     return SUNB_OK;
 }
@@ -755,7 +789,7 @@ int sunb_stem_wgrad(const float* x, const void* da1, const void* didn, float* dw
     SUNB_REQUIRE((((size_t)scratch) & 31) == 0, "stem_wgrad: scratch must be 32-byte aligned");
     const int P = B * 1600;
     bf16* patches = reinterpret_cast<bf16*>(scratch);
-    stem_im2col_kernel<<<grid_for(P), 256, 0, ST(stream)>>>(x, patches, P);
+    SUNB_CHECK_CUDA(sunb_launch(&stem_im2col_kernel, dim3(grid_for(P)), dim3(256), 0, ST(stream), x, patches, P));
     SUNB_CHECK_CUDA(cudaGetLastError());
     WgradParams p;
     memset(&p, 0, sizeof(p));

@@ -169,6 +169,8 @@ __global__ void __launch_bounds__(NUM_THREADS) wgrad_tc_kernel(const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();      // the next kernel may start its set-up; nothing above touched global memory
+    pdl_wait();         // the previous kernel has completed, its writes are visible
 
     if (nk > 0) {
         if (warp == 0) {
@@ -315,8 +317,7 @@ int launch_w(const WgradParams& p, const CUtensorMap& tmY, const CUtensorMap& tm
     SUNB_TRY(sunb_opt_in_smem(reinterpret_cast<const void*>(&wgrad_tc_kernel<BN>), L::TOTAL));
     const int n_tiles = (p.Nb + BN - 1) / BN, m_tiles = (p.Ma + BM - 1) / BM;
     dim3 grid(n_tiles * m_tiles, p.taps * p.groups, p.ksplit);
-    wgrad_tc_kernel<BN><<<grid, NUM_THREADS, L::TOTAL, stream>>>(tmY, tmX, p, n_tiles);
-    SUNB_CHECK_CUDA(cudaGetLastError());
+    SUNB_CHECK_CUDA(sunb_launch(&wgrad_tc_kernel<BN>, grid, dim3(NUM_THREADS), L::TOTAL, stream, tmY, tmX, p, n_tiles));
     return SUNB_OK;
 }
 

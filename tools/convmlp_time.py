@@ -44,3 +44,6 @@ gconv = lambda: N.check(lib.sunb_gconv3x3(h1.data_ptr(), 256, wg.data_ptr(), h2.
 conv3 = lambda: N.check(lib.sunb_gemm(C.byref(d3), 0, st), "conv3")
 tail = lambda: N.check(lib.sunb_convmlp_tail(h1.data_ptr(), blob.data_ptr(), x.data_ptr(), xo.data_ptr(), B, 0, st), "tail")
 print(f"B={B}: conv1 {t(conv1):.1f} us, gconv {t(gconv):.1f} us, conv3 {t(conv3):.1f} us, fused tail {t(tail):.1f} us")
+blk = lambda: (conv1(), tail())
+tb = t(blk)
+print(f"B={B}: conv1 + tail back to back {tb:.1f} us = {tb * 2500 / B:.1f} us per 2500 images")
