@@ -465,16 +465,20 @@ __global__ void permute_cast_kernel(const float* __restrict__ src, long off, lon
 // Every bf16 operand layout of the training step (forward + dgrad copies of all GEMM / conv weights) in ONE launch.
 // Each entry is a 4-D permute + cast  dst[a][b][c][d] = src[off + a*sa + b*sb + c*sc + d*sd]  (last dim padded to ldd);
 // the table travels by value in the kernel arguments (graph-capturable, nothing uploaded at step time).
-constexpr int PK_MAX = 96, PK_CHUNK = 2048;
+constexpr int PK_MAX = 96, PK_T2 = 32, PK_T3 = 64;     // work unit: a 32 (dim 2) x 64 (dim 3) tile through shared memory
 struct PackArgs {
     SunbPackDesc d[PK_MAX];
-    int prefix[PK_MAX + 1];
+    int prefix[PK_MAX + 1];                             // prefix sums of the per-entry tile counts
     int n;
 };
+// Reads run along whichever of the two inner dimensions is denser in the SOURCE (a `.d` operand is the transpose of the
+// master weight: its dim 2 is the contiguous one), writes always along dim 3 of the destination as bf16 pairs.
 __global__ void __launch_bounds__(256) pack_multi_kernel(const __grid_constant__ PackArgs args) {
     pdl_trigger();
     pdl_wait();
+    __shared__ float tile[PK_T2][PK_T3 + 1];
     const int total = args.prefix[args.n];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int c = blockIdx.x; c < total; c += gridDim.x) {
         int lo = 0, hi = args.n;
         while (hi - lo > 1) {
@@ -484,18 +488,48 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const __grid_constant__
         const SunbPackDesc& D = args.d[lo];
         const float* __restrict__ src = reinterpret_cast<const float*>(D.src) + D.off;
         bf16* __restrict__ dst = reinterpret_cast<bf16*>(D.dst);
-        const int n_el = D.dims[0] * D.dims[1] * D.dims[2] * D.ldd;
-        const int base = (c - args.prefix[lo]) * PK_CHUNK;
-        const int end = min(base + PK_CHUNK, n_el);
-        for (int i = base + threadIdx.x; i < end; i += 256) {
-            const int d3 = i % D.ldd;
-            int r = i / D.ldd;
-            const int d2 = r % D.dims[2];
-            r /= D.dims[2];
-            const int d1 = r % D.dims[1], d0 = r / D.dims[1];
-            dst[i] = __float2bfloat16(d3 < D.dims[3] && (D.valid2 == 0 || d2 < D.valid2)
-                ? src[(long)d0 * D.strides[0] + (long)d1 * D.strides[1] + (long)d2 * D.strides[2] + (long)d3 * D.strides[3]] : 0.f);
+        const int D2 = D.dims[2], D3 = D.dims[3], ldd = D.ldd;
+        const int v2 = D.valid2 ? D.valid2 : D2;
+        const int t3n = (ldd + PK_T3 - 1) / PK_T3, t2n = (D2 + PK_T2 - 1) / PK_T2;
+        int t = c - args.prefix[lo];
+        const int t3 = t % t3n; t /= t3n;
+        const int t2 = t % t2n; t /= t2n;
+        const int d1 = t % D.dims[1], d0 = t / D.dims[1];
+        const long sbase = (long)d0 * D.strides[0] + (long)d1 * D.strides[1];
+        const long s2 = D.strides[2], s3 = D.strides[3];
+        const int r0 = t2 * PK_T2, c0 = t3 * PK_T3;
+        if ((s3 < 0 ? -s3 : s3) <= (s2 < 0 ? -s2 : s2)) {
+            // source denser along dim 3: a warp reads rows of 64
+            for (int r = warp; r < PK_T2; r += 8) {
+                const int d2 = r0 + r;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int d3 = c0 + lane + 32 * h;
+                    tile[r][lane + 32 * h] = (d2 < v2 && d3 < D3) ? src[sbase + d2 * s2 + d3 * s3] : 0.f;
+                }
+            }
+        } else {
+            // source denser along dim 2 (transposed operand): a warp reads columns of 32
+            for (int cc = warp; cc < PK_T3; cc += 8) {
+                const int d3 = c0 + cc, d2 = r0 + lane;
+                tile[lane][cc] = (d2 < v2 && d3 < D3) ? src[sbase + d2 * s2 + d3 * s3] : 0.f;
+            }
         }
+        __syncthreads();
+        const size_t obase = ((size_t)(d0 * D.dims[1] + d1) * D2) * ldd;
+        for (int r = warp; r < PK_T2; r += 8) {
+            const int d2 = r0 + r, d3 = c0 + 2 * lane;
+            if (d2 < D2 && d3 < ldd) {
+                bf16* o = dst + obase + (size_t)d2 * ldd + d3;
+                if (d3 + 1 < ldd && ((reinterpret_cast<size_t>(o) & 3) == 0))
+                    *reinterpret_cast<__nv_bfloat162*>(o) = __floats2bfloat162_rn(tile[r][2 * lane], tile[r][2 * lane + 1]);
+                else {
+                    o[0] = __float2bfloat16(tile[r][2 * lane]);
+                    if (d3 + 1 < ldd) o[1] = __float2bfloat16(tile[r][2 * lane + 1]);
+                }
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -582,15 +616,30 @@ inline int grid_for(long total, int threads = 256) {
 
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
+// rows per block of the column-statistics pass: 16 rows per thread for large tensors (at most 8 blocks per SM), fewer for
+// small ones so that a data-parallel shard's tensors (1.5 - 24 MB) still spread over ~2 blocks per SM with one or two
+// load batches per thread instead of a 16-deep serial walk on a few dozen blocks
+static void colstats_plan(long M, int C, int* rows_per_block, long* blocks) {
+    const int lanes = 256 / (C / 8);
+    const long target = 2L * sunb_num_sms();
+    long rpt = (M + lanes * target - 1) / (lanes * target);
+    rpt = rpt < 2 ? 2 : (rpt > 16 ? 16 : rpt);
+    long rpb = lanes * rpt;
+    long nb = (M + rpb - 1) / rpb;
+    const long cap = 8L * sunb_num_sms();
+    if (nb > cap) { rpb = (M + cap - 1) / cap; rpb = (rpb + lanes - 1) / lanes * lanes; nb = (M + rpb - 1) / rpb; }
+    *rows_per_block = (int)rpb;
+    *blocks = nb;
+}
+
 extern "C" {
 
 int sunb_colstats(const void* x, int ldx, const void* u, int ldu, long M, int C, float* sum, float* sq, void* stream) {
     SUNB_REQUIRE(x && sum && sq && M > 0, "colstats: bad arguments");
     SUNB_REQUIRE(C % 8 == 0 && C / 8 <= 256 && ldx % 8 == 0, "colstats: C must be a multiple of 8 and <= 2048 (got %d)", C);
-    const int lanes = 256 / (C / 8);
-    int rpb = lanes * 16;
-    long blocks = (M + rpb - 1) / rpb;
-    if (blocks > 148L * 8) { rpb = (int)((M + 148L * 8 - 1) / (148L * 8)); rpb = (rpb + lanes - 1) / lanes * lanes; blocks = (M + rpb - 1) / rpb; }
+    int rpb;
+    long blocks;
+    colstats_plan(M, C, &rpb, &blocks);
     BnFin fin;
     memset(&fin, 0, sizeof(fin));
     SUNB_CHECK_CUDA(sunb_launch(&colstats_kernel, dim3((int)blocks), dim3(256), 2 * 2048 * sizeof(float), ST(stream), 
@@ -602,10 +651,9 @@ int sunb_colstats(const void* x, int ldx, const void* u, int ldu, long M, int C,
 static int launch_colstats_fin(const void* x, int ldx, const void* u, int ldu, long M, int C, float* sum, float* sq,
                                const BnFin& fin, void* stream) {
     SUNB_REQUIRE(C % 8 == 0 && C / 8 <= 256 && ldx % 8 == 0, "bn_stats: C must be a multiple of 8 and <= 2048 (got %d)", C);
-    const int lanes = 256 / (C / 8);
-    int rpb = lanes * 16;
-    long blocks = (M + rpb - 1) / rpb;
-    if (blocks > 148L * 8) { rpb = (int)((M + 148L * 8 - 1) / (148L * 8)); rpb = (rpb + lanes - 1) / lanes * lanes; blocks = (M + rpb - 1) / rpb; }
+    int rpb;
+    long blocks;
+    colstats_plan(M, C, &rpb, &blocks);
     SUNB_CHECK_CUDA(sunb_launch(&colstats_kernel, dim3((int)blocks), dim3(256), 2 * 2048 * sizeof(float), ST(stream), 
         reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<const bf16*>(u), ldu, (int)M, C, rpb, sum, sq, fin));
     SUNB_CHECK_CUDA(cudaGetLastError());
@@ -751,9 +799,10 @@ int sunb_pack_weights(const SunbPackDesc* descs, int n, void* stream) {
             const SunbPackDesc& D = a.d[i];
             SUNB_REQUIRE(D.src && D.dst && D.dims[0] > 0 && D.dims[1] > 0 && D.dims[2] > 0 && D.dims[3] > 0 && D.ldd >= D.dims[3],
                          "pack_weights: bad entry %d", t0 + i);
-            const long n_el = (long)D.dims[0] * D.dims[1] * D.dims[2] * D.ldd;
-            SUNB_REQUIRE(n_el < (1L << 30), "pack_weights: entry %d too large", t0 + i);
-            a.prefix[i + 1] = a.prefix[i] + (int)((n_el + PK_CHUNK - 1) / PK_CHUNK);
+            const long tiles = (long)D.dims[0] * D.dims[1] * ((D.dims[2] + PK_T2 - 1) / PK_T2) * ((D.ldd + PK_T3 - 1) / PK_T3);
+            SUNB_REQUIRE((long)D.dims[0] * D.dims[1] * D.dims[2] * D.ldd < (1L << 30) && a.prefix[i] + tiles < (1L << 30),
+                         "pack_weights: entry %d too large", t0 + i);
+            a.prefix[i + 1] = a.prefix[i] + (int)tiles;
         }
         const int total = a.prefix[a.n];
         SUNB_CHECK_CUDA(sunb_launch(&pack_multi_kernel, dim3(total < 148 * 16 ? total : 148 * 16), dim3(256), 0, ST(stream), a));
