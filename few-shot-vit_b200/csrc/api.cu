@@ -42,6 +42,16 @@ extern "C" int sunb_gconv3x3(const void* x, int ldx, const void* wg, void* y, in
                              int ldaux, int B, int act, int dact, void* stream);
 
 static thread_local char g_err[512] = "";
+static thread_local bool g_pdl = true;
+bool sunb_pdl_allowed() { return g_pdl; }
+void sunb_pdl_allow(bool on) { g_pdl = on; }
+namespace {
+struct PdlScope {                       // restores the calling thread's setting on every return path
+    bool prev;
+    explicit PdlScope(bool on) : prev(g_pdl) { g_pdl = on; }
+    ~PdlScope() { g_pdl = prev; }
+};
+}  // namespace
 
 void sunb_set_error(const char* fmt, ...) {
     va_list ap;
@@ -193,6 +203,7 @@ int sunb_encoder_forward(const SunbEncoderWeights* w, const float* x, int B, voi
     }
     SUNB_REQUIRE((((size_t)workspace) & 255) == 0, "encoder_forward: workspace must be 256-byte aligned");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    PdlScope pdl(B <= SUNB_PDL_MAX_IMAGES);       // long kernels gain nothing from overlapped set-up (common.cuh)
     SunbEncoderTaps none;
     memset(&none, 0, sizeof(none));
     const SunbEncoderTaps& tp = taps ? *taps : none;

@@ -374,7 +374,13 @@ inline int sunb_launch_gemm(const GemmParams& p, cudaStream_t stream) { return s
 //     all CTAs of a grid are resident (or done) when its trigger fires, a waiting successor never holds a resource an
 //     unscheduled predecessor CTA needs.
 // In a kernel launched without the attribute both instructions are no-ops.  -DSUNB_NO_PDL builds without the attribute.
+// The overlap pays when kernels are short.  The eval engine at throughput batch sizes runs 40 kernels of 50-1000 us each,
+// where early-resident successors measured 1-2 % SLOWER, so sunb_encoder_forward suspends the attribute above
+// SUNB_PDL_MAX_IMAGES images for the duration of the call (a scheduling hint scoped to the calling thread, not a kernel switch).
 // ------------------------------------------------------------------------------------------------
+constexpr int SUNB_PDL_MAX_IMAGES = 640;
+bool sunb_pdl_allowed();                 // api.cu: false while a large-batch encoder forward is being enqueued on this thread
+void sunb_pdl_allow(bool on);
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
@@ -389,8 +395,10 @@ inline cudaError_t sunb_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, 
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
+    if (sunb_pdl_allowed()) {
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+    }
 #endif
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }

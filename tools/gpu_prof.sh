@@ -9,3 +9,4 @@ SUNB_BENCH_PROFILE=train SUNB_TRAIN_GRAPH=0 timeout 900 ncu --metrics gpu__time_
 SUNB_BENCH_PROFILE=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_slab -s 3 -c 1 -f -o gpurun_out/prof_conv3 python bench.py --steps 1 --warmup 1 > gpurun_out/prof_full.log 2>&1; echo "ncu full exit $?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:convmlp_tail -s 2 -c 1 -f -o gpurun_out/prof_tail python tools/tail_one.py > /dev/null 2>&1; echo "ncu tail exit $?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:attention_tc -s 2 -c 1 -f -o gpurun_out/prof_att100 python tools/att_one.py 100 42 48 > /dev/null 2>&1; echo "ncu att exit $?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:attention_bwd_tc -s 2 -c 1 -f -o gpurun_out/prof_attb100 python tools/attb_time.py 480 > /dev/null 2>&1; echo "ncu attb exit $?"

@@ -61,7 +61,7 @@ def main():
         for k, (n, t) in sorted(by.items(), key=lambda kv: -kv[1][1]):
             f.write(f"| `{k}` | {n} | {t / 1000:.1f} | {100 * t / tot:.1f}% |\n")
     rows = load("gpurun_out/launches_train.csv")
-    idx = [i for i, r in enumerate(rows) if "stem_in" in r[1]]
+    idx = [i for i, r in enumerate(rows) if "pack_multi" in r[1]]          # first launch of a step: the weight-operand pack
     seg = rows[idx[-1]:]
     tot = sum(r[3] for r in seg)
     by = collections.defaultdict(lambda: [0, 0.0])
@@ -76,7 +76,7 @@ def main():
         for k, (n, t) in sorted(by.items(), key=lambda kv: -kv[1][1]):
             f.write(f"| `{k}` | {n} | {t / 1000:.1f} | {100 * t / tot:.1f}% |\n")
         f.write(f"\n{len(seg)} launches, {tot / 1e6:.2f} ms = {3 * 2030.6e6 * 480 / (tot * 1e-9) / 1e12:.0f} TFLOP/s (3x forward FLOPs).  "
-                "`at::` kernels are torch plumbing (gradient-buffer zero fill, gradient layout permutes, foreach SGD).\n")
+                "`at::` kernels are torch plumbing (zero fill of the gradient buffer / accumulator arena, gradient layout permutes).\n")
     print("wrote", tag)
 
 
