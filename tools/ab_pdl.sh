@@ -1,5 +1,5 @@
 #!/bin/bash
-# A/B of programmatic dependent launch: product library vs a -DSUNB_NO_PDL build (tools/_ab/libsunb200_nopdl.so)
+# A/B of programmatic dependent launch: product library vs a -DSUNB_NO_PDL build (tools/build_variants.sh -> tools/_ab/libsunb200_nopdl.so)
 for lib in "" "tools/_ab/libsunb200_nopdl.so"; do
   echo "=== lib: ${lib:-product}"
   export SUNB200_LIB=$lib; [ -z "$lib" ] && unset SUNB200_LIB
