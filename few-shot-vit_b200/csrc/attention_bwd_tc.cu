@@ -347,21 +347,21 @@ int launch_bwd_tc(const bf16* qkv, const bf16* dout, bf16* dqkv, int B, int head
 
 }  // namespace
 
-// 1 when the tcgen05 backward covers this problem (padded head layouts of both engines), else the caller keeps the warp-MMA
-// kernel of attention_bwd.cu (the reference's packed layout).
-int sunb_attention_bwd_tc_supported(const bf16* qkv, const bf16* dout, const bf16* dqkv, int S, int d, int ds, int ld_qkv,
-                                    int ld_out) {
-    if ((((size_t)qkv) & 15) || (((size_t)dout) & 15) || (((size_t)dqkv) & 31) || (ld_qkv % 16) || (ld_out % 8)) return 0;
-    if (S == 100 && ds == 48 && d <= 48) return 1;
-    if (S == 25 && ds == 96 && d <= 96 && d > 48) return 1;
-    return 0;
-}
-
-int sunb_launch_attention_bwd_tc(const bf16* qkv, const bf16* dout, bf16* dqkv, int B, int S, int d, int ds, int heads,
-                                 int ld_qkv, int ld_out, cudaStream_t stream) {
+extern "C" int sunb_attention_backward(const void* qkv_, const void* dout_, void* dqkv_, int B, int S, int d, int d_stride,
+                                       int heads, int ld_qkv, int ld_out, void* stream) {
+    SUNB_REQUIRE(qkv_ && dout_ && dqkv_ && B > 0 && heads > 0 && d > 0 && d_stride >= d, "attention_backward: bad arguments");
+    SUNB_REQUIRE(ld_qkv >= 3 * heads * d_stride && ld_out >= heads * d_stride, "attention_backward: row strides too small");
+    const bf16* qkv = reinterpret_cast<const bf16*>(qkv_);
+    const bf16* dout = reinterpret_cast<const bf16*>(dout_);
+    bf16* dqkv = reinterpret_cast<bf16*>(dqkv_);
+    const bool aligned = !((((size_t)qkv) & 15) || (((size_t)dout) & 15) || (((size_t)dqkv) & 31) || (ld_qkv % 16) || (ld_out % 8));
+    const bool shape = (S == 100 && d_stride == 48) || (S == 25 && d_stride == 96 && d > 48);
+    SUNB_REQUIRE(aligned && shape,
+                 "attention_backward: unsupported problem S=%d d=%d d_stride=%d ld_qkv=%d ld_out=%d (supported: S=100 with d_stride 48, "
+                 "S=25 with d_stride 96; 16-byte aligned inputs, 32-byte aligned dqkv, ld_qkv %% 16 == 0, ld_out %% 8 == 0)",
+                 S, d, d_stride, ld_qkv, ld_out);
     const float scale = 1.0f / sqrtf((float)d);
-    if (S == 100 && ds == 48) return launch_bwd_tc<BCfg<100, 1, 112, 1, 2>>(qkv, dout, dqkv, B, heads, ld_qkv, ld_out, scale, stream);
-    if (S == 25 && ds == 96) return launch_bwd_tc<BCfg<25, 5, 128, 2, 1>>(qkv, dout, dqkv, B, heads, ld_qkv, ld_out, scale, stream);
-    sunb_set_error("attention_bwd_tc: unsupported shape S=%d ds=%d", S, ds);
-    return SUNB_ERR_ARG;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (S == 100) return launch_bwd_tc<BCfg<100, 1, 112, 1, 2>>(qkv, dout, dqkv, B, heads, ld_qkv, ld_out, scale, st);
+    return launch_bwd_tc<BCfg<25, 5, 128, 2, 1>>(qkv, dout, dqkv, B, heads, ld_qkv, ld_out, scale, st);
 }

@@ -1,5 +1,5 @@
-// Multi-head self-attention core on tcgen05 / TMEM / TMA (reference: test_phase/models/visformer.py:183-190) for the eval
-// engine's padded head layout (head stride ds = 48 for d = 42, ds = 96 for d = 85; pad channels are exact zeros).
+// Multi-head self-attention core on tcgen05 / TMEM / TMA (reference: test_phase/models/visformer.py:183-190) for the
+// engines' padded head layout (head stride ds = 48 for d = 42, ds = 96 for d = 85; pad channels are exact zeros).
 //   qkv : bf16 [B*S, ld_qkv], channel c = x*(heads*ds) + y*ds + z   (x in {q,k,v}, y head, z < ds)
 //   out : bf16 [B*S, ld_out], channel y*ds + z          P = softmax(q k^T * d^-0.5), O = P v
 //
@@ -334,20 +334,25 @@ int launch_tc(const bf16* qkv, bf16* out, int B, int heads, int ld_qkv, int ld_o
 
 }  // namespace
 
-// 1 when the tcgen05 kernel covers this problem (the eval engine's padded head layouts), else the caller keeps the warp-MMA
-// kernel of attention.cu (the training path's packed layout).
-int sunb_attention_tc_supported(const bf16* qkv, const bf16* out, int S, int d, int ds, int ld_qkv, int ld_out) {
+// The product serves the padded head layouts of the two engines (head stride 48 for d = 42 at S = 100, 96 for d = 85 at S = 25);
+// the reference's packed layout (head stride == d: segments not 16-byte aligned, no TMA box) is only implemented by the
+// warp-MMA cross-check kernel of the test library.
+static int attention_tc_supported(const bf16* qkv, const bf16* out, int S, int d, int ds, int ld_qkv, int ld_out) {
     if ((((size_t)qkv) & 15) || (((size_t)out) & 31) || (ld_qkv % 8) || (ld_out % 16)) return 0;
     if (S == 100 && ds == 48 && d <= 48) return 1;
     if (S == 25 && ds == 96 && d <= 96 && d > 48) return 1;
     return 0;
 }
 
-int sunb_launch_attention_tc(const bf16* qkv, bf16* out, int B, int S, int d, int ds, int heads, int ld_qkv, int ld_out,
-                             cudaStream_t stream) {
+int sunb_launch_attention(const bf16* qkv, bf16* out, int B, int S, int d, int ds, int heads, int ld_qkv, int ld_out,
+                          cudaStream_t stream) {
+    SUNB_REQUIRE(B > 0 && heads > 0, "attention: empty problem");
+    SUNB_REQUIRE(ds >= d && ld_qkv >= 3 * heads * ds && ld_out >= heads * ds, "attention: head stride %d / row strides too small", ds);
+    SUNB_REQUIRE(attention_tc_supported(qkv, out, S, d, ds, ld_qkv, ld_out),
+                 "attention: unsupported problem S=%d d=%d d_stride=%d ld_qkv=%d ld_out=%d (supported: S=100 with d_stride 48, S=25 with "
+                 "d_stride 96; qkv 16-byte aligned with ld_qkv %% 8 == 0, out 32-byte aligned with ld_out %% 16 == 0)",
+                 S, d, ds, ld_qkv, ld_out);
     const float scale = 1.0f / sqrtf((float)d);
-    if (S == 100 && ds == 48) return launch_tc<ACfg<100, 1, 112, 1, 3, 5, 2>>(qkv, out, B, heads, ld_qkv, ld_out, scale, stream);
-    if (S == 25 && ds == 96) return launch_tc<ACfg<25, 5, 128, 2, 2, 2, 1>>(qkv, out, B, heads, ld_qkv, ld_out, scale, stream);
-    sunb_set_error("attention_tc: unsupported shape S=%d ds=%d", S, ds);
-    return SUNB_ERR_ARG;
+    if (S == 100) return launch_tc<ACfg<100, 1, 112, 1, 3, 5, 2>>(qkv, out, B, heads, ld_qkv, ld_out, scale, stream);
+    return launch_tc<ACfg<25, 5, 128, 2, 2, 2, 1>>(qkv, out, B, heads, ld_qkv, ld_out, scale, stream);
 }

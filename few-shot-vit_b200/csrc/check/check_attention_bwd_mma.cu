@@ -1,4 +1,6 @@
-// Backward of the attention core (forward: attention.cu; reference: autograd through visformer.py:183-190).
+// TEST-ONLY warp-MMA cross-check of attention_bwd_tc.cu (tests/native/libsunb200_check.so): never linked into libsunb200.so.
+// Backward of the attention core on the reference's PACKED head layout (forward: check_attention_mma.cu; reference: autograd
+// through visformer.py:183-190).
 //   inputs : qkv bf16 [B*S, ld_qkv] (saved forward input), dout bf16 [B*S, ld_out] (gradient of the head-concatenated output)
 //   output : dqkv bf16 [B*S, ld_qkv], same channel order (qkv, head, d)
 // Per (image, head) the whole problem lives in shared memory (zero padded to MMA shapes) and is processed in two phases,
@@ -8,7 +10,7 @@
 //   B (warp owns 16 key rows)  : S^T = K Q^T -> P^T from the stored row statistics, dP^T = V dO^T,
 //                                dV = P^T dO, dK = dS^T Q
 // Probabilities / dS are rounded to bf16 only as MMA operands; statistics and accumulators stay fp32.
-#include "common.cuh"
+#include "../common.cuh"
 
 #ifndef SUNB_ATTB_CTAS
 #define SUNB_ATTB_CTAS 2
@@ -236,7 +238,7 @@ template <int S_PAD, int D_PAD, int PAIRS>
 int launch_bwd(const bf16* qkv, const bf16* dout, bf16* dqkv, int n_pairs, int S, int d, int heads, int ld_qkv, int ld_out,
                cudaStream_t stream) {
     using Cfg = BwdCfg<S_PAD, D_PAD, PAIRS>;
-    SUNB_TRY(sunb_opt_in_smem(reinterpret_cast<const void*>(&attention_bwd_mma_kernel<S_PAD, D_PAD, PAIRS>), (int)Cfg::SMEM));
+    SUNB_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_mma_kernel<S_PAD, D_PAD, PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     const int blocks = (n_pairs + PAIRS - 1) / PAIRS;
     attention_bwd_mma_kernel<S_PAD, D_PAD, PAIRS><<<blocks, Cfg::THREADS, Cfg::SMEM, stream>>>(
         qkv, dout, dqkv, n_pairs, S, d, heads, ld_qkv, ld_out, 1.0f / sqrtf((float)d));
@@ -246,29 +248,19 @@ int launch_bwd(const bf16* qkv, const bf16* dout, bf16* dqkv, int n_pairs, int S
 
 }  // namespace
 
-int sunb_attention_bwd_tc_supported(const bf16* qkv, const bf16* dout, const bf16* dqkv, int S, int d, int ds, int ld_qkv,
-                                    int ld_out);
-int sunb_launch_attention_bwd_tc(const bf16* qkv, const bf16* dout, bf16* dqkv, int B, int S, int d, int ds, int heads,
-                                 int ld_qkv, int ld_out, cudaStream_t stream);
-
-extern "C" int sunb_attention_backward(const void* qkv, const void* dout, void* dqkv, int B, int S, int d, int d_stride,
-                                       int heads, int ld_qkv, int ld_out, void* stream) {
-    SUNB_REQUIRE(qkv && dout && dqkv && B > 0 && heads > 0 && d > 0 && d_stride >= d, "attention_backward: bad arguments");
-    SUNB_REQUIRE(ld_qkv >= 3 * heads * d_stride && ld_out >= heads * d_stride, "attention_backward: row strides too small");
+// TEST-ONLY cross-check of the tcgen05 attention backward: the reference's PACKED head layout (head stride == d)
+extern "C" int sunb_check_attention_backward(const void* qkv, const void* dout, void* dqkv, int B, int S, int d, int heads,
+                                             int ld_qkv, int ld_out, void* stream) {
+    SUNB_REQUIRE(qkv && dout && dqkv && B > 0 && heads > 0 && d > 0, "check_attention_backward: bad arguments");
     const bf16* q = reinterpret_cast<const bf16*>(qkv);
     const bf16* o = reinterpret_cast<const bf16*>(dout);
     bf16* dq = reinterpret_cast<bf16*>(dqkv);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (d_stride != d) {                                    // padded heads: the tcgen05 kernel (attention_bwd_tc.cu)
-        SUNB_REQUIRE(sunb_attention_bwd_tc_supported(q, o, dq, S, d, d_stride, ld_qkv, ld_out),
-                     "attention_backward: padded layout S=%d d=%d d_stride=%d is not supported", S, d, d_stride);
-        return sunb_launch_attention_bwd_tc(q, o, dq, B, S, d, d_stride, heads, ld_qkv, ld_out, st);
-    }
     const int n_pairs = B * heads;
     if (S <= 32 && d <= 96 && d > 48) return launch_bwd<32, 96, 2>(q, o, dq, n_pairs, S, d, heads, ld_qkv, ld_out, st);
     if (S <= 32 && d <= 48) return launch_bwd<32, 48, 2>(q, o, dq, n_pairs, S, d, heads, ld_qkv, ld_out, st);
     if (S <= 112 && d <= 48) return launch_bwd<112, 48, 1>(q, o, dq, n_pairs, S, d, heads, ld_qkv, ld_out, st);
     if (S <= 112 && d <= 96) return launch_bwd<112, 96, 1>(q, o, dq, n_pairs, S, d, heads, ld_qkv, ld_out, st);
-    sunb_set_error("attention_backward: unsupported shape S=%d d=%d (supported: S <= 112, d <= 96)", S, d);
+    sunb_set_error("check_attention_backward: unsupported shape S=%d d=%d (supported: S <= 112, d <= 96)", S, d);
     return SUNB_ERR_ARG;
 }

@@ -9,9 +9,11 @@
 // shared memory (zero-padded to MMA shapes: S -> 112 / 32 keys, d 42 -> 48, 85 -> 96); each warp owns 16 query rows,
 // computes the full score row block with mma.sync.m16n8k16 (bf16 in, fp32 accumulate), does the softmax on the
 // accumulator registers (row max / sum via quad shuffles, exp2 with the scale folded in) and feeds the probabilities
-// straight back as the A operand of the P.V MMAs.  This kernel serves the TRAINING path's packed head layout (ds == d);
-// the eval engine's padded layout runs on the tcgen05 kernel in attention_tc.cu.
-#include "common.cuh"
+// straight back as the A operand of the P.V MMAs.
+// TEST-ONLY warp-MMA cross-check of attention_tc.cu (tests/native/libsunb200_check.so): never linked into libsunb200.so.
+// It was round 1's product kernel; both engines run the tcgen05 kernel on the padded layout now, and this one also covers
+// the reference's packed layout (ds == d), which the product rejects.
+#include "../common.cuh"
 
 #ifndef SUNB_ATT_CTAS
 #define SUNB_ATT_CTAS 3
@@ -234,7 +236,7 @@ template <int S_PAD, int D_PAD, int PAIRS>
 int launch_cfg(const bf16* qkv, bf16* out, int n_pairs, int S, int d, int ds, int heads, int ld_qkv, int ld_out, float scale,
                cudaStream_t stream) {
     using Cfg = AttnCfg<S_PAD, D_PAD, PAIRS>;
-    SUNB_TRY(sunb_opt_in_smem(reinterpret_cast<const void*>(&attention_mma_kernel<S_PAD, D_PAD, PAIRS>), (int)Cfg::SMEM));
+    SUNB_CHECK_CUDA(cudaFuncSetAttribute(attention_mma_kernel<S_PAD, D_PAD, PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     const int blocks = (n_pairs + PAIRS - 1) / PAIRS;
     attention_mma_kernel<S_PAD, D_PAD, PAIRS><<<blocks, Cfg::THREADS, Cfg::SMEM, stream>>>(
         qkv, out, n_pairs, S, d, ds, heads, ld_qkv, ld_out, scale * 1.4426950408889634f);
@@ -244,24 +246,20 @@ int launch_cfg(const bf16* qkv, bf16* out, int n_pairs, int S, int d, int ds, in
 
 }  // namespace
 
-int sunb_attention_tc_supported(const bf16* qkv, const bf16* out, int S, int d, int ds, int ld_qkv, int ld_out);   // attention_tc.cu
-int sunb_launch_attention_tc(const bf16* qkv, bf16* out, int B, int S, int d, int ds, int heads, int ld_qkv, int ld_out,
-                             cudaStream_t stream);
-
-int sunb_launch_attention(const bf16* qkv, bf16* out, int B, int S, int d, int ds, int heads, int ld_qkv, int ld_out,
-                          cudaStream_t stream) {
-    SUNB_REQUIRE(B > 0 && heads > 0, "attention: empty problem");
-    SUNB_REQUIRE(ds >= d && ld_qkv >= 3 * heads * ds && ld_out >= heads * ds, "attention: head stride %d / row strides too small", ds);
-    // the eval engine's padded head layouts (ds = 48 / 96) run on tcgen05 (attention_tc.cu); the packed layout of the training
-    // path (ds == d = 42 / 85: head segments are not 16-byte aligned, no TMA box) stays on the warp-MMA kernel below
-    if (sunb_attention_tc_supported(qkv, out, S, d, ds, ld_qkv, ld_out))
-        return sunb_launch_attention_tc(qkv, out, B, S, d, ds, heads, ld_qkv, ld_out, stream);
+// TEST-ONLY cross-check of the tcgen05 attention core: any head stride ds >= d (the reference's packed layout ds == d included)
+extern "C" int sunb_check_attention(const void* qkv_, void* out_, int B, int S, int d, int ds, int heads, int ld_qkv, int ld_out,
+                                    void* stream_) {
+    const bf16* qkv = reinterpret_cast<const bf16*>(qkv_);
+    bf16* out = reinterpret_cast<bf16*>(out_);
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    SUNB_REQUIRE(qkv && out && B > 0 && heads > 0, "check_attention: empty problem");
+    SUNB_REQUIRE(ds >= d && ld_qkv >= 3 * heads * ds && ld_out >= heads * ds, "check_attention: head stride %d / row strides too small", ds);
     const float scale = 1.0f / sqrtf((float)d);
     const int n_pairs = B * heads;
     if (S <= 32 && d <= 96 && d > 48) return launch_cfg<32, 96, 4>(qkv, out, n_pairs, S, d, ds, heads, ld_qkv, ld_out, scale, stream);
     if (S <= 32 && d <= 48) return launch_cfg<32, 48, 4>(qkv, out, n_pairs, S, d, ds, heads, ld_qkv, ld_out, scale, stream);
     if (S <= 112 && d <= 48) return launch_cfg<112, 48, 1>(qkv, out, n_pairs, S, d, ds, heads, ld_qkv, ld_out, scale, stream);
     if (S <= 112 && d <= 96) return launch_cfg<112, 96, 1>(qkv, out, n_pairs, S, d, ds, heads, ld_qkv, ld_out, scale, stream);
-    sunb_set_error("attention: unsupported shape S=%d d=%d (supported: S <= 112, d <= 96)", S, d);
+    sunb_set_error("check_attention: unsupported shape S=%d d=%d (supported: S <= 112, d <= 96)", S, d);
     return SUNB_ERR_ARG;
 }

@@ -125,9 +125,11 @@ int sunb_encoder_forward(const SunbEncoderWeights* w, const float* x, int B, voi
                          float* pooled, float* dense, void* dense_bf16, void* pooled_bf16, const SunbEncoderTaps* taps,
                          void* stream);
 
-/* Attention core (visformer.py:183-190).  qkv bf16 [B*S, ld_qkv], channel (x*heads + y)*d_stride + z for x in {q,k,v},
- * head y, z < d; out bf16 [B*S, ld_out], channel y*d_stride + z.  d_stride == d is the reference's packed layout;
- * d_stride > d (a multiple of 8) is the padded layout, whose pad channels must be zero on input and are written as zero. */
+/* Attention core (visformer.py:183-190) on tcgen05.  qkv bf16 [B*S, ld_qkv], channel (x*heads + y)*d_stride + z for x in
+ * {q,k,v}, head y, z < d; out bf16 [B*S, ld_out], channel y*d_stride + z.  Heads are PADDED: d_stride = 48 for S = 100
+ * (d <= 48), d_stride = 96 for S = 25 (48 < d <= 96) -- the two attention stages of visformer_micro_80; pad channels must
+ * be zero on input and are written as zero.  Any other layout (the reference's packed d_stride == d included) returns
+ * SUNB_ERR_ARG: there is one implementation and no fallback. */
 int sunb_attention(const void* qkv, void* out, int B, int S, int d, int d_stride, int heads, int ld_qkv, int ld_out,
                    void* stream);
 
@@ -265,9 +267,8 @@ int sunb_gconv_pack(const float* w, void* dst, int transpose_flip, void* stream)
  * PatchEmbed GEMM).  The 256-channel hidden tensor between the grouped conv and conv3 never leaves the SM. */
 int sunb_convmlp_tail(const void* h1, const void* wblob, const void* resid, void* out, int B, int s2d, void* stream);
 
-/* backward of the attention core (same layouts as sunb_attention: d_stride == d packed -> warp-MMA kernel, padded heads
- * d_stride = 48 (S = 100) / 96 (S = 25) -> tcgen05 kernel; dout: gradient of `out`; dqkv pad channels are written as zero)
- * and of the episode head */
+/* backward of the attention core (same padded layouts as sunb_attention, tcgen05; dout: gradient of `out`; the pad channels
+ * of dqkv are written as zero) and of the episode head */
 int sunb_attention_backward(const void* qkv, const void* dout, void* dqkv, int B, int S, int d, int d_stride, int heads,
                             int ld_qkv, int ld_out, void* stream);
 int sunb_episode_logits_backward(const float* feat_shot, const float* feat_query, const float* dlogits, float* dshot,

@@ -12,7 +12,8 @@ _CHECK = None
 
 
 def check_lib():
-    """tests/native/libsunb200_check.so: SIMT GEMM, CUDA-core stem and warp-MMA grouped conv cross-check kernels (built by
+    """tests/native/libsunb200_check.so: SIMT GEMM, CUDA-core stem, warp-MMA grouped conv and warp-MMA attention (forward /
+    backward, any head stride incl. the reference's packed layout) cross-check kernels (built by
     `make -C few-shot-vit_b200/csrc`; test-only, never linked into the product library)."""
     global _CHECK
     if _CHECK is None:
@@ -23,6 +24,10 @@ def check_lib():
         vp = C.c_void_p
         l.sunb_check_stem_in.restype = C.c_int
         l.sunb_check_stem_in.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp]
+        l.sunb_check_attention.restype = C.c_int
+        l.sunb_check_attention.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+        l.sunb_check_attention_backward.restype = C.c_int
+        l.sunb_check_attention_backward.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
         l.sunb_check_gconv3x3.restype = C.c_int
         l.sunb_check_gconv3x3.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
         _CHECK = l

@@ -8,7 +8,7 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
-from gpu_helpers import run_gemm, act_ref, rel_err, max_err  # noqa: E402
+from gpu_helpers import run_gemm, act_ref, rel_err, max_err, check_lib, check_call  # noqa: E402
 from sunb200 import native as N, engine  # noqa: E402
 import sun_oracle as O  # noqa: E402
 
@@ -111,20 +111,34 @@ def test_grouped_conv_pairs(impl):
 
 
 @pytest.mark.parametrize("S,d,C", [(100, 42, 256), (25, 85, 512)])
-def test_attention(S, d, C):
+def test_attention_checker_packed_layout(S, d, C):
+    """The warp-MMA cross-check kernel (test library) on the reference's packed head layout vs the fp32 formula."""
     B, heads = 5, 6
     inner = heads * d
     ld_qkv = (3 * inner + 7) // 8 * 8
     qkv = torch.full((B * S, ld_qkv), float("nan"), device=DEV, dtype=torch.bfloat16)
     qkv[:, : 3 * inner] = rnd(B * S, 3 * inner, seed=17).bfloat16()
     out = torch.zeros(B * S, C, device=DEV, dtype=torch.bfloat16)
-    N.check(N.lib().sunb_attention(qkv.data_ptr(), out.data_ptr(), B, S, d, d, heads, ld_qkv, C, N.current_stream()), "attention")
+    check_call(check_lib().sunb_check_attention(qkv.data_ptr(), out.data_ptr(), B, S, d, d, heads, ld_qkv, C, N.current_stream()),
+               "check_attention")
     torch.cuda.synchronize()
     t = qkv[:, : 3 * inner].float().reshape(B, S, 3, heads, d).permute(2, 0, 3, 1, 4)
     p = torch.softmax(t[0] @ t[1].transpose(-1, -2) * d ** -0.5, dim=-1)
     ref = (p @ t[2]).permute(0, 2, 1, 3).reshape(B * S, inner)
     assert rel_err(out[:, :inner], ref) < BF16_OUT
     assert (out[:, inner:] == 0).all()
+
+
+def test_attention_rejects_unsupported_layouts():
+    """The product has ONE attention implementation (tcgen05, padded heads); other layouts fail loudly instead of falling back."""
+    B, S, d, heads = 2, 100, 42, 6
+    qkv = torch.zeros(B * S, 768, device=DEV, dtype=torch.bfloat16)
+    out = torch.zeros(B * S, 256, device=DEV, dtype=torch.bfloat16)
+    assert N.lib().sunb_attention(qkv.data_ptr(), out.data_ptr(), B, S, d, d, heads, 768, 256, N.current_stream()) != 0
+    assert b"unsupported" in N.lib().sunb_last_error()
+    assert N.lib().sunb_attention_backward(qkv.data_ptr(), out.data_ptr(), qkv.data_ptr(), B, S, d, d, heads, 768, 256,
+                                           N.current_stream()) != 0
+    assert b"unsupported" in N.lib().sunb_last_error()
 
 
 @pytest.mark.parametrize("B", [7, 301])
@@ -147,6 +161,12 @@ def test_attention_padded_heads(S, d, dp, B):
     o = out.reshape(B, S, heads, dp)
     assert rel_err(o[..., :d], ref) < BF16_OUT
     assert (o[..., d:] == 0).all()                            # pad channels written as exact zeros
+    # second opinion: the warp-MMA checker on the same padded buffers
+    out2 = torch.full_like(out, float("nan"))
+    check_call(check_lib().sunb_check_attention(qkv.data_ptr(), out2.data_ptr(), B, S, d, dp, heads, 3 * heads * dp, heads * dp,
+                                                N.current_stream()), "check_attention")
+    torch.cuda.synchronize()
+    assert rel_err(o[..., :d], out2.reshape(B, S, heads, dp)[..., :d]) < BF16_OUT
 
 
 @pytest.mark.parametrize("metric", ["cos", "dot", "sqr"])

@@ -17,7 +17,7 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
-from gpu_helpers import rel_err, max_err  # noqa: E402
+from gpu_helpers import rel_err, max_err, check_lib, check_call  # noqa: E402
 from sunb200 import native as N, train as T, engine  # noqa: E402
 import sun_oracle as O  # noqa: E402
 
@@ -114,8 +114,9 @@ def test_bn_forward_backward_kernels():
 @pytest.mark.parametrize("S,d,ds,B", [(100, 42, 42, 3), (25, 85, 85, 3)] +
                          [(S, d, ds, B) for S, d, ds in ((100, 42, 48), (25, 85, 96)) for B in (3, 7, 61)])
 def test_attention_backward(S, d, ds, B):
-    """Packed heads (ds == d: warp-MMA kernel) and padded heads (ds = 48 / 96: tcgen05 kernel, five images per tile for
-    S = 25 -- B = 3, 7, 61 leave ragged last tiles) against autograd through the fp32 formula of visformer.py:183-190."""
+    """Padded heads (ds = 48 / 96: the product's tcgen05 kernel, five images per tile for S = 25 -- B = 3, 7, 61 leave ragged
+    last tiles) and the reference's packed layout (ds == d: the warp-MMA cross-check kernel of the test library) against
+    autograd through the fp32 formula of visformer.py:183-190."""
     heads = 6
     inner = heads * ds
     ld3, ldi = (3 * inner + 15) // 16 * 16, (inner + 15) // 16 * 16
@@ -126,8 +127,12 @@ def test_attention_backward(S, d, ds, B):
     dout = torch.zeros(B * S, ldi, device=DEV, dtype=torch.bfloat16)
     dout[:, :inner] = (rnd(B * S, inner, seed=14) * val[:heads].reshape(1, -1)).bfloat16()
     dqkv = torch.full((B * S, ld3), float("nan"), device=DEV, dtype=torch.bfloat16)
-    N.check(N.lib().sunb_attention_backward(qkv.data_ptr(), dout.data_ptr(), dqkv.data_ptr(), B, S, d, ds, heads, ld3, ldi,
-                                            N.current_stream()), "attention_backward")
+    if ds == d:
+        check_call(check_lib().sunb_check_attention_backward(qkv.data_ptr(), dout.data_ptr(), dqkv.data_ptr(), B, S, d, heads,
+                                                             ld3, ldi, N.current_stream()), "check_attention_backward")
+    else:
+        N.check(N.lib().sunb_attention_backward(qkv.data_ptr(), dout.data_ptr(), dqkv.data_ptr(), B, S, d, ds, heads, ld3, ldi,
+                                                N.current_stream()), "attention_backward")
     torch.cuda.synchronize()
     t = qkv[:, : 3 * inner].float().requires_grad_(True)
     u = t.reshape(B, S, 3, heads, ds).permute(2, 0, 3, 1, 4)
