@@ -340,6 +340,33 @@ __device__ __forceinline__ void epilogue_row(const GemmParams& p, int g, int m, 
     }
 }
 
+// Straight-line epilogue for the hottest GELU GEMMs of the eval forward (conv1 of every MLP: folded-BN bias + GELU -> bf16, no
+// residual / DropPath / pre-activation copy / row map).  The general epilogue_row above spends ~100 of its ~415 warp
+// instructions per 32-column chunk on uniform flag tests and parameter reloads (ncu source page of gemm_tc_kernel<256>, 57 %
+// issue utilisation with the ready warps queueing): this one keeps only the math, the loads and the stores.
+__device__ __forceinline__ bool epilogue_is_bias_gelu(const GemmParams& p) {
+    return p.act == ACT_GELU && p.bias && p.bias_mod == 1 && p.out && !p.row_scale && !p.resid && !p.out2 && !p.dact_aux &&
+           !p.out_f32 && p.out_map == MAP_IDENT && p.groups == 1 && (p.N % 32) == 0 && (p.ldc % 16) == 0 &&
+           ((((size_t)p.out) & 31) == 0) && ((((size_t)p.bias) & 15) == 0);
+}
+template <int NC>
+__device__ __forceinline__ void epilogue_row_bias_gelu(const float* __restrict__ bias, bf16* __restrict__ out, int ldc, int M, int m,
+                                                       int col, float* v) {
+    if (m >= M) return;
+    const float4* b4 = reinterpret_cast<const float4*>(bias + col);
+#pragma unroll
+    for (int i = 0; i < NC; i += 4) {
+        const float4 b = __ldg(b4 + i / 4);
+        v[i] = gelu_fast(v[i] + b.x);
+        v[i + 1] = gelu_fast(v[i + 1] + b.y);
+        v[i + 2] = gelu_fast(v[i + 2] + b.z);
+        v[i + 3] = gelu_fast(v[i + 3] + b.w);
+    }
+    bf16* o = out + (size_t)m * ldc + col;
+#pragma unroll
+    for (int i = 0; i < NC; i += 16) store16_bf16(o + i, v + i);
+}
+
 struct WgradParams {
     int P;                    // reduction length: pixel rows (2-D mode) or B*H*W (conv mode)
     int Ma, Nb;               // output rows (= dY channels) and columns (= X channels) per group

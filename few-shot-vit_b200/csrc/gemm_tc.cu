@@ -272,6 +272,10 @@ __global__ void __launch_bounds__(THREADS1, 1) gemm_tc_kernel(const __grid_const
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;      // which share of the column chunks (0 .. CSTEP1-1)
         const int r = q * 32 + lane;
+        const bool bias_gelu = epilogue_is_bias_gelu(p);      // kernel-uniform: straight-line epilogue (common.cuh)
+        const float* const fb_bias = p.bias;
+        bf16* const fb_out = p.out;
+        const int fb_ldc = p.ldc, fb_M = p.M;
         uint32_t lt = 0;
         for (int tile = tile0; tile < total_tiles; tile += tstep, ++lt) {
             const int n0 = (tile % n_tiles) * BN;
@@ -287,7 +291,8 @@ __global__ void __launch_bounds__(THREADS1, 1) gemm_tc_kernel(const __grid_const
                 if (n0 + c * 32 >= p.N) break;            // warp-uniform
                 float v[32];
                 tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
-                epilogue_row<32>(p, g, mm, n0 + c * 32, v);
+                if (bias_gelu) epilogue_row_bias_gelu<32>(fb_bias, fb_out, fb_ldc, fb_M, mm, n0 + c * 32, v);
+                else epilogue_row<32>(p, g, mm, n0 + c * 32, v);
             }
             tc_fence_before();
             __syncwarp();
