@@ -145,6 +145,8 @@ int tap_copy(void* dst, const bf16* src, size_t elems, cudaStream_t s) {
     return SUNB_OK;
 }
 
+constexpr int SUNB_MLP_FUSED_MIN_ROWS = 6000;    // 60 images: measured break-even of the fused stage-2 MLP (tools/mlp_time.py)
+
 // stage-2/3 Block (visformer.py:259-263 with attention enabled); x is updated in place, last block may store
 // its output 2x2 space-to-depth for the following PatchEmbed.
 int attn_block(const SunbAttnBlockW& w, bf16* x, int B, int S, int C, int d, int dp, bf16* qkv, bf16* ao,
@@ -158,6 +160,10 @@ int attn_block(const SunbAttnBlockW& w, bf16* x, int B, int S, int C, int d, int
     p = base_gemm(M, C, inner, ao, inner, w.wproj, inner, x, C);
     p.resid = x; p.ldr = C;
     SUNB_TRY(sunb_launch_gemm(p, st));
+    if (C == 256 && M >= SUNB_MLP_FUSED_MIN_ROWS)
+        // stage 2: conv1 + GELU + conv3 + residual in one kernel, the 1024-wide hidden tensor stays on the SM (mlp_fused.cu).
+        // Bit-identical to the two GEMMs below; those win only on tiny batches (6 tiles of 8 serial chunks vs 4x more CTAs).
+        return sunb_mlp_fused(x, w.w1, w.b1, w.w3, s2d_out ? s2d_out : x, M, s2d_out ? 1 : 0, side, side, st);
     p = base_gemm(M, 4 * C, C, x, C, w.w1, C, hid, 4 * C);
     p.bias = w.b1; p.act = ACT_GELU;
     SUNB_TRY(sunb_launch_gemm(p, st));

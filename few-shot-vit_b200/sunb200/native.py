@@ -131,6 +131,7 @@ SIGNATURES = {
     "sunb_gconv_pack": (C.c_int, [fp, vp, C.c_int, vp]),
     "sunb_convmlp_tail": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, vp]),
     "sunb_layernorm_rows": (C.c_int, [fp, fp, fp, fp, C.c_long, C.c_int, C.c_float, vp]),
+    "sunb_mlp_fused": (C.c_int, [vp, vp, fp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "sunb_attention_backward": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "sunb_episode_logits_backward": (C.c_int, [fp, fp, fp, fp, fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                C.c_int, fp, C.c_float, vp]),

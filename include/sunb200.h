@@ -267,6 +267,13 @@ int sunb_gconv_pack(const float* w, void* dst, int transpose_flip, void* stream)
  * PatchEmbed GEMM).  The 256-channel hidden tensor between the grouped conv and conv3 never leaves the SM. */
 int sunb_convmlp_tail(const void* h1, const void* wblob, const void* resid, void* out, int B, int s2d, void* stream);
 
+/* Fused MLP of a stage-2 attention block, eval mode (visformer.py:127-163 inside Block :259-263 with BatchNorm folded into conv1):
+ *   out = x + conv3(gelu(conv1(x) + b1)),  x / out: bf16 [M, 256] (out may alias x unless s2d), w1: bf16 [1024, 256], b1: fp32
+ *   [1024], w3: bf16 [256, 1024].  s2d = 1 stores the rows 2x2 space-to-depth of an oH x oW raster (input order of the next
+ *   PatchEmbed GEMM).  The 1024-wide hidden tensor never leaves the SM. */
+int sunb_mlp_fused(const void* x, const void* w1, const float* b1, const void* w3, void* out, int M, int s2d, int oH, int oW,
+                   void* stream);
+
 /* backward of the attention core (same padded layouts as sunb_attention, tcgen05; dout: gradient of `out`; the pad channels
  * of dqkv are written as zero) and of the episode head */
 int sunb_attention_backward(const void* qkv, const void* dout, void* dqkv, int B, int S, int d, int d_stride, int heads,

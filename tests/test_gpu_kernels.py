@@ -350,3 +350,27 @@ def test_convmlp_tail_fused(B, s2d):
     ref = y.reshape(B * 400, 128)
     assert torch.isfinite(out.float()).all()
     assert rel_err(out, ref) < BF16_OUT
+
+
+@pytest.mark.parametrize("B,s2d", [(1, 0), (3, 1), (77, 0), (301, 1)])
+def test_mlp_fused(B, s2d):
+    """Fused stage-2 MLP (mlp_fused.cu): out = x + conv3(gelu(conv1(x) + b1)) vs the fp32 formula (visformer.py:127-163, 259-263)
+    and BIT-EXACT vs the two tcgen05 GEMMs it replaces; ragged last tile (B = 1, 3, 77 -> 100, 300, 7700 rows), in-place
+    update and the 2x2 space-to-depth store."""
+    M, Cc, H = B * 100, 256, 1024
+    x = rnd(M, Cc, seed=31).bfloat16()
+    w1 = (rnd(H, Cc, seed=32) * 0.06).bfloat16()
+    b1 = rnd(H, seed=33) * 0.1
+    w3 = (rnd(Cc, H, seed=34) * 0.03).bfloat16()
+    hid = run_gemm(x, w1, M, H, Cc, bias=b1, act=2)
+    two = run_gemm(hid, w3, M, Cc, H, resid=x, out_map=s2d, oHW=(10, 10))
+    xin = x.clone()
+    out = torch.full_like(x, float("nan")) if s2d else xin          # in place unless space-to-depth
+    N.check(N.lib().sunb_mlp_fused(xin.data_ptr(), w1.data_ptr(), b1.data_ptr(), w3.data_ptr(), out.data_ptr(), M, s2d, 10, 10,
+                                   N.current_stream()), "mlp_fused")
+    torch.cuda.synchronize()
+    assert torch.equal(out, two)
+    ref = x.float() + act_ref(x.float() @ w1.float().t() + b1, 2).bfloat16().float() @ w3.float().t()
+    if s2d:
+        ref = ref.reshape(B, 5, 2, 5, 2, Cc).permute(0, 1, 3, 2, 4, 5).reshape(M, Cc)
+    assert rel_err(out, ref) < BF16_OUT

@@ -30,7 +30,7 @@ LAYERS = ([("stem conv1+downsample", 16.59), ("stem conv2", 235.93), ("stem conv
                                            (f"stage1.{i} grouped 3x3 + GELU + conv3 + residual (fused)", 58.98 + 26.21))]
           + [("patch_embed2", 26.21)]
           + [x for i in range(2) for x in ((f"stage2.{i} qkv", 38.71), (f"stage2.{i} attention", 10.08), (f"stage2.{i} proj", 12.90),
-                                           (f"stage2.{i} mlp.conv1", 52.43), (f"stage2.{i} mlp.conv3", 52.43))]
+                                           (f"stage2.{i} mlp conv1 + GELU + conv3 + residual (fused)", 104.86))]
           + [("patch_embed3", 26.21)]
           + [x for i in range(3) for x in ((f"stage3.{i} qkv", 39.17), (f"stage3.{i} attention", 1.28), (f"stage3.{i} proj", 13.06),
                                            (f"stage3.{i} mlp.conv1", 52.43), (f"stage3.{i} mlp.conv3", 52.43))]
