@@ -1,9 +1,12 @@
-"""Time the attention backward cores (packed warp-MMA vs padded tcgen05) at a batch size: python tools/attb_time.py [B]"""
+"""Time the attention backward: the product's tcgen05 kernel (padded heads) and the warp-MMA cross-check kernel of the test
+library (the reference's packed heads) at a batch size: python tools/attb_time.py [B]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "few-shot-vit_b200"))
 import torch
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 from sunb200 import native as N
+from gpu_helpers import check_lib, check_call
 lib, st = N.lib(), N.current_stream()
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 480
 for S, d, ds in ((100, 42, 42), (100, 42, 48), (25, 85, 85), (25, 85, 96)):
@@ -11,7 +14,10 @@ for S, d, ds in ((100, 42, 42), (100, 42, 48), (25, 85, 85), (25, 85, 96)):
     qkv = torch.randn(B * S, ld3, device="cuda").bfloat16()
     dout = torch.randn(B * S, ldi, device="cuda").bfloat16()
     dqkv = torch.empty(B * S, ld3, device="cuda", dtype=torch.bfloat16)
-    f = lambda: N.check(lib.sunb_attention_backward(qkv.data_ptr(), dout.data_ptr(), dqkv.data_ptr(), B, S, d, ds, 6, ld3, ldi, st), "attb")
+    if ds == d:
+        f = lambda: check_call(check_lib().sunb_check_attention_backward(qkv.data_ptr(), dout.data_ptr(), dqkv.data_ptr(), B, S, d, 6, ld3, ldi, st), "check attb")
+    else:
+        f = lambda: N.check(lib.sunb_attention_backward(qkv.data_ptr(), dout.data_ptr(), dqkv.data_ptr(), B, S, d, ds, 6, ld3, ldi, st), "attb")
     for _ in range(3): f()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(); e0.record()
