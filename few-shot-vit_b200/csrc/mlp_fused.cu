@@ -214,28 +214,33 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                 __syncwarp();
                 if (lane == 0) mbar_arrive(HID_FULL);
             }
-            // ---- output: out = x + acc2, 64 columns per warp
-            mbar_wait(ACC2_FULL, lt & 1);
-            tc_fence_after();
+            // ---- output: out = x + acc2, 64 columns per warp.  The residual row is fetched BEFORE the wait for the last G2: the
+            //      global-load latency hides under it instead of sitting between two tiles on these warps' critical path.
             const int m = tile * 128 + r;
             int orow = m;
             if (s2d && m < M) {
                 const int hw = oH * oW, img = m / hw, rem = m % hw, y = rem / oW, x = rem % oW;
                 orow = ((img * (oH / 2) + y / 2) * (oW / 2) + x / 2) * 4 + (y & 1) * 2 + (x & 1);
             }
+            uint32_t rr[4][8];
+            if (m < M) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ld_global_256(resid + (size_t)m * C + part * 64 + j * 16, rr[j]);
+            }
+            mbar_wait(ACC2_FULL, lt & 1);
+            tc_fence_after();
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {
                 const int col = part * 64 + cc * 32;
                 float v[32];
                 tmem_ld32(tmem_base + lane_sel + COL_ACC2 + col, v);
                 if (m < M) {
-                    float f[16];
-                    load16_bf16(resid + (size_t)m * C + col, f);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] += f[j];
-                    load16_bf16(resid + (size_t)m * C + col + 16, f);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[16 + j] += f[j];
+                    for (int j = 0; j < 16; ++j) {
+                        const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&rr[cc * 2 + j / 8][j % 8]);
+                        v[2 * j] += __bfloat162float(h.x);
+                        v[2 * j + 1] += __bfloat162float(h.y);
+                    }
                     store16_bf16(out + (size_t)orow * C + col, v);
                     store16_bf16(out + (size_t)orow * C + col + 16, v + 16);
                 }
