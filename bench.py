@@ -43,14 +43,17 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """SM clock / throttle reasons DURING the timed region.  Primary source: one `nvidia-smi -lms 20` child process started when
+    the object is built (before the warm-up, so it is streaming by the time the region starts); its rows carry nvidia-smi's
+    own timestamps and are filtered to [enter, exit].  A Python thread polling NVML starved behind the launch loop on some
+    boxes (0 samples in a 130 ms region), a separate process does not.  Fallback: one NVML / nvidia-smi sample at exit."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         # `index` is the CUDA ordinal; NVML / nvidia-smi enumerate physical GPUs (CUDA_VISIBLE_DEVICES may remap), so the
         # device is addressed by UUID whenever torch exposes it
-        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.index, self.rows, self.raw = index, [], []
         self.uuid = None
         try:
             import torch
@@ -64,46 +67,62 @@ class ClockSampler:
                     self.uuid = ids[index]
                 elif ids[index].isdigit():
                     self.index = int(ids[index])
-        self.th = threading.Thread(target=self._run, daemon=True)
-
-    def _run(self):
-        # NVML in-process (nvidia_ml_py) samples every 20 ms; nvidia-smi (one process per sample) is the fallback
+        self.t0 = self.t1 = None
+        self.proc = None
         try:
-            import pynvml as nv
-            nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByUUID(self.uuid.encode()) if self.uuid else nv.nvmlDeviceGetHandleByIndex(self.index)
-            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            bits = ((0x8, 2), (0x40, 3), (0x20, 4), (0x4, 5))       # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap
-            while not self.stop.is_set():
-                try:
-                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                except Exception:
-                    reasons = 0
-                row = [str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx), "", "", "", ""]
-                for bit, col in bits:
-                    row[col] = "Active" if reasons & bit else "Not Active"
-                self.rows.append(row)
-                self.stop.wait(0.02)
-            return
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                          self.uuid or str(self.index), "-lms", "20"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True, bufsize=1)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        try:
+            for line in self.proc.stdout:
+                self.raw.append(line)
         except Exception:
             pass
-        while not self.stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                      self.uuid or str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            self.stop.wait(0.2)
+
+    @staticmethod
+    def _stamp(text):
+        import datetime
+        try:
+            return datetime.datetime.strptime(text.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except Exception:
+            return None
+
+    def _sample_once(self):
+        try:
+            out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                  self.uuid or str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+            if out:
+                self.rows.append([c.strip() for c in out.split(",")][1:])
+        except Exception:
+            pass
 
     def __enter__(self):
-        self.th.start()
+        self.t0 = time.time()
         return self
 
     def __exit__(self, *a):
-        self.stop.set()
-        self.th.join(timeout=5)
+        self.t1 = time.time()
+        if self.proc is not None:
+            time.sleep(0.06)                       # let the rows stamped inside the region reach the pipe
+            try:
+                self.proc.terminate()
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+            self.th.join(timeout=2)
+            for line in self.raw:
+                cols = [c.strip() for c in line.split(",")]
+                ts = self._stamp(cols[0]) if cols else None
+                if ts is not None and self.t0 - 0.005 <= ts <= self.t1 + 0.005 and len(cols) >= 7:
+                    self.rows.append(cols[1:])
+        if not self.rows:                          # nothing landed inside the region: one sample now, the GPU is still loaded
+            self._sample_once()
 
     def summary(self):
         sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
@@ -697,9 +716,10 @@ def run_product(args):
     use_graph = os.environ.get("SUNB_EVAL_GRAPH", "0") == "1" and not profile_mode
     launch_mode = "eager"
     with torch.no_grad():
+        clk = ClockSampler(local)                                      # starts streaming now, filtered to the timed region below
         for _ in range(max(args.warmup, 3)):
             outs = step_device()
-        with ClockSampler(local) as clk:
+        with clk:
             ms_eager = timed(step_device, args.steps)
         clocks = clk.summary()
         ms_total = ms_eager
