@@ -23,6 +23,14 @@
 #include "tc_common.cuh"
 #include "../../include/sunb200.h"
 
+#ifdef SUNB_TAIL_TRACE
+// developer build only (tools/build_variants.sh trace): clock64 stamps of CTA 0's third work item, read by tools/tail_trace.py
+__device__ long long g_tail_trace[16][12];          // [group 0..7, 8 = epilogue][event]
+#define TTRACE(g, ev) do { if (blockIdx.x == 0 && it == 2 && lane == 0) g_tail_trace[g][ev] = clock64(); } while (0)
+#else
+#define TTRACE(g, ev) do { } while (0)
+#endif
+
 namespace {
 
 using namespace tc;
@@ -165,10 +173,13 @@ convmlp_tail_kernel(const __grid_constant__ CUtensorMap tmH, const uint8_t* __re
             for (int g = 0; g < 8; ++g) {
                 const int pr = it * 8 + g, pb = pr & 1, k = pr >> 1, s2 = pr % NW2;
                 const int an = it * 4 + (g >> 1), as = an % NA;
+                TTRACE(g, 0);
                 if ((g & 1) == 0) mbar_wait(ATOM_FULL(as), (an / NA) & 1);
+                TTRACE(g, 1);
                 mbar_wait(W2_FULL(s2), (pr / NW2) & 1);
                 mbar_wait(D2_EMPTY(pb), (k & 1) ^ 1);
                 tc_fence_after();
+                TTRACE(g, 2);
                 const uint32_t a_sm = base + A_OFF + as * ATOM_BYTES + (g & 1) * 64;
                 const uint32_t b_sm = base + W2_OFF + s2 * W2_BYTES;
                 const uint32_t d0 = tmem_base + D2_COL + pb * 64;
@@ -188,6 +199,7 @@ convmlp_tail_kernel(const __grid_constant__ CUtensorMap tmH, const uint8_t* __re
                     if (g & 1) umma_commit(ATOM_EMPTY(as));
                 }
                 __syncwarp();
+                TTRACE(g, 3);
             }
         }
     } else if (warp == 3) {
@@ -196,10 +208,12 @@ convmlp_tail_kernel(const __grid_constant__ CUtensorMap tmH, const uint8_t* __re
         for (int it = 0; it < n_items; ++it) {
             for (int g = 0; g < 8; ++g) {
                 const int pr = it * 8 + g, pb = pr & 1, k = pr >> 1, s3 = pr % NW3;
+                TTRACE(g, 4);
                 if (g == 0) mbar_wait(D3_EMPTY(0), (it & 1) ^ 1);
                 mbar_wait(W3_FULL(s3), (pr / NW3) & 1);
                 mbar_wait(H2_FULL(pb), k & 1);
                 tc_fence_after();
+                TTRACE(g, 5);
                 const uint32_t b_sm = base + W3_OFF + s3 * W3_BYTES;
                 if (elect_one()) {
 #pragma unroll
@@ -216,6 +230,7 @@ convmlp_tail_kernel(const __grid_constant__ CUtensorMap tmH, const uint8_t* __re
                     if (g == 7) umma_commit(D3_FULL(0));
                 }
                 __syncwarp();
+                TTRACE(g, 6);
             }
         }
     } else if (warp >= 4 && warp < 20) {
@@ -227,8 +242,16 @@ convmlp_tail_kernel(const __grid_constant__ CUtensorMap tmH, const uint8_t* __re
         const int pairs = n_items * 8;
         for (int pr = pb; pr < pairs; pr += 2) {
             const int k = pr >> 1;
+#ifdef SUNB_TAIL_TRACE
+            const int it = pr >> 3;
+            const bool tr = (warp == 4 || warp == 12);
+            if (tr) TTRACE(pr & 7, 7);
+#endif
             mbar_wait(D2_FULL(pb), k & 1);
             tc_fence_after();
+#ifdef SUNB_TAIL_TRACE
+            if (tr) TTRACE(pr & 7, 8);
+#endif
             float v[32];
             tmem_ld32(tmem_base + lane_sel + D2_COL + pb * 64 + t * 32, v);
             tc_fence_before();
@@ -246,6 +269,9 @@ convmlp_tail_kernel(const __grid_constant__ CUtensorMap tmH, const uint8_t* __re
             fence_async_proxy();
             __syncwarp();
             if (lane == 0) mbar_arrive(H2_FULL(pb));
+#ifdef SUNB_TAIL_TRACE
+            if (tr) TTRACE(pr & 7, 9);
+#endif
         }
     } else if (warp >= 20) {
         // ================================================================ conv3 epilogue: + residual, bf16, store.  Warp (q, half)
@@ -273,8 +299,10 @@ convmlp_tail_kernel(const __grid_constant__ CUtensorMap tmH, const uint8_t* __re
             }
             uint32_t rb[8];
             if (valid[0]) ld_global_256(resid + (size_t)mrow[0] * 128 + half * 64, rb);
+            if (warp == 20) TTRACE(8, 0);
             mbar_wait(D3_FULL(0), it & 1);
             tc_fence_after();
+            if (warp == 20) TTRACE(8, 1);
 #pragma unroll
             for (int step = 0; step < 8; ++step) {
                 const int t = step >> 2, col = half * 64 + (step & 3) * 16;
@@ -302,6 +330,7 @@ convmlp_tail_kernel(const __grid_constant__ CUtensorMap tmH, const uint8_t* __re
 #pragma unroll
                 for (int j = 0; j < 8; ++j) rb[j] = rn[j];
             }
+            if (warp == 20) TTRACE(8, 2);
         }
     }
 
@@ -314,6 +343,12 @@ convmlp_tail_kernel(const __grid_constant__ CUtensorMap tmH, const uint8_t* __re
 }
 
 }  // namespace
+
+#ifdef SUNB_TAIL_TRACE
+extern "C" int sunb_tail_trace_read(long long* dst) {
+    return cudaMemcpyFromSymbol(dst, g_tail_trace, sizeof(g_tail_trace)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 extern "C" int sunb_convmlp_tail(const void* h1, const void* wblob, const void* resid, void* out, int B, int s2d, void* stream) {
     SUNB_REQUIRE(h1 && wblob && resid && out && B > 0, "convmlp_tail: bad arguments");
