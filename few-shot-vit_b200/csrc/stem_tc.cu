@@ -56,6 +56,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 }
 
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {   // bounded: a broken pipeline traps instead of hanging
+    if (mbar_try_wait(bar, parity)) return;     // fast path: no clock read (CS2R costs ~100+ cycles on the issuer's serial path)
     const long long t0 = clock64();
     for (;;) {
 #pragma unroll 1

@@ -44,6 +44,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     // try_wait suspends in hardware; the watchdog (a broken pipeline traps instead of hanging the GPU) is only
     // consulted every 4096 failed polls so the spin loop stays two instructions long
+    if (mbar_try_wait(bar, parity)) return;     // fast path: no clock read (CS2R costs ~100+ cycles on the issuer's serial path)
     const long long t0 = clock64();
     for (;;) {
 #pragma unroll 1
