@@ -122,3 +122,32 @@ def test_c_abi_exports_every_declared_symbol():
     # struct layouts mirror the header (sizes are what the C compiler produces for these field lists)
     assert ctypes.sizeof(N.ConvMlpW) == 40 and ctypes.sizeof(N.AttnBlockW) == 48
     assert ctypes.sizeof(N.EncoderWeights) == 9 * 8 + 4 * 40 + 16 + 2 * 48 + 16 + 3 * 48 + 16
+
+
+def test_every_pdl_launched_kernel_waits_for_its_predecessor():
+    """Launch protocol (csrc/common.cuh): a kernel launched through sunb_launch carries the programmatic-dependent-launch
+    attribute, so it MUST execute griddepcontrol.wait (pdl_wait) before its first global access; a kernel without the wait
+    would race with the previous kernel of the stream.  Source-level audit of csrc/*.cu."""
+    import glob
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "few-shot-vit_b200", "csrc")
+    sources = {f: open(f).read() for f in glob.glob(os.path.join(csrc, "*.cu"))}
+    launched = {(f, m.group(1)) for f, s in sources.items() for m in re.finditer(r"sunb_launch\(&([A-Za-z_0-9]+)", s)}
+    assert len(launched) >= 30
+    for f, name in sorted(launched):
+        s = sources[f]
+        m = re.search(r"__global__[^;{]*?\b" + name + r"\s*\(", s, re.S)
+        assert m, f"{name}: kernel definition not found in {os.path.basename(f)}"
+        i, depth = m.end() - 1, 0
+        while True:                                   # end of the parameter list
+            depth += s[i] == "("
+            depth -= s[i] == ")"
+            if depth == 0:
+                break
+            i += 1
+        body_start = s.index("{", i)
+        nxt = s.find("__global__", body_start)
+        body = s[body_start: nxt if nxt > 0 else len(s)]
+        w = body.find("pdl_wait()")
+        assert w >= 0, f"{name} is launched with the PDL attribute but never calls pdl_wait()"
+        pre = body[:w]
+        assert "__ldg" not in pre and "ld_global" not in pre and "tma_load" not in pre, f"{name}: global access before pdl_wait()"
