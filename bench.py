@@ -710,8 +710,8 @@ def run_product(args):
             torch.cuda.synchronize()
             return None
 
-    # Graph replay of the whole eval step measured SLOWER than stream launches at this size (r02c: 30.9 vs 29.5 ms per step:
-    # the 48 launches per chunk are ~200 us each and the host runs ahead), so it is opt-in; the single-episode latency
+    # Graph replay of the whole eval step measured SLOWER than stream launches at this size (round 1: 30.9 vs 29.5 ms per step:
+    # the ~40 launches per chunk are ~200 us each and the host runs ahead), so it is opt-in; the single-episode latency
     # probe below shows where graphs pay (0.82 -> 0.69 ms).
     use_graph = os.environ.get("SUNB_EVAL_GRAPH", "0") == "1" and not profile_mode
     launch_mode = "eager"
@@ -725,7 +725,7 @@ def run_product(args):
         ms_total = ms_eager
         step_fn = step_device
         if use_graph:
-            # the whole step (split_shot_query + MetaBaseline forward of every chunk, 48 launches per chunk) as ONE graph:
+            # the whole step (split_shot_query + MetaBaseline forward of every chunk, 38 launches per chunk) as ONE graph:
             # the library's launches are stream-ordered and allocation-free apart from torch's caching allocator
             cap = capture(step_device)
             if cap is not None:

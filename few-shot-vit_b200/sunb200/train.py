@@ -3,8 +3,10 @@
 Schedule of the SUN-M meta-tuning step's device work (reference: meta_tuning_sun_m/train_meta.py:168-174 driving
 autograd through test_phase/models/visformer.py).  Every device operation is a libsunb200 entry point
 (include/sunb200.h): sunb_gemm (forward convs, dgrads with the activation derivative fused into the epilogue),
-sunb_wgrad (tcgen05 weight gradients), sunb_attention(+_backward), and the BatchNorm / stem-tail / helper kernels.
-torch is used to allocate buffers and for views/permutes of small gradient tensors.
+sunb_wgrad (tcgen05 weight gradients), sunb_attention(+_backward) on the padded head layout (tcgen05 forward and backward),
+sunb_pack_weights (all bf16 operand layouts of a step in one launch) and the BatchNorm / stem-tail / helper kernels.
+torch is used to allocate buffers and for views/permutes of small gradient tensors.  Weight gradients run on a second stream
+(on_wgrad_stream) next to the dgrad / BatchNorm chain; every kernel is launched with programmatic dependent launch.
 
 Semantics kept from the reference: BN statistics over the whole concatenated batch, biased variance
 for normalisation / unbiased for the running stats with momentum 0.1, DropPath as a per-sample scale mask/keep drawn
