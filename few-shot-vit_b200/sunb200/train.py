@@ -103,6 +103,53 @@ def head_dims(dim):
     return d, (48 if d <= 48 else 96)
 
 
+def weight_pack_plan(P):
+    """Pure host description of every bf16 operand copy of a training step: a list of
+    (key, source parameter, dims[4], source strides[4], source offset, padded last dim, row length of the 2-D view, valid2)
+    with  dst[a][b][c][d] = src.flat[off + a*s0 + b*s1 + c*s2 + d*s3]  for d < dims[3] (and c < valid2 if valid2), else 0.
+    `.f` = forward operand, `.d` = data-gradient operand (transposed, taps mirrored).  tests/test_host_logic.py emulates it."""
+    plan = []                                   # (key, src, dims4, strides4, off, ldd, row length of the 2-D view)
+
+    def add(key, src, dims, strides, off=0, ldd=None, cols=None, valid2=0):
+        dims, strides = tuple(dims), tuple(strides)
+        while len(dims) < 4:                    # leading unit dims
+            dims, strides = (1,) + dims, (0,) + strides
+        plan.append((key, src, dims, strides, off, ldd or dims[3], cols or ldd or dims[3], valid2))
+
+    for name, cin, cout in (("stem.conv2", 64, 128), ("stem.conv3", 128, 128)):
+        w = P[name + ".weight"]
+        add(name + ".f", w, (9, cout, cin), (1, cin * 9, 9))                          # [tap][n][c]
+        add(name + ".d", w, (9, cin, cout), (-1, 9, cin * 9), off=8)                   # [tap][c][n], taps mirrored
+    for i in range(DEPTH[0]):
+        b = f"stage1.{i}.mlp."
+        add(b + "conv1.f", P[b + "conv1.weight"], (256, 128), (128, 1))
+        add(b + "conv1.d", P[b + "conv1.weight"], (128, 256), (1, 128))
+        add(b + "conv3.f", P[b + "conv3.weight"], (128, 256), (256, 1))
+        add(b + "conv3.d", P[b + "conv3.weight"], (256, 128), (1, 256))
+        # grouped [256][32][3][3] -> [8 groups][9 taps][32 n][32 k]; the dgrad copy swaps n / k and mirrors the taps
+        add(b + "conv2.f", P[b + "conv2.weight"], (8, 9, 32, 32), (32 * 288, 1, 288, 9))
+        add(b + "conv2.d", P[b + "conv2.weight"], (8, 9, 32, 32), (32 * 288, -1, 9, 288), off=8)
+    for stage, cin, dim, depth in (("2", 128, 256, DEPTH[1]), ("3", 256, 512, DEPTH[2])):
+        w = P[f"patch_embed{stage}.proj.weight"]
+        add(f"pe{stage}.f", w, (dim, 4, cin), (cin * 4, 1, 4), cols=4 * cin)          # [n][(tap,c)]
+        add(f"pe{stage}.d", w, (4, cin, dim), (1, 4, cin * 4))                        # [(tap,c)][n]
+        d, ds = head_dims(dim)
+        inner = HEADS * d
+        for i in range(depth):
+            b = f"stage{stage}.{i}."
+            # heads padded from d to ds channels (zero weights): the tcgen05 attention kernels' layout
+            wq, wp = P[b + "attn.qkv.weight"], P[b + "attn.proj.weight"]
+            add(b + "qkv.f", wq, (3 * HEADS, ds, dim), (d * dim, dim, 1), valid2=d)          # [(x,y)][z][c]
+            add(b + "qkv.d", wq, (dim, 3 * HEADS, d), (1, d * dim, dim), ldd=ds, cols=3 * HEADS * ds)   # [c][(x,y)][z]
+            add(b + "proj.f", wp, (dim, HEADS, d), (inner, d, 1), ldd=ds, cols=HEADS * ds)     # [n][y][z]
+            add(b + "proj.d", wp, (HEADS, ds, dim), (d, 1, inner), valid2=d)                    # [y][z][n]
+            add(b + "conv1.f", P[b + "mlp.conv1.weight"], (4 * dim, dim), (dim, 1))
+            add(b + "conv1.d", P[b + "mlp.conv1.weight"], (dim, 4 * dim), (1, dim))
+            add(b + "conv3.f", P[b + "mlp.conv3.weight"], (dim, 4 * dim), (4 * dim, 1))
+            add(b + "conv3.d", P[b + "mlp.conv3.weight"], (4 * dim, dim), (1, 4 * dim))
+    return plan
+
+
 class BNRec:
     """Per-layer BatchNorm record: statistics of this step and the tensors the backward needs."""
     __slots__ = ("name", "C", "count", "buf", "x", "frozen")
@@ -226,45 +273,7 @@ class TrainEngine:
         return W
 
     def _plan_weight_pack(self, P):
-        plan = []                                   # (key, src, dims4, strides4, off, ldd, row length of the 2-D view)
-
-        def add(key, src, dims, strides, off=0, ldd=None, cols=None, valid2=0):
-            dims, strides = tuple(dims), tuple(strides)
-            while len(dims) < 4:                    # leading unit dims
-                dims, strides = (1,) + dims, (0,) + strides
-            plan.append((key, src, dims, strides, off, ldd or dims[3], cols or ldd or dims[3], valid2))
-
-        for name, cin, cout in (("stem.conv2", 64, 128), ("stem.conv3", 128, 128)):
-            w = P[name + ".weight"]
-            add(name + ".f", w, (9, cout, cin), (1, cin * 9, 9))                          # [tap][n][c]
-            add(name + ".d", w, (9, cin, cout), (-1, 9, cin * 9), off=8)                   # [tap][c][n], taps mirrored
-        for i in range(DEPTH[0]):
-            b = f"stage1.{i}.mlp."
-            add(b + "conv1.f", P[b + "conv1.weight"], (256, 128), (128, 1))
-            add(b + "conv1.d", P[b + "conv1.weight"], (128, 256), (1, 128))
-            add(b + "conv3.f", P[b + "conv3.weight"], (128, 256), (256, 1))
-            add(b + "conv3.d", P[b + "conv3.weight"], (256, 128), (1, 256))
-            # grouped [256][32][3][3] -> [8 groups][9 taps][32 n][32 k]; the dgrad copy swaps n / k and mirrors the taps
-            add(b + "conv2.f", P[b + "conv2.weight"], (8, 9, 32, 32), (32 * 288, 1, 288, 9))
-            add(b + "conv2.d", P[b + "conv2.weight"], (8, 9, 32, 32), (32 * 288, -1, 9, 288), off=8)
-        for stage, cin, dim, depth in (("2", 128, 256, DEPTH[1]), ("3", 256, 512, DEPTH[2])):
-            w = P[f"patch_embed{stage}.proj.weight"]
-            add(f"pe{stage}.f", w, (dim, 4, cin), (cin * 4, 1, 4), cols=4 * cin)          # [n][(tap,c)]
-            add(f"pe{stage}.d", w, (4, cin, dim), (1, 4, cin * 4))                        # [(tap,c)][n]
-            d, ds = head_dims(dim)
-            inner = HEADS * d
-            for i in range(depth):
-                b = f"stage{stage}.{i}."
-                # heads padded from d to ds channels (zero weights): the tcgen05 attention kernels' layout
-                wq, wp = P[b + "attn.qkv.weight"], P[b + "attn.proj.weight"]
-                add(b + "qkv.f", wq, (3 * HEADS, ds, dim), (d * dim, dim, 1), valid2=d)          # [(x,y)][z][c]
-                add(b + "qkv.d", wq, (dim, 3 * HEADS, d), (1, d * dim, dim), ldd=ds, cols=3 * HEADS * ds)   # [c][(x,y)][z]
-                add(b + "proj.f", wp, (dim, HEADS, d), (inner, d, 1), ldd=ds, cols=HEADS * ds)     # [n][y][z]
-                add(b + "proj.d", wp, (HEADS, ds, dim), (d, 1, inner), valid2=d)                    # [y][z][n]
-                add(b + "conv1.f", P[b + "mlp.conv1.weight"], (4 * dim, dim), (dim, 1))
-                add(b + "conv1.d", P[b + "mlp.conv1.weight"], (dim, 4 * dim), (1, dim))
-                add(b + "conv3.f", P[b + "mlp.conv3.weight"], (dim, 4 * dim), (4 * dim, 1))
-                add(b + "conv3.d", P[b + "mlp.conv3.weight"], (4 * dim, dim), (1, 4 * dim))
+        plan = weight_pack_plan(P)
         sizes = [(dm[0] * dm[1] * dm[2] * ldd + 127) // 128 * 128 for _, _, dm, _, _, ldd, _, _ in plan]  # 256-byte aligned
         buf = torch.empty(sum(sizes), dtype=torch.bfloat16, device=self.dev)
         descs = (N.PackDesc * len(plan))()

@@ -151,3 +151,62 @@ def test_every_pdl_launched_kernel_waits_for_its_predecessor():
         assert w >= 0, f"{name} is launched with the PDL attribute but never calls pdl_wait()"
         pre = body[:w]
         assert "__ldg" not in pre and "ld_global" not in pre and "tma_load" not in pre, f"{name}: global access before pdl_wait()"
+
+
+def _emulate_pack(entry):
+    """Reference semantics of one SunbPackDesc (include/sunb200.h): gather with strides, zero padding."""
+    key, src, dims, strides, off, ldd, cols, valid2 = entry
+    flat = src.detach().reshape(-1)
+    a, b, c, d = (torch.arange(n) for n in dims)
+    idx = (off + a[:, None, None, None] * strides[0] + b[None, :, None, None] * strides[1] + c[None, None, :, None] * strides[2]
+           + d[None, None, None, :] * strides[3])
+    out = torch.zeros(dims[0], dims[1], dims[2], ldd)
+    c_ok = dims[2] if not valid2 else valid2                          # the kernel never reads the source for c >= valid2
+    assert int(idx[:, :, :c_ok].min()) >= 0 and int(idx[:, :, :c_ok].max()) < flat.numel(), f"{key}: plan reads out of bounds"
+    out[:, :, :c_ok, : dims[3]] = flat[idx[:, :, :c_ok]]
+    return out.reshape(-1, cols)
+
+
+def test_weight_pack_plan_layouts():
+    """The table that drives sunb_pack_weights (train.py::weight_pack_plan) produces, for every GEMM / conv weight, the forward
+    operand [N][K] and the data-gradient operand [K][N] the kernels expect: taps mirrored for 3x3 dgrads, grouped weights as
+    [group][tap][n][k], heads padded from d to 48 / 96 channels with zero rows / columns (reference shapes: visformer.py:146-194)."""
+    from sunb200 import train as T
+    g = torch.Generator().manual_seed(5)
+    sd = O.init_meta_baseline_state_dict(12345)
+    P = {k[len("encoder."):]: torch.randn(v.shape, generator=g) for k, v in sd.items()
+         if k.startswith("encoder.") and v.dtype == torch.float32 and v.dim() >= 2}
+    plan = {e[0]: e for e in T.weight_pack_plan(P)}
+    assert len(plan) == 72
+    got = {k: _emulate_pack(e) for k, e in plan.items()}
+    # dense 3x3: forward [tap][n][c]; dgrad = transposed conv: [tap'][c][n] with tap' = 8 - tap
+    w = P["stem.conv3.weight"]                                        # [n, c, 3, 3]
+    assert torch.equal(got["stem.conv3.f"], w.permute(2, 3, 0, 1).reshape(9 * 128, 128))
+    assert torch.equal(got["stem.conv3.d"], w.flip(2, 3).permute(2, 3, 1, 0).reshape(9 * 128, 128))
+    w = P["stem.conv2.weight"]
+    assert torch.equal(got["stem.conv2.d"], w.flip(2, 3).permute(2, 3, 1, 0).reshape(9 * 64, 128))
+    # 1x1 convs: forward = the weight matrix, dgrad = its transpose
+    w = P["stage1.0.mlp.conv1.weight"].reshape(256, 128)
+    assert torch.equal(got["stage1.0.mlp.conv1.f"], w) and torch.equal(got["stage1.0.mlp.conv1.d"], w.t())
+    w = P["stage3.2.mlp.conv3.weight"].reshape(512, 2048)
+    assert torch.equal(got["stage3.2.conv3.f"], w) and torch.equal(got["stage3.2.conv3.d"], w.t())
+    # grouped 3x3 [256, 32, 3, 3] -> [group][tap][n][k]; dgrad swaps n / k and mirrors the taps
+    w = P["stage1.1.mlp.conv2.weight"].reshape(8, 32, 32, 9)          # [group, n, k, tap]
+    assert torch.equal(got["stage1.1.mlp.conv2.f"], w.permute(0, 3, 1, 2).reshape(-1, 32))
+    assert torch.equal(got["stage1.1.mlp.conv2.d"], w.flip(3).permute(0, 3, 2, 1).reshape(-1, 32))
+    # PatchEmbed 2x2 stride 2: forward [n][(tap, c)], dgrad [(tap, c)][n]
+    w = P["patch_embed2.proj.weight"]                                 # [256, 128, 2, 2]
+    assert torch.equal(got["pe2.f"], w.permute(0, 2, 3, 1).reshape(256, 512))
+    assert torch.equal(got["pe2.d"], w.permute(2, 3, 1, 0).reshape(512, 256))
+    # attention: heads padded d -> ds with zeros
+    for stage, dim, d, ds in (("2", 256, 42, 48), ("3", 512, 85, 96)):
+        wq = P[f"stage{stage}.0.attn.qkv.weight"].reshape(18, d, dim)
+        pad = torch.zeros(18, ds, dim)
+        pad[:, :d] = wq
+        assert torch.equal(got[f"stage{stage}.0.qkv.f"], pad.reshape(18 * ds, dim))
+        assert torch.equal(got[f"stage{stage}.0.qkv.d"], pad.reshape(18 * ds, dim).t())
+        wp = P[f"stage{stage}.0.attn.proj.weight"].reshape(dim, 6, d)
+        padp = torch.zeros(dim, 6, ds)
+        padp[:, :, :d] = wp
+        assert torch.equal(got[f"stage{stage}.0.proj.f"], padp.reshape(dim, 6 * ds))
+        assert torch.equal(got[f"stage{stage}.0.proj.d"], padp.reshape(dim, 6 * ds).t())
